@@ -1,0 +1,168 @@
+/* sysid_b200.h -- C ABI of the B200-native inertial-identification hot path.
+ *
+ * Drop-in boundary for xiaohu97/system_identification (reference, pure Python).  The reference has
+ * no FFI layer of its own; the native code its hot path reaches lives in third-party libraries.
+ * Each entry point below names the reference call site(s) it replaces:
+ *
+ *   sysid_model_create        pin.buildModelFromUrdf(path, JointModelFreeFlyer()) + gravity + foot frame ids
+ *                             reference src/sys_identification.py:16,22,51-54  (host flattens the URDF; this uploads it)
+ *   sysid_regressor_batch     pin.computeJointTorqueRegressor(model, data, q, dq, ddq)
+ *                             reference src/sys_identification.py:395,406
+ *   sysid_projected_batch     get_proj_regressor_torque + get_proj_friction_regressors
+ *                             (_update_fk, _compute_J_c, _compute_null_space_proj = I - pinv(J_c) J_c, P@Y, P@S^T@tau,
+ *                             P@S^T@diag(dq), P@S^T@diag(sign dq))   reference src/sys_identification.py:113-135,401-418
+ *   sysid_gram_accumulate     the demo stacking loops + the normal equations MOSEK forms internally:
+ *                             reference demo/solo_identification.py:36-55,79-84 and src/solver.py:186-190
+ *   sysid_gram_from_stack     same statistics from an already stacked (rows x c) matrix, for callers that built
+ *                             Y_proj/B_v/B_c through the per-sample API and hand them to Solver(...)  src/solver.py:6-29
+ *   sysid_sdp_solve           Solver.solve_fully_consistent: cvxpy problem + problem.solve(solver=cp.MOSEK)
+ *                             reference src/solver.py:123-210
+ *   sysid_predict_rmse        SystemIdentification.print_tau_prediction_rmse   reference src/sys_identification.py:421-437
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / CUDA types in signatures (stream is a void* cudaStream_t).
+ *   - Every data pointer is a DEVICE pointer unless its name ends in _host.  The caller owns all buffers; the
+ *     library owns only the immutable model handle.  No hidden allocation on the hot path: scratch is passed in
+ *     (sysid_gram_workspace_bytes / sysid_sdp_workspace_bytes).
+ *   - Sample arrays are CHANNEL-MAJOR exactly as the reference's read_data returns them
+ *     (demo/solo_identification.py:9-33): q (nq x N), dq (nv x N), ddq (nv x N), tau (d x N), contact (n_ee x N),
+ *     fp64, element (ch, i) at base[ch * ld + i].
+ *   - All calls are asynchronous on the given stream.  Return value: 0 = ok, negative = sysid_status.
+ *     Never throws across the ABI; sysid_last_error() returns a thread-local message.
+ *   - A model handle is immutable after creation and may be shared by threads/streams.
+ */
+#ifndef SYSID_B200_H
+#define SYSID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SYSID_ABI_VERSION 1
+
+typedef enum sysid_status {
+    SYSID_OK = 0,
+    SYSID_ERR_INVALID = -1,      /* null pointer, bad size, malformed tree */
+    SYSID_ERR_UNSUPPORTED = -2,  /* tree outside the compiled kernel envelope (see sysid_limits) */
+    SYSID_ERR_CUDA = -3,         /* a CUDA runtime call failed; message has the cudaError string */
+    SYSID_ERR_NOT_OPTIMAL = -4,  /* SDP did not reach tolerance ("The problem did not solve to optimality.") */
+    SYSID_ERR_WORKSPACE = -5     /* workspace too small */
+} sysid_status;
+
+enum { SYSID_JT_FREEFLYER = 0, SYSID_JT_RX = 1, SYSID_JT_RY = 2, SYSID_JT_RZ = 3, SYSID_JT_RU = 4 };
+
+/* Flat kinematic tree in pinocchio's joint numbering: index 0 = universe, 1 = free-flyer root_joint,
+ * 2.. = revolute joints (depth-first, children by joint name).  All pointers are HOST pointers. */
+typedef struct sysid_tree_desc {
+    int32_t njoints;            /* including the universe */
+    int32_t n_ee;               /* number of end-effector (foot) frames, in contact-channel order */
+    const int32_t* parent;      /* [njoints] */
+    const int32_t* jtype;       /* [njoints] SYSID_JT_*; entry 0 ignored */
+    const double* axis;         /* [njoints*3] unit axis in the joint frame (used for SYSID_JT_RU) */
+    const double* place_R;      /* [njoints*9] row-major rotation of the joint placement in the parent joint frame */
+    const double* place_p;      /* [njoints*3] translation of the joint placement */
+    const int32_t* ee_joint;    /* [n_ee] joint each foot frame is rigidly attached to */
+    const double* ee_offset;    /* [n_ee*3] foot point in that joint's frame */
+    double gravity[3];          /* linear gravity, reference uses (0, 0, -9.81) */
+} sysid_tree_desc;
+
+typedef struct sysid_model sysid_model;   /* opaque */
+
+typedef struct sysid_dims {
+    int32_t nq, nv, nbodies, ndof;        /* ndof = actuated joints d = nv - 6 */
+    int32_t nparams;                      /* 10 * nbodies */
+    int32_t ncols;                        /* nparams + 2 * ndof (with friction columns) */
+    int32_t n_ee;
+} sysid_dims;
+
+/* Compile-time envelope of the kernels in this build. */
+typedef struct sysid_limits {
+    int32_t max_bodies, max_nv, max_ee, max_depth, max_cols_padded;
+} sysid_limits;
+
+int sysid_abi_version(void);
+const char* sysid_last_error(void);
+void sysid_get_limits(sysid_limits* out);
+
+int sysid_model_create(const sysid_tree_desc* desc, sysid_model** out);
+void sysid_model_destroy(sysid_model* model);
+int sysid_model_dims(const sysid_model* model, sysid_dims* out);
+
+/* Y_out: N x nv x nparams row-major, pinocchio column order per body [m, mcx,mcy,mcz, Ixx,Ixy,Iyy,Ixz,Iyz,Izz]. */
+int sysid_regressor_batch(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                          int64_t N, int64_t ld, double* Y_out, void* stream);
+
+/* A_out: N x nv x ncols row-major = P [Y | S^T diag(dq_j) | S^T diag(sign dq_j)]  (ncols = nparams + 2 ndof when
+ * friction != 0, else nparams);  b_out: N x nv = P S^T tau;  P_out (nullable): N x nv x nv.
+ * Contact rule: foot k is in stance iff contact[k] != 0 (reference quirk: state 2 counts). */
+int sysid_projected_batch(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                          const double* tau, const double* contact, int64_t N, int64_t ld, int32_t friction,
+                          double* A_out, double* b_out, double* P_out, void* stream);
+
+/* Sufficient statistics of the stacked least-squares system, never materialising the stack.
+ * stats layout (fp64, c = ncols as above):  G (c x c, row-major, full symmetric) | r (c) | s (1) | n (1)
+ *   G = sum_i A_i^T A_i,  r = sum_i A_i^T b_i,  s = sum_i b_i^T b_i,  n = nv * N (rows of the stack, reference quirk Q4).
+ * The call ADDS into stats (zero it first for a fresh accumulation), so shards/chunks can be streamed.
+ * weights (nullable): per-sample non-negative weights w_i (bootstrap multiplicities); then n += nv * sum_i w_i.
+ * info (nullable, device, 2 x int64): [0] += samples whose contact Jacobian lost rank (a dependent row was dropped),
+ *                                     [1] += samples with a non-finite input (skipped). */
+size_t sysid_stats_len(const sysid_model* model, int32_t friction);           /* doubles in stats */
+size_t sysid_gram_workspace_bytes(const sysid_model* model);
+int sysid_gram_accumulate(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                          const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
+                          int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* Same statistics from a stacked matrix A (rows x c, row-major, device) and vector b (rows). */
+int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,
+                          void* workspace, size_t workspace_bytes, void* stream);
+size_t sysid_gram_from_stack_workspace_bytes(int32_t c);
+
+/* LMI-constrained fit (reference src/solver.py:123-210).  All pointers in the desc are HOST pointers. */
+enum { SYSID_REG_CONSTANT_PULLBACK = 0, SYSID_REG_EUCLIDEAN = 1 };
+typedef struct sysid_sdp_desc {
+    int32_t num_links;            /* L */
+    int32_t ndof;                 /* friction coefficients per kind (0 = no friction identification) */
+    const double* phi_prior;      /* [10 L] reference order [m, hx,hy,hz, Ixx,Ixy,Ixz,Iyy,Iyz,Izz]; float32 values widened */
+    const double* semi_axes;      /* [3 L] bounding-ellipsoid semi axes */
+    const double* centers;        /* [3 L] bounding-ellipsoid centres */
+    double total_mass;
+    double lambda_reg;            /* reference default 1e-1 */
+    int32_t reg_type;             /* SYSID_REG_* */
+    double epsilon;               /* LMI margin, reference 1e-6 */
+    double tol;                   /* reference default 1e-10 (MOSEK rel-gap); here the ADMM residual tolerance scale */
+    int32_t max_iters;            /* ADMM iteration cap (0 = library default) */
+} sysid_sdp_desc;
+
+typedef struct sysid_sdp_info {
+    int32_t status;               /* 0 optimal, SYSID_ERR_NOT_OPTIMAL otherwise */
+    int32_t iterations;
+    int32_t refactorizations;
+    int32_t reserved;
+    double primal_residual, dual_residual, rho, objective;
+    double min_eig_J, min_eig_C;  /* smallest eigenvalue over links of J+eps I and C+eps I at the solution */
+    double mass_residual;
+} sysid_sdp_info;
+
+size_t sysid_sdp_workspace_bytes(int32_t num_links, int32_t ndof);
+/* stats: device, layout above with c = 10 L + 2 ndof.  x_out: device, c doubles [phi | b_v | b_c].
+ * info_out: device, one sysid_sdp_info per problem.  batch >= 1 solves `batch` independent problems whose stats are
+ * stats + k * stats_stride (same priors/ellipsoids), one thread block each. */
+int sysid_sdp_solve(const sysid_sdp_desc* desc, const double* stats, int64_t stats_stride, int32_t batch,
+                    double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* tau-prediction error of phi (nparams, multiplies the pinocchio-ordered regressor as is -- reference quirk Q1):
+ * out (device): [0] = mean_i ||e_i||^2 (the reference's "total", no root), [1..ndof] = per-joint RMSE,
+ * with e_i = (P Y phi)[6:] - (P S^T tau)[6:]. */
+int sysid_predict_rmse(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                       const double* tau, const double* contact, int64_t N, int64_t ld, const double* phi,
+                       double* out, void* workspace, size_t workspace_bytes, void* stream);
+size_t sysid_predict_rmse_workspace_bytes(const sysid_model* model);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SYSID_B200_H */

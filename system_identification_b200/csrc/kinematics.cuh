@@ -1,0 +1,534 @@
+// Per-sample kinematics: stage 1 of the hot path.
+//
+//   forward_sample()  one THREAD per sample ("F phase"): joint sines/cosines, poses relative to the base,
+//                     contact Jacobian in the base frame, its Gram S = J J^T, Cholesky, and the null-space
+//                     projector P = I - J^T S^-1 J; then spatial velocity / gravity-biased acceleration of every
+//                     body.  Results go to a small per-sample context in shared memory.
+//   column_item()     one THREAD per (sample, regressor column) ("C phase"): the 6-vector column of the body
+//                     regressor, walked up the kinematic chain (S_j^T B, then liMi[j].act), multiplied by P on
+//                     the fly.  Produces one column (MAXV values) of the projected row block
+//                     A_i = P [Y | S^T diag(dq) | S^T diag(sign dq) | S^T tau].
+//
+// Algorithms restated from pinocchio (upstream of reference src/sys_identification.py:395,406,113-135):
+// computeJointTorqueRegressor / bodyRegressor / getFrameJacobian(LOCAL_WORLD_ALIGNED); see SURVEY.md App. A.
+// Motions are [linear; angular], forces [f; n]; all quantities in LOCAL joint frames.
+//
+// The contact Jacobian only involves position DIFFERENCES, so the base position drops out and the poses are
+// accumulated relative to the base; the result is then rotated by R_b, the matrix Eigen builds from the
+// UN-normalised logged quaternion (float32 logs are off unit norm by ~3e-8, which moves P by ~2e-10 -- above the
+// parity gate -- if R_b were assumed orthonormal):  J_k = [ R_b | -[r_k]x R_b | (R_b a_c) x (R_b d_kc) ],
+// r_k = R_b (foot in base frame), a_c / d_kc = joint axis / lever arm in the base frame.
+#pragma once
+#include "model.cuh"
+
+namespace sysid {
+
+// ---- per-sample context (doubles), sample-major in shared memory -----------------------------------------
+constexpr int CTX_SC = 0;                      // [MAXD][2]  sin, cos of each revolute joint
+constexpr int CTX_B9 = CTX_SC + 2 * MAXD;      // [MAXB][9]  omega(3), alpha(3), acc(3) of each body
+constexpr int CTX_DQ = CTX_B9 + 9 * MAXB;      // [MAXD]     joint velocities
+constexpr int CTX_TAU = CTX_DQ + MAXD;         // [MAXD]     joint torques
+constexpr int CTX_W = CTX_TAU + MAXD;          // sqrt(weight) (0 => sample skipped)
+constexpr int CTX_P = CTX_W + 1;               // [MAXV][MAXV] projector, row-major (offset even => 16 B aligned rows)
+constexpr int CTX_STRIDE = CTX_P + MAXV * MAXV;   // 490 == 2 (mod 4): 2-way conflicts at most for the F-phase writes
+static_assert(CTX_P % 2 == 0 && CTX_STRIDE % 4 == 2, "context layout");
+
+// ---- F-phase scratch (doubles per lane), lane-minor: element e of lane l at scr[e * 32 + l] ---------------
+constexpr int SCR_POSE = 0;                          // [MAXD][12] R(9) p(3) of revolute joints relative to the base
+constexpr int SCR_RF = SCR_POSE + 12 * MAXD;         // [MAXEE][3] stance-foot positions in the base frame
+constexpr int SCR_JL = SCR_RF + 3 * MAXEE;           // [MAXEE][MAXCH][3] leg columns of J'
+constexpr int SCR_S = SCR_JL + 3 * MAXEE * MAXCH;    // [78] packed lower triangle of S / L / L^-1
+constexpr int SCR_DOUBLES = SCR_S + 78;              // 306
+constexpr int SCR_VA = 0;                            // second pass reuses the front: [MAXB][12] v(6) a(6)
+static_assert(12 * MAXB <= SCR_DOUBLES, "scratch reuse");
+constexpr int SCR_LANES = 32;
+
+struct SampleIO {
+    const double* q; const double* dq; const double* ddq; const double* tau; const double* cnt;
+    const double* weights;   // nullable
+    long long ld;
+};
+
+#define SCR(e) scr[(e) * SCR_LANES]
+
+__device__ __forceinline__ void joint_rotation_compose(const DevModel& M, int j, double s, double c, double R[9]) {
+    // R = pR[j] * Rot(axis_j, angle)   (row-major)
+    const double* p = M.pR[j];
+    const int jt = M.jtype[j];
+    if (jt == JT_RX) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { R[3 * r] = p[3 * r]; R[3 * r + 1] = c * p[3 * r + 1] + s * p[3 * r + 2]; R[3 * r + 2] = c * p[3 * r + 2] - s * p[3 * r + 1]; }
+    } else if (jt == JT_RY) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { R[3 * r] = c * p[3 * r] - s * p[3 * r + 2]; R[3 * r + 1] = p[3 * r + 1]; R[3 * r + 2] = s * p[3 * r] + c * p[3 * r + 2]; }
+    } else if (jt == JT_RZ) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { R[3 * r] = c * p[3 * r] + s * p[3 * r + 1]; R[3 * r + 1] = c * p[3 * r + 1] - s * p[3 * r]; R[3 * r + 2] = p[3 * r + 2]; }
+    } else {  // Rodrigues about a unit axis u: I + s [u]x + (1-c) [u]x^2
+        const double ux = M.axis[j][0], uy = M.axis[j][1], uz = M.axis[j][2], t = 1.0 - c;
+        const double Q[9] = {1.0 - t * (uy * uy + uz * uz), t * ux * uy - s * uz, t * ux * uz + s * uy,
+                             t * ux * uy + s * uz, 1.0 - t * (ux * ux + uz * uz), t * uy * uz - s * ux,
+                             t * ux * uz - s * uy, t * uy * uz + s * ux, 1.0 - t * (ux * ux + uy * uy)};
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) R[3 * r + k] = p[3 * r] * Q[k] + p[3 * r + 1] * Q[3 + k] + p[3 * r + 2] * Q[6 + k];
+    }
+}
+
+__device__ __forceinline__ int tri(int i, int j) { return i * (i + 1) / 2 + j; }   // i >= j
+
+// One thread = one sample.  `scr` already points at this lane's column of the scratch; `ctx` at this sample's context.
+// Returns flags: bit0 = contact Jacobian lost rank (dependent row dropped), bit1 = non-finite input (sample skipped).
+__device__ __noinline__ int forward_sample(const DevModel& M, const SampleIO& io, long long i, double* scr, double* ctx) {
+    int flags = 0;
+    const int nb = M.nb, nd = M.nd;
+    // ---------------- pass 1: joint angles, poses relative to the base --------------------------------------
+    double finite_probe = 0.0;
+    double Rb[9];
+    {   // Eigen::Quaternion::toRotationMatrix on the raw (x, y, z, w): no normalisation, as pinocchio's free-flyer does
+        const double qx = io.q[3 * io.ld + i], qy = io.q[4 * io.ld + i], qz = io.q[5 * io.ld + i], qw = io.q[6 * io.ld + i];
+        finite_probe += qx + qy + qz + qw;
+        const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+        const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+        Rb[0] = 1 - (tyy + tzz); Rb[1] = txy - twz; Rb[2] = txz + twy;
+        Rb[3] = txy + twz; Rb[4] = 1 - (txx + tzz); Rb[5] = tyz - twx;
+        Rb[6] = txz - twy; Rb[7] = tyz + twx; Rb[8] = 1 - (txx + tyy);
+    }
+    for (int j = 2; j <= nb; ++j) {
+        const double th = io.q[(7 + (j - 2)) * io.ld + i];
+        double s, c;
+        sincos(th, &s, &c);
+        finite_probe += th;
+        ctx[CTX_SC + 2 * (j - 2)] = s;
+        ctx[CTX_SC + 2 * (j - 2) + 1] = c;
+        double R[9];
+        joint_rotation_compose(M, j, s, c, R);
+        const int lam = M.parent[j];
+        const int o = SCR_POSE + 12 * (j - 2);
+        if (lam == 1) {
+#pragma unroll
+            for (int k = 0; k < 9; ++k) SCR(o + k) = R[k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) SCR(o + 9 + k) = M.pp[j][k];
+        } else {
+            const int po = SCR_POSE + 12 * (lam - 2);
+            double PR[9], Pp[3];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) PR[k] = SCR(po + k);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) Pp[k] = SCR(po + 9 + k);
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) SCR(o + 3 * r + k) = PR[3 * r] * R[k] + PR[3 * r + 1] * R[3 + k] + PR[3 * r + 2] * R[6 + k];
+                SCR(o + 9 + r) = Pp[r] + PR[3 * r] * M.pp[j][0] + PR[3 * r + 1] * M.pp[j][1] + PR[3 * r + 2] * M.pp[j][2];
+            }
+        }
+    }
+    // ---------------- contact Jacobian, world-aligned (rows of getFrameJacobian(LOCAL_WORLD_ALIGNED)[0:3]) -----
+    int foot_of[MAXEE];   // stance slot -> foot index
+    int m = 0;
+#pragma unroll
+    for (int k = 0; k < MAXEE; ++k) foot_of[k] = 0;
+#pragma unroll
+    for (int k = 0; k < MAXEE; ++k) {
+        if (k < M.n_ee) {
+            const double cv = io.cnt[k * io.ld + i];
+            if (cv != 0.0) {   // truthiness rule of the reference: state 2 counts as stance; NaN is truthy too
+#pragma unroll
+                for (int t = 0; t < MAXEE; ++t) if (t == m) foot_of[t] = k;
+                ++m;
+            }
+        }
+    }
+    for (int t = 0; t < m; ++t) {
+        int k = 0;
+#pragma unroll
+        for (int u = 0; u < MAXEE; ++u) if (u == t) k = foot_of[u];
+        const int jf = M.ee_joint[k];
+        double rf[3];   // foot point in the base frame
+        if (jf == 1) {
+#pragma unroll
+            for (int e = 0; e < 3; ++e) rf[e] = M.ee_off[k][e];
+        } else {
+            const int o = SCR_POSE + 12 * (jf - 2);
+#pragma unroll
+            for (int e = 0; e < 3; ++e)
+                rf[e] = SCR(o + 9 + e) + SCR(o + 3 * e) * M.ee_off[k][0] + SCR(o + 3 * e + 1) * M.ee_off[k][1] + SCR(o + 3 * e + 2) * M.ee_off[k][2];
+        }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) SCR(SCR_RF + 3 * t + e) = Rb[3 * e] * rf[0] + Rb[3 * e + 1] * rf[1] + Rb[3 * e + 2] * rf[2];
+        const int len = M.chain_len[k];
+        for (int e = 0; e < len; ++e) {
+            const int cj = M.chain[k][e];
+            const int o = SCR_POSE + 12 * (cj - 2);
+            double ax[3];   // joint axis in the base frame
+            const int jt = M.jtype[cj];
+            if (jt == JT_RU) {
+#pragma unroll
+                for (int r = 0; r < 3; ++r) ax[r] = SCR(o + 3 * r) * M.axis[cj][0] + SCR(o + 3 * r + 1) * M.axis[cj][1] + SCR(o + 3 * r + 2) * M.axis[cj][2];
+            } else {
+                const int col = jt - JT_RX;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) ax[r] = SCR(o + 3 * r + col);
+            }
+            const double bx = rf[0] - SCR(o + 9), by = rf[1] - SCR(o + 10), bz = rf[2] - SCR(o + 11);
+            const double a0 = Rb[0] * ax[0] + Rb[1] * ax[1] + Rb[2] * ax[2], a1 = Rb[3] * ax[0] + Rb[4] * ax[1] + Rb[5] * ax[2], a2 = Rb[6] * ax[0] + Rb[7] * ax[1] + Rb[8] * ax[2];
+            const double dx = Rb[0] * bx + Rb[1] * by + Rb[2] * bz, dy = Rb[3] * bx + Rb[4] * by + Rb[5] * bz, dz = Rb[6] * bx + Rb[7] * by + Rb[8] * bz;
+            const int jo = SCR_JL + 3 * (t * MAXCH + e);
+            SCR(jo) = a1 * dz - a2 * dy;
+            SCR(jo + 1) = a2 * dx - a0 * dz;
+            SCR(jo + 2) = a0 * dy - a1 * dx;
+        }
+    }
+    // ---------------- S = J J^T (3m x 3m), packed lower --------------------------------------------------------
+    const int m3 = 3 * m;
+    double BB[9];   // R_b R_b^T: identity up to the quaternion's deviation from unit norm, kept for parity
+#pragma unroll
+    for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int y = 0; y < 3; ++y) BB[3 * x + y] = Rb[3 * x] * Rb[3 * y] + Rb[3 * x + 1] * Rb[3 * y + 1] + Rb[3 * x + 2] * Rb[3 * y + 2];
+    for (int t = 0; t < m; ++t) {
+        int kt = 0;
+#pragma unroll
+        for (int u = 0; u < MAXEE; ++u) if (u == t) kt = foot_of[u];
+        const double rt0 = SCR(SCR_RF + 3 * t), rt1 = SCR(SCR_RF + 3 * t + 1), rt2 = SCR(SCR_RF + 3 * t + 2);
+        for (int u2 = 0; u2 <= t; ++u2) {
+            int ku = 0;
+#pragma unroll
+            for (int u = 0; u < MAXEE; ++u) if (u == u2) ku = foot_of[u];
+            const double ru0 = SCR(SCR_RF + 3 * u2), ru1 = SCR(SCR_RF + 3 * u2 + 1), ru2 = SCR(SCR_RF + 3 * u2 + 2);
+            // block(t,u) = J_t J_u^T.  Base part: BB + [r_t]x BB [r_u]x^T
+            double XB[9], B[9];
+#pragma unroll
+            for (int y = 0; y < 3; ++y) {          // XB = [r_t]x BB
+                XB[y] = -rt2 * BB[3 + y] + rt1 * BB[6 + y];
+                XB[3 + y] = rt2 * BB[y] - rt0 * BB[6 + y];
+                XB[6 + y] = -rt1 * BB[y] + rt0 * BB[3 + y];
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x) {          // B = BB - XB [r_u]x   ([r]x^T = -[r]x)
+                const double m0 = XB[3 * x], m1 = XB[3 * x + 1], m2 = XB[3 * x + 2];
+                B[3 * x] = BB[3 * x] - (m1 * ru2 - m2 * ru1);
+                B[3 * x + 1] = BB[3 * x + 1] - (m2 * ru0 - m0 * ru2);
+                B[3 * x + 2] = BB[3 * x + 2] - (m0 * ru1 - m1 * ru0);
+            }
+            // leg part: joints common to both foot chains (aligned at the root end of the chains)
+            const int ns = M.nshared[kt][ku];
+            const int lt = M.chain_len[kt], lu = M.chain_len[ku];
+            for (int e = 0; e < ns; ++e) {
+                const int ot = SCR_JL + 3 * (t * MAXCH + (lt - ns + e));
+                const int ou = SCR_JL + 3 * (u2 * MAXCH + (lu - ns + e));
+                const double a0 = SCR(ot), a1 = SCR(ot + 1), a2 = SCR(ot + 2);
+                const double b0 = SCR(ou), b1 = SCR(ou + 1), b2 = SCR(ou + 2);
+                B[0] += a0 * b0; B[1] += a0 * b1; B[2] += a0 * b2;
+                B[3] += a1 * b0; B[4] += a1 * b1; B[5] += a1 * b2;
+                B[6] += a2 * b0; B[7] += a2 * b1; B[8] += a2 * b2;
+            }
+#pragma unroll
+            for (int x = 0; x < 3; ++x)
+#pragma unroll
+                for (int y = 0; y < 3; ++y) {
+                    const int gi = 3 * t + x, gj = 3 * u2 + y;
+                    if (gi >= gj) SCR(SCR_S + tri(gi, gj)) = B[3 * x + y];
+                }
+        }
+    }
+    // ---------------- Cholesky S = L L^T in place; dependent rows are dropped (pinv semantics) ---------------
+    double maxdiag = 0.0;
+    for (int a = 0; a < m3; ++a) maxdiag = fmax(maxdiag, SCR(SCR_S + tri(a, a)));
+    const double piv_tol = 1e-13 * maxdiag;
+    for (int a = 0; a < m3; ++a) {
+        double d = SCR(SCR_S + tri(a, a));
+        for (int k = 0; k < a; ++k) { const double l = SCR(SCR_S + tri(a, k)); d -= l * l; }
+        double inv;
+        if (d > piv_tol) { const double sd = sqrt(d); SCR(SCR_S + tri(a, a)) = sd; inv = 1.0 / sd; }
+        else { SCR(SCR_S + tri(a, a)) = 0.0; inv = 0.0; flags |= 1; }    // row a is (numerically) dependent: drop it
+        for (int b = a + 1; b < m3; ++b) {
+            double v = SCR(SCR_S + tri(b, a));
+            for (int k = 0; k < a; ++k) v -= SCR(SCR_S + tri(b, k)) * SCR(SCR_S + tri(a, k));
+            SCR(SCR_S + tri(b, a)) = v * inv;
+        }
+    }
+    // ---------------- L^-1 in place (dropped rows/cols become zero) ------------------------------------------
+    for (int a = 0; a < m3; ++a) {
+        const double laa = SCR(SCR_S + tri(a, a));
+        SCR(SCR_S + tri(a, a)) = (laa != 0.0) ? 1.0 / laa : 0.0;
+    }
+    for (int a = 1; a < m3; ++a) {
+        const double inva = SCR(SCR_S + tri(a, a));
+        for (int b = 0; b < a; ++b) {
+            double v = 0.0;
+            for (int k = b; k < a; ++k) v -= SCR(SCR_S + tri(a, k)) * SCR(SCR_S + tri(k, b));   // rows k < a already inverted
+            SCR(SCR_S + tri(a, b)) = v * inva;
+        }
+    }
+    // ---------------- P = I - J^T (L^-T L^-1) J ----------------------------------------------------------------
+    // column a of J as a 3m-vector u_a: a<3: R_b[:,a] per foot; 3<=a<6: R_b[:,a-3] x r_t; a>=6: leg column of joint a-4 if on the chain
+    const int nv = M.nv;
+    double* P = ctx + CTX_P;
+    for (int a = 0; a < MAXV; ++a) {
+        double u[3 * MAXEE], w[3 * MAXEE], z[3 * MAXEE];
+#pragma unroll
+        for (int k = 0; k < 3 * MAXEE; ++k) u[k] = 0.0;
+        if (a < nv) {
+#pragma unroll
+            for (int t = 0; t < MAXEE; ++t) {
+                if (t < m) {
+                    if (a < 3) {
+#pragma unroll
+                        for (int e = 0; e < 3; ++e) u[3 * t + e] = (a == 0) ? Rb[3 * e] : ((a == 1) ? Rb[3 * e + 1] : Rb[3 * e + 2]);
+                    } else if (a < 6) {
+                        const double r0 = SCR(SCR_RF + 3 * t), r1 = SCR(SCR_RF + 3 * t + 1), r2 = SCR(SCR_RF + 3 * t + 2);
+                        // -[r]x c = c x r, c = column (a-3) of R_b
+                        const double c0 = (a == 3) ? Rb[0] : ((a == 4) ? Rb[1] : Rb[2]);
+                        const double c1 = (a == 3) ? Rb[3] : ((a == 4) ? Rb[4] : Rb[5]);
+                        const double c2 = (a == 3) ? Rb[6] : ((a == 4) ? Rb[7] : Rb[8]);
+                        u[3 * t] = c1 * r2 - c2 * r1; u[3 * t + 1] = c2 * r0 - c0 * r2; u[3 * t + 2] = c0 * r1 - c1 * r0;
+                    } else {
+                        int kt = 0;
+#pragma unroll
+                        for (int uu = 0; uu < MAXEE; ++uu) if (uu == t) kt = foot_of[uu];
+                        const int cj = a - 4;   // joint id with idx_v == a
+                        const int len = M.chain_len[kt];
+                        for (int e = 0; e < len; ++e) {
+                            if (M.chain[kt][e] == cj) {
+                                const int jo = SCR_JL + 3 * (t * MAXCH + e);
+                                u[3 * t] = SCR(jo); u[3 * t + 1] = SCR(jo + 1); u[3 * t + 2] = SCR(jo + 2);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // w = L^-1 u ; z = L^-T w
+#pragma unroll
+        for (int r = 0; r < 3 * MAXEE; ++r) {
+            double acc = 0.0;
+            if (r < m3) {
+#pragma unroll
+                for (int k = 0; k <= r; ++k) acc += SCR(SCR_S + tri(r, k)) * u[k];
+            }
+            w[r] = acc;
+        }
+#pragma unroll
+        for (int r = 0; r < 3 * MAXEE; ++r) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = r; k < 3 * MAXEE; ++k) if (k < m3) acc += SCR(SCR_S + tri(k, r)) * w[k];
+            z[r] = acc;
+        }
+        // P[a][b] = delta_ab - u_b . z   for b >= a, mirrored
+        for (int b = a; b < MAXV; ++b) {
+            double dotv = 0.0;
+            if (a < nv && b < nv) {
+#pragma unroll
+                for (int t = 0; t < MAXEE; ++t) {
+                    if (t < m) {
+                        if (b < 3) {
+                            dotv += ((b == 0) ? Rb[0] : (b == 1) ? Rb[1] : Rb[2]) * z[3 * t] + ((b == 0) ? Rb[3] : (b == 1) ? Rb[4] : Rb[5]) * z[3 * t + 1]
+                                  + ((b == 0) ? Rb[6] : (b == 1) ? Rb[7] : Rb[8]) * z[3 * t + 2];
+                        } else if (b < 6) {
+                            const double r0 = SCR(SCR_RF + 3 * t), r1 = SCR(SCR_RF + 3 * t + 1), r2 = SCR(SCR_RF + 3 * t + 2);
+                            const double c0 = (b == 3) ? Rb[0] : ((b == 4) ? Rb[1] : Rb[2]);
+                            const double c1 = (b == 3) ? Rb[3] : ((b == 4) ? Rb[4] : Rb[5]);
+                            const double c2 = (b == 3) ? Rb[6] : ((b == 4) ? Rb[7] : Rb[8]);
+                            dotv += (c1 * r2 - c2 * r1) * z[3 * t] + (c2 * r0 - c0 * r2) * z[3 * t + 1] + (c0 * r1 - c1 * r0) * z[3 * t + 2];
+                        } else {
+                            int kt = 0;
+#pragma unroll
+                            for (int uu = 0; uu < MAXEE; ++uu) if (uu == t) kt = foot_of[uu];
+                            const int cj = b - 4;
+                            const int len = M.chain_len[kt];
+                            for (int e = 0; e < len; ++e) {
+                                if (M.chain[kt][e] == cj) {
+                                    const int jo = SCR_JL + 3 * (t * MAXCH + e);
+                                    dotv += SCR(jo) * z[3 * t] + SCR(jo + 1) * z[3 * t + 1] + SCR(jo + 2) * z[3 * t + 2];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            const double val = ((a == b && a < nv) ? 1.0 : 0.0) - dotv;
+            P[a * MAXV + b] = val;
+            P[b * MAXV + a] = val;
+        }
+    }
+    // ---------------- pass 2: spatial velocities and gravity-biased accelerations (local frames) ---------------
+    {
+        // root (free-flyer): v = dq[0:6]; a = ddq[0:6] + [R_b^T (-g); 0], R_b from the UN-normalised quaternion (Eigen)
+        const double g0 = -M.gravity[0], g1 = -M.gravity[1], g2 = -M.gravity[2];
+        double v[6], a[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { v[k] = io.dq[k * io.ld + i]; a[k] = io.ddq[k * io.ld + i]; finite_probe += v[k] + a[k]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a[k] += Rb[k] * g0 + Rb[3 + k] * g1 + Rb[6 + k] * g2;   // R_b^T (-g)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { SCR(SCR_VA + k) = v[k]; SCR(SCR_VA + 6 + k) = a[k]; }
+        double* b9 = ctx + CTX_B9;
+        b9[0] = v[3]; b9[1] = v[4]; b9[2] = v[5];
+        b9[3] = a[3]; b9[4] = a[4]; b9[5] = a[5];
+        b9[6] = a[0] + (v[4] * v[2] - v[5] * v[1]);
+        b9[7] = a[1] + (v[5] * v[0] - v[3] * v[2]);
+        b9[8] = a[2] + (v[3] * v[1] - v[4] * v[0]);
+    }
+    for (int j = 2; j <= nb; ++j) {
+        const double s = ctx[CTX_SC + 2 * (j - 2)], c = ctx[CTX_SC + 2 * (j - 2) + 1];
+        double R[9];
+        joint_rotation_compose(M, j, s, c, R);
+        const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
+        const int lam = M.parent[j];
+        const int po = SCR_VA + 12 * (lam - 1);
+        double pv[6], pa[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { pv[k] = SCR(po + k); pa[k] = SCR(po + 6 + k); }
+        // actInv: [R^T (v - p x w); R^T w]
+        const double tvx = pv[0] - (py * pv[5] - pz * pv[4]), tvy = pv[1] - (pz * pv[3] - px * pv[5]), tvz = pv[2] - (px * pv[4] - py * pv[3]);
+        const double tax = pa[0] - (py * pa[5] - pz * pa[4]), tay = pa[1] - (pz * pa[3] - px * pa[5]), taz = pa[2] - (px * pa[4] - py * pa[3]);
+        double v[6], a[6];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            v[k] = R[k] * tvx + R[3 + k] * tvy + R[6 + k] * tvz;
+            v[3 + k] = R[k] * pv[3] + R[3 + k] * pv[4] + R[6 + k] * pv[5];
+            a[k] = R[k] * tax + R[3 + k] * tay + R[6 + k] * taz;
+            a[3 + k] = R[k] * pa[3] + R[3 + k] * pa[4] + R[6 + k] * pa[5];
+        }
+        const double qd = io.dq[(6 + (j - 2)) * io.ld + i], qdd = io.ddq[(6 + (j - 2)) * io.ld + i];
+        finite_probe += qd + qdd;
+        double wj[3];
+        const int jt = M.jtype[j];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) wj[k] = (jt == JT_RU) ? M.axis[j][k] : ((jt - JT_RX) == k ? 1.0 : 0.0);
+        // v_i = actInv(v_parent) + (0; wj qd)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) v[3 + k] += wj[k] * qd;
+        // a_i = actInv(a_parent) + v_i x vJ + (0; wj qdd), with vJ = (0; wj qd): v x vJ = (v_lin x wJ ; w x wJ)
+        const double w0 = wj[0] * qd, w1 = wj[1] * qd, w2 = wj[2] * qd;
+        a[0] += v[1] * w2 - v[2] * w1; a[1] += v[2] * w0 - v[0] * w2; a[2] += v[0] * w1 - v[1] * w0;
+        a[3] += v[4] * w2 - v[5] * w1 + wj[0] * qdd; a[4] += v[5] * w0 - v[3] * w2 + wj[1] * qdd; a[5] += v[3] * w1 - v[4] * w0 + wj[2] * qdd;
+        const int o = SCR_VA + 12 * (j - 1);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { SCR(o + k) = v[k]; SCR(o + 6 + k) = a[k]; }
+        double* b9 = ctx + CTX_B9 + 9 * (j - 1);
+        b9[0] = v[3]; b9[1] = v[4]; b9[2] = v[5];
+        b9[3] = a[3]; b9[4] = a[4]; b9[5] = a[5];
+        b9[6] = a[0] + (v[4] * v[2] - v[5] * v[1]);
+        b9[7] = a[1] + (v[5] * v[0] - v[3] * v[2]);
+        b9[8] = a[2] + (v[3] * v[1] - v[4] * v[0]);
+    }
+    for (int k = 0; k < nd; ++k) {
+        const double dqk = io.dq[(6 + k) * io.ld + i];
+        const double tk = io.tau ? io.tau[k * io.ld + i] : 0.0;
+        finite_probe += tk;
+        ctx[CTX_DQ + k] = dqk;
+        ctx[CTX_TAU + k] = tk;
+    }
+    double wgt = io.weights ? io.weights[i] : 1.0;
+    if (!(fabs(finite_probe) < 1e300)) { flags |= 2; wgt = 0.0; }   // NaN/Inf anywhere: skip the sample
+    ctx[CTX_W] = sqrt(fmax(wgt, 0.0));
+    return flags;
+}
+#undef SCR
+
+// One thread = one column of one sample's projected row block.  col in [0, CW): body columns, then viscous,
+// Coulomb, then the tau column.  PROJECT=false yields the raw (unprojected) regressor column instead.
+// Returns false for padding columns (nothing written to out).
+template <bool PROJECT>
+__device__ __forceinline__ bool column_item(const DevModel& M, const double* ctx, int col, double out[MAXV]) {
+    const int np = M.nparams, nd = M.nd;
+    const double* P = ctx + CTX_P;
+#pragma unroll
+    for (int r = 0; r < MAXV; ++r) out[r] = 0.0;
+    if (col < np) {
+        const int i = col / 10 + 1, k = col - 10 * (i - 1);
+        const double* b9 = ctx + CTX_B9 + 9 * (i - 1);
+        const double w0 = b9[0], w1 = b9[1], w2 = b9[2], al0 = b9[3], al1 = b9[4], al2 = b9[5], ac0 = b9[6], ac1 = b9[7], ac2 = b9[8];
+        double f0 = 0, f1 = 0, f2 = 0, n0 = 0, n1 = 0, n2 = 0;
+        if (k == 0) { f0 = ac0; f1 = ac1; f2 = ac2; }
+        else if (k < 4) {
+            // f = alpha x e + w x (w x e);  n = e x acc
+            const double e0 = (k == 1), e1 = (k == 2), e2 = (k == 3);
+            const double c0 = w1 * e2 - w2 * e1, c1 = w2 * e0 - w0 * e2, c2 = w0 * e1 - w1 * e0;   // w x e
+            f0 = al1 * e2 - al2 * e1 + (w1 * c2 - w2 * c1);
+            f1 = al2 * e0 - al0 * e2 + (w2 * c0 - w0 * c2);
+            f2 = al0 * e1 - al1 * e0 + (w0 * c1 - w1 * c0);
+            n0 = e1 * ac2 - e2 * ac1; n1 = e2 * ac0 - e0 * ac2; n2 = e0 * ac1 - e1 * ac0;
+        } else {
+            // n = Br(alpha)[:,k'] + w x Br(w)[:,k'],  Br(u) columns (Ixx,Ixy,Iyy,Ixz,Iyz,Izz):
+            //   (u0,0,0) (u1,u0,0) (0,u1,0) (u2,0,u0) (0,u2,u1) (0,0,u2)
+            double a0, a1, a2, b0, b1, b2;
+            switch (k) {
+                case 4: a0 = al0; a1 = 0; a2 = 0; b0 = w0; b1 = 0; b2 = 0; break;
+                case 5: a0 = al1; a1 = al0; a2 = 0; b0 = w1; b1 = w0; b2 = 0; break;
+                case 6: a0 = 0; a1 = al1; a2 = 0; b0 = 0; b1 = w1; b2 = 0; break;
+                case 7: a0 = al2; a1 = 0; a2 = al0; b0 = w2; b1 = 0; b2 = w0; break;
+                case 8: a0 = 0; a1 = al2; a2 = al1; b0 = 0; b1 = w2; b2 = w1; break;
+                default: a0 = 0; a1 = 0; a2 = al2; b0 = 0; b1 = 0; b2 = w2; break;
+            }
+            n0 = a0 + (w1 * b2 - w2 * b1); n1 = a1 + (w2 * b0 - w0 * b2); n2 = a2 + (w0 * b1 - w1 * b0);
+        }
+        int j = i;
+        while (j > 1) {
+            const int jt = M.jtype[j];
+            const double val = (jt == JT_RX) ? n0 : (jt == JT_RY) ? n1 : (jt == JT_RZ) ? n2
+                                                                   : (M.axis[j][0] * n0 + M.axis[j][1] * n1 + M.axis[j][2] * n2);
+            const int row = 6 + (j - 2);
+            if (PROJECT) {
+                const double* Pr = P + row * MAXV;   // P symmetric: column `row` == row `row`
+#pragma unroll
+                for (int r = 0; r < MAXV; ++r) out[r] = fma(Pr[r], val, out[r]);
+            } else {
+#pragma unroll
+                for (int r = 0; r < MAXV; ++r) if (r == row) out[r] = val;
+            }
+            // force transform to the parent frame: f' = R f, n' = R n + p x f'
+            double R[9];
+            joint_rotation_compose(M, j, ctx[CTX_SC + 2 * (j - 2)], ctx[CTX_SC + 2 * (j - 2) + 1], R);
+            const double g0 = R[0] * f0 + R[1] * f1 + R[2] * f2, g1 = R[3] * f0 + R[4] * f1 + R[5] * f2, g2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
+            const double h0 = R[0] * n0 + R[1] * n1 + R[2] * n2, h1 = R[3] * n0 + R[4] * n1 + R[5] * n2, h2 = R[6] * n0 + R[7] * n1 + R[8] * n2;
+            const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
+            f0 = g0; f1 = g1; f2 = g2;
+            n0 = h0 + (py * g2 - pz * g1); n1 = h1 + (pz * g0 - px * g2); n2 = h2 + (px * g1 - py * g0);
+            j = M.parent[j];
+        }
+        // free-flyer root: rows 0..5 = (f; n)
+        const double y[6] = {f0, f1, f2, n0, n1, n2};
+        if (PROJECT) {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                const double* Pr = P + q * MAXV;
+#pragma unroll
+                for (int r = 0; r < MAXV; ++r) out[r] = fma(Pr[r], y[q], out[r]);
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) out[q] = y[q];
+        }
+        return true;
+    }
+    if (!PROJECT) return false;
+    if (col < np + 2 * nd) {
+        const int jj = (col - np) % nd;
+        const bool coulomb = (col - np) >= nd;
+        const double dqv = ctx[CTX_DQ + jj];
+        const double sc = coulomb ? ((dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv))) : dqv;   // numpy sign: sign(nan)=nan
+        const double* Pr = P + (6 + jj) * MAXV;
+#pragma unroll
+        for (int r = 0; r < MAXV; ++r) out[r] = Pr[r] * sc;
+        return true;
+    }
+    if (col == np + 2 * nd) {
+        for (int jj = 0; jj < nd; ++jj) {
+            const double t = ctx[CTX_TAU + jj];
+            const double* Pr = P + (6 + jj) * MAXV;
+#pragma unroll
+            for (int r = 0; r < MAXV; ++r) out[r] = fma(Pr[r], t, out[r]);
+        }
+        return true;
+    }
+    return false;
+}
+
+}  // namespace sysid

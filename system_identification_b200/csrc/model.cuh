@@ -1,0 +1,36 @@
+// Device-side model image and compile-time envelope shared by all kernels.
+#pragma once
+#include <cstdint>
+
+namespace sysid {
+
+constexpr int MAXJ = 14;     // joints including the universe (index 0)
+constexpr int MAXB = 13;     // bodies = moving joints (free-flyer root + 12 revolute)
+constexpr int MAXV = 18;     // nv = 6 + 12
+constexpr int MAXD = 12;     // actuated joints
+constexpr int MAXEE = 4;     // contact frames
+constexpr int MAXCH = 6;     // longest foot chain (joints between the foot and the root, root excluded)
+constexpr int CW = 160;      // padded width of one stacked row: 10*nb + 2*d + 1 (tau column) <= 155 -> 160
+
+enum { JT_FF = 0, JT_RX = 1, JT_RY = 2, JT_RZ = 3, JT_RU = 4 };
+
+// Passed to kernels BY VALUE as a __grid_constant__ parameter (lives in the constant bank, ~2 KB):
+// no global symbol, so any number of models can be in flight on any streams.
+struct DevModel {
+    int32_t njoints, nb, nv, nq, nd, n_ee;
+    int32_t nparams;                 // 10 * nb
+    int32_t parent[MAXJ];
+    int32_t jtype[MAXJ];
+    double axis[MAXJ][3];
+    double pR[MAXJ][9];              // joint placement rotation, row-major
+    double pp[MAXJ][3];              // joint placement translation
+    double gravity[3];
+    // contact frames: chain[k][e] = e-th joint walking from the foot's joint towards the root (root excluded)
+    int32_t ee_joint[MAXEE];
+    double ee_off[MAXEE][3];
+    int32_t chain_len[MAXEE];
+    int32_t chain[MAXEE][MAXCH];
+    int32_t nshared[MAXEE][MAXEE];   // length of the common suffix of two foot chains
+};
+
+}  // namespace sysid

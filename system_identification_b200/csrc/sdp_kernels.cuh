@@ -1,0 +1,698 @@
+// Stage 3: the LMI-constrained fit of reference src/solver.py:123-210 as ONE persistent thread block per problem.
+//
+//   min_x  1/2 x^T H x - g^T x      H = G/n + lambda blkdiag(M_i),  g = r/n + lambda M phi0     (x = [phi; b_v; b_c])
+//   s.t.   J(phi_i) + eps I >= 0,  C(phi_i) + eps I >= 0  (4x4 LMIs),  m_i >= 0,  tr(J(phi_i) Q_i) >= 0,
+//          sum_i m_i = total_mass,  b_v >= 0,  b_c >= 0.
+//
+// Method: ADMM on the block-Jacobi-scaled problem (x = T y, T_i = chol(H_ii)^-T per link, 1/sqrt(H_kk) for friction;
+// cond(H) ~1e14 raw -> ~20 scaled).  Every LMI is an svec'd 10-row block with ONE scale factor (keeps the PSD cone
+// invariant), so the z-update is 2L independent 4x4 eigen-projections (cyclic Jacobi) plus clamps; the y-update is one
+// dense mat-vec with W = K^-1 - (K^-1 a)(K^-1 a)^T / (a^T K^-1 a), K = H~ + rho A^T A, held in shared memory
+// (the single mass equality is eliminated exactly).  rho is re-balanced from the residuals and K re-inverted in place.
+#pragma once
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sysid_b200.h"
+
+namespace sysid {
+
+constexpr int SDP_THREADS = 512;
+constexpr int SDP_MAXL = 13;
+constexpr int SDP_MAXD = 12;
+constexpr int SDP_MAXC = 10 * SDP_MAXL + 2 * SDP_MAXD;     // 154
+constexpr int SDP_ROWS_PER_LINK = 22;                      // 10 (J) + 10 (C) + m>=0 + tr(JQ)>=0
+constexpr int SDP_MAXM = SDP_ROWS_PER_LINK * SDP_MAXL + 2 * SDP_MAXD;   // 310
+constexpr int SDP_PLAN_LINK = 320;                         // doubles per link in the plan: M(100) Jmap(100) Cmap(100) q(10) Mphi0(10)
+constexpr int SDP_CHECK = 25;                              // residual check period (iterations)
+constexpr int SDP_DEFAULT_MAX_ITERS = 40000;
+
+struct SdpParams {
+    int L, nd, c, m;
+    double total_mass, eps, const_reg, tol;
+    int max_iters;
+    long long stats_stride;
+    size_t ws_stride;          // doubles of workspace per problem
+};
+
+// workspace per problem (doubles): Hs (c*c) | Amat (L*22*10) | T (L*100) | tfric (2nd)
+__host__ __device__ inline size_t sdp_ws_doubles(int L, int nd) {
+    const size_t c = 10 * (size_t)L + 2 * (size_t)nd;
+    return c * c + (size_t)L * SDP_ROWS_PER_LINK * 10 + (size_t)L * 100 + 2 * (size_t)nd + 16;
+}
+inline size_t sdp_plan_doubles(int L) { return (size_t)L * SDP_PLAN_LINK; }
+inline size_t sdp_workspace_bytes(int L, int nd) {
+    // plan + one problem; the launcher checks batch * per-problem against the size it is given
+    return sizeof(double) * (sdp_plan_doubles(L) + sdp_ws_doubles(L, nd));
+}
+
+// ------------------------------------------------------------------------------------------------ host: plan
+namespace sdp_host {
+
+inline void pseudo_inertia(const double* p, double J[16]) {
+    const double m = p[0], hx = p[1], hy = p[2], hz = p[3], Ixx = p[4], Ixy = p[5], Ixz = p[6], Iyy = p[7], Iyz = p[8], Izz = p[9];
+    const double t = 0.5 * (Ixx + Iyy + Izz);
+    const double v[16] = {t - Ixx, -Ixy, -Ixz, hx, -Ixy, t - Iyy, -Iyz, hy, -Ixz, -Iyz, t - Izz, hz, hx, hy, hz, m};
+    std::memcpy(J, v, sizeof(v));
+}
+
+inline bool invert4(const double* A, double* inv) {
+    double a[4][8];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { a[i][j] = A[4 * i + j]; a[i][4 + j] = (i == j); }
+    for (int k = 0; k < 4; ++k) {
+        int piv = k;
+        for (int i = k + 1; i < 4; ++i) if (std::fabs(a[i][k]) > std::fabs(a[piv][k])) piv = i;
+        if (a[piv][k] == 0.0) return false;
+        if (piv != k) for (int j = 0; j < 8; ++j) std::swap(a[k][j], a[piv][j]);
+        const double p = 1.0 / a[k][k];
+        for (int j = 0; j < 8; ++j) a[k][j] *= p;
+        for (int i = 0; i < 4; ++i) if (i != k) { const double f = a[i][k]; for (int j = 0; j < 8; ++j) a[i][j] -= f * a[k][j]; }
+    }
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) inv[4 * i + j] = a[i][4 + j];
+    return true;
+}
+
+// smallest eigenvalue of a symmetric n x n matrix (n <= 10) by cyclic Jacobi
+inline double min_eig_sym(const double* A, int n) {
+    double a[10][10];
+    for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) a[i][j] = A[n * i + j];
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0, tot = 0;
+        for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) { tot += a[i][j] * a[i][j]; if (i != j) off += a[i][j] * a[i][j]; }
+        if (off <= 1e-30 * tot) break;
+        for (int p = 0; p < n; ++p) for (int q = p + 1; q < n; ++q) {
+            if (a[p][q] == 0.0) continue;
+            const double th = (a[q][q] - a[p][p]) / (2 * a[p][q]);
+            const double t = (th >= 0 ? 1.0 : -1.0) / (std::fabs(th) + std::sqrt(th * th + 1));
+            const double c = 1 / std::sqrt(t * t + 1), s = t * c;
+            for (int k = 0; k < n; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = c * x - s * y; a[k][q] = s * x + c * y; }
+            for (int k = 0; k < n; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = c * x - s * y; a[q][k] = s * x + c * y; }
+        }
+    }
+    double mn = a[0][0];
+    for (int i = 1; i < n; ++i) mn = std::fmin(mn, a[i][i]);
+    return mn;
+}
+
+static const int SV_I[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3};
+static const int SV_J[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+
+// Fills the plan; returns false (msg set) when a pullback metric cannot be built (singular / indefinite prior).
+inline bool build_plan(const sysid_sdp_desc& d, std::vector<double>& plan, double& const_reg, char* msg, size_t msglen) {
+    const int L = d.num_links;
+    plan.assign(sdp_plan_doubles(L), 0.0);
+    const_reg = 0.0;
+    const double SQ2 = std::sqrt(2.0);
+    double V[10][16];
+    for (int a = 0; a < 10; ++a) { double e[10] = {0}; e[a] = 1.0; pseudo_inertia(e, V[a]); }
+    for (int i = 0; i < L; ++i) {
+        double* pl = plan.data() + (size_t)i * SDP_PLAN_LINK;
+        double* Mi = pl; double* Jm = pl + 100; double* Cm = pl + 200; double* qr = pl + 300; double* Mp = pl + 310;
+        const double* phi0 = d.phi_prior + 10 * i;
+        const double* sa = d.semi_axes + 3 * i; const double* ce = d.centers + 3 * i;
+        // regulariser
+        if (d.reg_type == SYSID_REG_CONSTANT_PULLBACK) {
+            double P[16], Pi[16];
+            pseudo_inertia(phi0, P);
+            if (!invert4(P, Pi)) { snprintf(msg, msglen, "link %d: prior pseudo-inertia is singular", i); return false; }
+            double PV[10][16];
+            for (int a = 0; a < 10; ++a)
+                for (int r = 0; r < 4; ++r) for (int cc = 0; cc < 4; ++cc) {
+                    double s = 0; for (int k = 0; k < 4; ++k) s += Pi[4 * r + k] * V[a][4 * k + cc];
+                    PV[a][4 * r + cc] = s;
+                }
+            double M[100];
+            for (int a = 0; a < 10; ++a) for (int b = 0; b < 10; ++b) {
+                double tr = 0;
+                for (int r = 0; r < 4; ++r) for (int k = 0; k < 4; ++k) tr += PV[a][4 * r + k] * PV[b][4 * k + r];
+                M[10 * a + b] = tr;
+            }
+            for (int a = 0; a < 10; ++a) for (int b = a + 1; b < 10; ++b) { const double s = 0.5 * (M[10 * a + b] + M[10 * b + a]); M[10 * a + b] = M[10 * b + a] = s; }
+            double mn = min_eig_sym(M, 10);
+            if (mn < 0) { for (int a = 0; a < 10; ++a) M[11 * a] += -mn + 1e-5; mn = min_eig_sym(M, 10); }
+            if (!(mn > 0)) { snprintf(msg, msglen, "link %d: Matrix is not positive definite. Minimum eigenvalue: %g", i, mn); return false; }
+            for (int k = 0; k < 100; ++k) Mi[k] = d.lambda_reg * M[k];
+            for (int a = 0; a < 10; ++a) { double s = 0; for (int b = 0; b < 10; ++b) s += Mi[10 * a + b] * phi0[b]; Mp[a] = s; const_reg += 0.5 * s * phi0[a]; }
+        } else {
+            for (int a = 0; a < 10; ++a) { Mi[11 * a] = 2.0 * d.lambda_reg; Mp[a] = 2.0 * d.lambda_reg * phi0[a]; const_reg += d.lambda_reg * phi0[a] * phi0[a]; }
+        }
+        // svec maps of J(phi) and C(phi)
+        for (int r = 0; r < 10; ++r) {
+            const int ii = SV_I[r], jj = SV_J[r];
+            const double w = (ii == jj) ? 1.0 : SQ2;
+            for (int a = 0; a < 10; ++a) Jm[10 * r + a] = w * V[a][4 * ii + jj];
+        }
+        // C = [[m, (h - m c)^T], [h - m c, m diag(s^2)]]
+        double Cmat[10][16];
+        std::memset(Cmat, 0, sizeof(Cmat));
+        Cmat[0][0] = 1.0;
+        for (int k = 0; k < 3; ++k) { Cmat[0][4 * 0 + 1 + k] = -ce[k]; Cmat[0][4 * (1 + k) + 0] = -ce[k]; Cmat[0][4 * (1 + k) + 1 + k] = sa[k] * sa[k]; }
+        for (int k = 0; k < 3; ++k) { Cmat[1 + k][4 * 0 + 1 + k] = 1.0; Cmat[1 + k][4 * (1 + k) + 0] = 1.0; }
+        for (int r = 0; r < 10; ++r) {
+            const int ii = SV_I[r], jj = SV_J[r];
+            const double w = (ii == jj) ? 1.0 : SQ2;
+            for (int a = 0; a < 10; ++a) Cm[10 * r + a] = w * Cmat[a][4 * ii + jj];
+        }
+        // tr(J Q): Q through float32 with +Q in the top-left block (reference quirk Q2)
+        float Qf[16];
+        std::memset(Qf, 0, sizeof(Qf));
+        double qd[3], qc[3], cqc = 0;
+        for (int k = 0; k < 3; ++k) { qd[k] = 1.0 / (sa[k] * sa[k]); qc[k] = qd[k] * ce[k]; cqc += ce[k] * qc[k]; }
+        for (int k = 0; k < 3; ++k) { Qf[5 * k] = (float)qd[k]; Qf[4 * k + 3] = (float)qc[k]; Qf[12 + k] = (float)qc[k]; }
+        Qf[15] = (float)(1.0 - cqc);
+        for (int a = 0; a < 10; ++a) { double tr = 0; for (int r = 0; r < 4; ++r) for (int k = 0; k < 4; ++k) tr += V[a][4 * r + k] * (double)Qf[4 * k + r]; qr[a] = tr; }
+    }
+    return true;
+}
+
+}  // namespace sdp_host
+
+// ------------------------------------------------------------------------------------------------ device helpers
+__device__ __forceinline__ double block_sum(double v, double* red, int tid) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < SDP_THREADS / 32; ++w) s += red[w];
+    return s;
+}
+
+// PSD projection of a symmetric 4x4 given/returned in svec form (off-diagonals carry sqrt(2)); also returns min eigenvalue.
+__device__ inline double project_psd4(const double* in, double* out, bool write) {
+    const double IS2 = 0.70710678118654752440, SQ2 = 1.41421356237309504880;
+    double a[4][4];
+    a[0][0] = in[0]; a[1][0] = a[0][1] = in[1] * IS2; a[1][1] = in[2];
+    a[2][0] = a[0][2] = in[3] * IS2; a[2][1] = a[1][2] = in[4] * IS2; a[2][2] = in[5];
+    a[3][0] = a[0][3] = in[6] * IS2; a[3][1] = a[1][3] = in[7] * IS2; a[3][2] = a[2][3] = in[8] * IS2; a[3][3] = in[9];
+    // quick accept: Cholesky succeeds with strictly positive pivots => already in the cone
+    {
+        bool pd = true;
+        double l[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                double s = a[i][j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= l[i][k] * l[j][k];
+                if (i == j) { if (s > 0.0) l[i][i] = sqrt(s); else { pd = false; l[i][i] = 1.0; } }
+                else l[i][j] = s / l[j][j];
+            }
+        }
+        if (pd && !write) {
+            // caller only wants to know the cone membership cheaply; min eigenvalue bound not needed
+        }
+        if (pd && write) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) out[k] = in[k];
+            return 1.0;   // positive => interior
+        }
+    }
+    double v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, tot = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { tot += a[i][j] * a[i][j]; if (i != j) off += a[i][j] * a[i][j]; }
+        if (off <= 1e-32 * tot) break;
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 4; ++q) {
+                const double apq = a[p][q];
+                if (apq != 0.0) {
+                    const double th = (a[q][q] - a[p][p]) / (2.0 * apq);
+                    const double t = copysign(1.0, th) / (fabs(th) + sqrt(th * th + 1.0));
+                    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const double x = a[k][p], y = a[k][q]; a[k][p] = c * x - s * y; a[k][q] = s * x + c * y; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const double x = a[p][k], y = a[q][k]; a[p][k] = c * x - s * y; a[q][k] = s * x + c * y; }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) { const double x = v[k][p], y = v[k][q]; v[k][p] = c * x - s * y; v[k][q] = s * x + c * y; }
+                }
+            }
+    }
+    double mn = fmin(fmin(a[0][0], a[1][1]), fmin(a[2][2], a[3][3]));
+    if (write) {
+        double w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) w[k] = fmax(a[k][k], 0.0);
+        const int SI[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, SJ[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += w[k] * v[SI[r]][k] * v[SJ[r]][k];
+            out[r] = (SI[r] == SJ[r]) ? s : s * SQ2;
+        }
+    }
+    return mn;
+}
+
+// In-place inverse of the SPD matrix A (n x n, leading dimension ld, in shared memory) by Gauss-Jordan.
+__device__ inline void spd_inverse_inplace(double* A, int n, int ld, double* colbuf, int tid) {
+    for (int k = 0; k < n; ++k) {
+        for (int i = tid; i < n; i += SDP_THREADS) colbuf[i] = A[i * ld + k];
+        __syncthreads();
+        const double p = 1.0 / colbuf[k];
+        for (int e = tid; e < n * n; e += SDP_THREADS) {
+            const int i = e / n, j = e - i * n;
+            if (i == k) continue;
+            const double f = colbuf[i] * p;
+            const double akj = (j == k) ? 1.0 : A[k * ld + j];
+            const double aij = (j == k) ? 0.0 : A[i * ld + j];
+            A[i * ld + j] = aij - f * akj;
+        }
+        __syncthreads();
+        for (int j = tid; j < n; j += SDP_THREADS) A[k * ld + j] = ((j == k) ? 1.0 : A[k * ld + j]) * p;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ the solver
+__global__ void __launch_bounds__(SDP_THREADS, 1)
+sdp_admm_kernel(const SdpParams prm, const double* __restrict__ plan, const double* __restrict__ stats_all,
+                double* __restrict__ ws_all, double* __restrict__ x_out_all, sysid_sdp_info* __restrict__ info_all) {
+    extern __shared__ __align__(16) double sm[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = prm.L, nd = prm.nd, c = prm.c, m = prm.m, np = 10 * L;
+    const int prob = blockIdx.x;
+    const double* stats = stats_all + (size_t)prob * prm.stats_stride;
+    double* ws = ws_all + (size_t)prob * prm.ws_stride;
+    double* Hs = ws;                                   // c*c  scaled Hessian (kept for re-factorisation)
+    double* Am = Hs + (size_t)c * c;                   // L*22*10 scaled constraint blocks
+    double* Tm = Am + (size_t)L * SDP_ROWS_PER_LINK * 10;   // L*100, T_i row-major (upper triangular)
+    double* tf = Tm + (size_t)L * 100;                 // 2nd friction scales
+    // shared memory carve-up
+    double* W = sm;                                    // c*c
+    double* gt = W + c * c;                            // c   scaled linear term
+    double* w0 = gt + c;                               // c
+    double* at = w0 + c;                               // c   scaled equality vector
+    double* y = at + c;                                // c
+    double* rhs = y + c;                               // c
+    double* z = rhs + c;                               // m
+    double* lam = z + m;                               // m
+    double* c0 = lam + m;                              // m
+    double* tv = c0 + m;                               // m  scratch (t1, then v + lam/rho)
+    double* zprev = tv + m;                            // m
+    double* red = zprev + m;                           // 32
+    __shared__ double s_scalar[8];
+    __shared__ int s_flag;
+
+    const double n_rows = stats[(size_t)c * c + c + 1];
+    const double inv_n = 1.0 / n_rows;
+
+    // ---- S1: per-link Cholesky of H_ii = G_ii/n + lambda M_i  ->  T_i = L_i^-T (one warp lane 0 per link; tiny) ----
+    if (tid < L) {
+        const int i = tid;
+        double B[10][10];
+        const double* Mi = plan + (size_t)i * SDP_PLAN_LINK;
+        for (int a = 0; a < 10; ++a) for (int b = 0; b < 10; ++b) B[a][b] = stats[(size_t)(10 * i + a) * c + 10 * i + b] * inv_n + Mi[10 * a + b];
+        // Cholesky (lower) in place
+        for (int a = 0; a < 10; ++a) {
+            for (int b = 0; b <= a; ++b) {
+                double s = B[a][b];
+                for (int k = 0; k < b; ++k) s -= B[a][k] * B[b][k];
+                B[a][b] = (a == b) ? sqrt(fmax(s, 1e-300)) : s / B[b][b];
+            }
+        }
+        // Linv (lower)
+        double Li[10][10];
+        for (int a = 0; a < 10; ++a) for (int b = 0; b < 10; ++b) Li[a][b] = 0.0;
+        for (int a = 0; a < 10; ++a) {
+            Li[a][a] = 1.0 / B[a][a];
+            for (int b = 0; b < a; ++b) {
+                double s = 0.0;
+                for (int k = b; k < a; ++k) s -= B[a][k] * Li[k][b];
+                Li[a][b] = s / B[a][a];
+            }
+        }
+        // T = Linv^T  (upper triangular), row-major
+        for (int a = 0; a < 10; ++a) for (int b = 0; b < 10; ++b) Tm[(size_t)i * 100 + 10 * a + b] = Li[b][a];
+        // warm start y0_i = T_i^-1 phi0_i = L_i^T phi0_i, recovered from lambda M phi0?  no: use z-init from c0 only (below)
+    }
+    if (tid < 2 * nd) {
+        const double hkk = stats[(size_t)(np + tid) * c + np + tid] * inv_n;
+        tf[tid] = (hkk > 0.0) ? rsqrt(hkk) : 1.0;
+    }
+    __syncthreads();
+    // ---- S2: Hs = T^T H T, gt = T^T g, at = T^T aeq ---------------------------------------------------------------
+    for (int e = tid; e < c * c; e += SDP_THREADS) {
+        const int a = e / c, b = e - a * c;
+        double s = 0.0;
+        if (a < np && b < np) {
+            const int ia = a / 10, ib = b / 10, la = a - 10 * ia, lb = b - 10 * ib;
+            const double* Ta = Tm + (size_t)ia * 100; const double* Tb = Tm + (size_t)ib * 100;
+            for (int k = 0; k <= la; ++k) {
+                const double tka = Ta[10 * k + la];
+                double inner = 0.0;
+                for (int l = 0; l <= lb; ++l) {
+                    double h = stats[(size_t)(10 * ia + k) * c + 10 * ib + l] * inv_n;
+                    if (ia == ib) h += plan[(size_t)ia * SDP_PLAN_LINK + 10 * k + l];
+                    inner += h * Tb[10 * l + lb];
+                }
+                s += tka * inner;
+            }
+        } else if (a < np) {
+            const int ia = a / 10, la = a - 10 * ia;
+            const double* Ta = Tm + (size_t)ia * 100;
+            for (int k = 0; k <= la; ++k) s += Ta[10 * k + la] * stats[(size_t)(10 * ia + k) * c + b] * inv_n;
+            s *= tf[b - np];
+        } else if (b < np) {
+            const int ib = b / 10, lb = b - 10 * ib;
+            const double* Tb = Tm + (size_t)ib * 100;
+            for (int l = 0; l <= lb; ++l) s += stats[(size_t)a * c + 10 * ib + l] * inv_n * Tb[10 * l + lb];
+            s *= tf[a - np];
+        } else {
+            s = stats[(size_t)a * c + b] * inv_n * tf[a - np] * tf[b - np];
+        }
+        Hs[e] = s;
+    }
+    for (int a = tid; a < c; a += SDP_THREADS) {
+        double s = 0.0, sa = 0.0;
+        if (a < np) {
+            const int ia = a / 10, la = a - 10 * ia;
+            const double* Ta = Tm + (size_t)ia * 100;
+            for (int k = 0; k <= la; ++k) {
+                const double gk = stats[(size_t)c * c + 10 * ia + k] * inv_n + plan[(size_t)ia * SDP_PLAN_LINK + 310 + k];
+                s += Ta[10 * k + la] * gk;
+            }
+            sa = Ta[la];           // T[0][la]: aeq picks the mass (local index 0) of every link
+        } else {
+            s = stats[(size_t)c * c + a] * inv_n * tf[a - np];
+        }
+        gt[a] = s; at[a] = sa;
+    }
+    // ---- S3: scaled constraint blocks -------------------------------------------------------------------------------
+    // raw rows r of link i (before T): 0-9 Jmap, 10-19 Cmap, 20 e_0, 21 q ; A_i = rows * T_i ; one uniform scale per LMI block
+    for (int e = tid; e < L * SDP_ROWS_PER_LINK * 10; e += SDP_THREADS) {
+        const int i = e / (SDP_ROWS_PER_LINK * 10), rr = (e / 10) % SDP_ROWS_PER_LINK, b = e % 10;
+        const double* pl = plan + (size_t)i * SDP_PLAN_LINK;
+        const double* Tb = Tm + (size_t)i * 100;
+        double s = 0.0;
+        for (int k = 0; k <= b; ++k) {
+            double raw;
+            if (rr < 10) raw = pl[100 + 10 * rr + k];
+            else if (rr < 20) raw = pl[200 + 10 * (rr - 10) + k];
+            else if (rr == 20) raw = (k == 0) ? 1.0 : 0.0;
+            else raw = pl[300 + k];
+            s += raw * Tb[10 * k + b];
+        }
+        Am[e] = s;
+    }
+    __syncthreads();
+    // scales: thread per (link, group) with group 0 = J block, 1 = C block, 2 = row 20, 3 = row 21
+    if (tid < 4 * L) {
+        const int i = tid >> 2, gsel = tid & 3;
+        const int r0 = (gsel == 0) ? 0 : (gsel == 1) ? 10 : (gsel == 2) ? 20 : 21;
+        const int nr = (gsel < 2) ? 10 : 1;
+        double* blk = Am + ((size_t)i * SDP_ROWS_PER_LINK + r0) * 10;
+        double ss = 0.0;
+        for (int k = 0; k < nr * 10; ++k) ss += blk[k] * blk[k];
+        const double sig = (ss > 0.0) ? 1.0 / sqrt(ss / nr) : 1.0;
+        for (int k = 0; k < nr * 10; ++k) blk[k] *= sig;
+        for (int r = 0; r < nr; ++r) {
+            double cc = 0.0;
+            if (gsel < 2 && (r == 0 || r == 2 || r == 5 || r == 9)) cc = prm.eps * sig;
+            c0[i * SDP_ROWS_PER_LINK + r0 + r] = cc;
+        }
+    }
+    for (int k = tid; k < 2 * nd; k += SDP_THREADS) c0[L * SDP_ROWS_PER_LINK + k] = 0.0;
+    __syncthreads();
+
+    double rho = 1.0;
+    const double alpha = 1.6;
+    int refacts = 0;
+
+    // K^-1 and the equality elimination; result in W, w0
+    auto factor = [&](double rho_) {
+        for (int e = tid; e < c * c; e += SDP_THREADS) {
+            const int a = e / c, b = e - a * c;
+            double s = Hs[e];
+            if (a < np && b < np) {
+                const int ia = a / 10;
+                if (ia == b / 10) {
+                    const double* Ai = Am + (size_t)ia * SDP_ROWS_PER_LINK * 10;
+                    const int la = a - 10 * ia, lb = b - 10 * ia;
+                    double t = 0.0;
+#pragma unroll
+                    for (int r = 0; r < SDP_ROWS_PER_LINK; ++r) t += Ai[10 * r + la] * Ai[10 * r + lb];
+                    s += rho_ * t;
+                }
+            } else if (a == b) {
+                s += rho_;
+            }
+            W[e] = s;
+        }
+        __syncthreads();
+        spd_inverse_inplace(W, c, c, rhs, tid);
+        // Ka = W at (into rhs), denom = at . Ka
+        for (int a = warp; a < c; a += SDP_THREADS / 32) {
+            double s = 0.0;
+            for (int b = lane; b < c; b += 32) s += W[a * c + b] * at[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) rhs[a] = s;
+        }
+        __syncthreads();
+        double part = 0.0;
+        for (int a = tid; a < c; a += SDP_THREADS) part += at[a] * rhs[a];
+        const double denom = block_sum(part, red, tid);
+        const double inv_d = 1.0 / denom;
+        for (int e = tid; e < c * c; e += SDP_THREADS) {
+            const int a = e / c, b = e - a * c;
+            W[e] -= rhs[a] * rhs[b] * inv_d;
+        }
+        for (int a = tid; a < c; a += SDP_THREADS) w0[a] = rhs[a] * prm.total_mass * inv_d;
+        __syncthreads();
+    };
+
+    auto apply_A = [&](const double* yy, int r) -> double {   // (A yy)[r] + c0[r]
+        if (r < L * SDP_ROWS_PER_LINK) {
+            const int i = r / SDP_ROWS_PER_LINK;
+            const double* row = Am + (size_t)r * 10;
+            double s = c0[r];
+#pragma unroll
+            for (int b = 0; b < 10; ++b) s += row[b] * yy[10 * i + b];
+            return s;
+        }
+        return yy[np + (r - L * SDP_ROWS_PER_LINK)];
+    };
+    auto apply_At = [&](const double* t, int a) -> double {  // (A^T t)[a]
+        if (a < np) {
+            const int i = a / 10, la = a - 10 * i;
+            const double* Ai = Am + (size_t)i * SDP_ROWS_PER_LINK * 10;
+            double s = 0.0;
+#pragma unroll
+            for (int r = 0; r < SDP_ROWS_PER_LINK; ++r) s += Ai[10 * r + la] * t[i * SDP_ROWS_PER_LINK + r];
+            return s;
+        }
+        return t[L * SDP_ROWS_PER_LINK + (a - np)];
+    };
+    auto project = [&](const double* in, double* out) {
+        // LMI blocks: 2L tasks spread over warps' lane 0; linear rows: clamps
+        for (int k = warp; k < 2 * L; k += SDP_THREADS / 32) {
+            if (lane == 0) {
+                const int i = k >> 1, off = i * SDP_ROWS_PER_LINK + 10 * (k & 1);
+                project_psd4(in + off, out + off, true);
+            }
+        }
+        for (int r = tid; r < m; r += SDP_THREADS) {
+            bool lin = (r >= L * SDP_ROWS_PER_LINK) || ((r % SDP_ROWS_PER_LINK) >= 20);
+            if (lin) out[r] = fmax(in[r], 0.0);
+        }
+    };
+
+    factor(rho);
+    // init: y = 0-ish start: z = Proj(c0) , lam = 0
+    for (int r = tid; r < m; r += SDP_THREADS) { lam[r] = 0.0; tv[r] = c0[r]; }
+    __syncthreads();
+    project(tv, z);
+    __syncthreads();
+
+    int iters = 0, status = SYSID_ERR_NOT_OPTIMAL;
+    double rp = 0.0, rd = 0.0;
+    int last_refactor = 0;
+    const double eps_rel = fmax(10.0 * prm.tol, 1e-11), eps_abs = eps_rel * 1e-2;
+    while (iters < prm.max_iters) {
+        const bool check = ((iters + 1) % SDP_CHECK) == 0;
+        // (a) rhs = gt + A^T (rho (z - c0) - lam)
+        for (int r = tid; r < m; r += SDP_THREADS) { tv[r] = rho * (z[r] - c0[r]) - lam[r]; if (check) zprev[r] = z[r]; }
+        __syncthreads();
+        for (int a = tid; a < c; a += SDP_THREADS) rhs[a] = gt[a] + apply_At(tv, a);
+        __syncthreads();
+        // (b) y = W rhs + w0
+        for (int a = warp; a < c; a += SDP_THREADS / 32) {
+            double s = 0.0;
+            for (int b = lane; b < c; b += 32) s += W[a * c + b] * rhs[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) y[a] = s + w0[a];
+        }
+        __syncthreads();
+        // (c) v = alpha (A y + c0) + (1 - alpha) z ; tv = v + lam / rho ; keep A y + c0 in rhs-sized? reuse: store Ay in zprev? no
+        double l_rp = 0.0, l_ay = 0.0;
+        for (int r = tid; r < m; r += SDP_THREADS) {
+            const double ay = apply_A(y, r);
+            const double v = alpha * ay + (1.0 - alpha) * z[r];
+            tv[r] = v + lam[r] / rho;
+            // stash v in lam temporarily? need lam; keep v recomputable: lam_new = lam + rho (v - z_new) = rho (tv - z_new)
+            if (check) { l_ay += ay * ay; }
+        }
+        __syncthreads();
+        // (d) z = Proj(tv) ; lam = rho (tv - z)
+        project(tv, z);
+        __syncthreads();
+        for (int r = tid; r < m; r += SDP_THREADS) lam[r] = rho * (tv[r] - z[r]);
+        ++iters;
+        if (check) {
+            double l_z = 0.0, l_lamn = 0.0;
+            for (int r = tid; r < m; r += SDP_THREADS) {
+                const double ay = apply_A(y, r);
+                const double d = ay - z[r];
+                l_rp += d * d; l_z += z[r] * z[r];
+                tv[r] = z[r] - zprev[r];
+            }
+            __syncthreads();
+            double l_rd = 0.0;
+            for (int a = tid; a < c; a += SDP_THREADS) {
+                const double d = rho * apply_At(tv, a);
+                const double al = apply_At(lam, a);
+                l_rd += d * d; l_lamn += al * al;
+            }
+            const double s_rp = block_sum(l_rp, red, tid), s_ay = block_sum(l_ay, red, tid), s_z = block_sum(l_z, red, tid);
+            const double s_rd = block_sum(l_rd, red, tid), s_ln = block_sum(l_lamn, red, tid);
+            rp = sqrt(s_rp); rd = sqrt(s_rd);
+            const double pn = fmax(sqrt(s_ay), sqrt(s_z)), dn = sqrt(s_ln);
+            const double tol_p = eps_abs * sqrt((double)m) + eps_rel * pn;
+            const double tol_d = eps_abs * sqrt((double)c) + eps_rel * dn;
+            if (rp <= tol_p && rd <= tol_d) { status = SYSID_OK; break; }
+            if (iters - last_refactor >= 2 * SDP_CHECK) {
+                const double rpn = rp / fmax(pn, 1e-300), rdn = rd / fmax(dn, 1e-300);
+                if (rpn > 5.0 * rdn || rdn > 5.0 * rpn) {
+                    double f = sqrt(rpn / fmax(rdn, 1e-300));
+                    f = fmin(fmax(f, 0.1), 10.0);
+                    const double new_rho = fmin(fmax(rho * f, 1e-6), 1e6);
+                    if (new_rho != rho) {
+                        rho = new_rho;
+                        __syncthreads();
+                        factor(rho);
+                        ++refacts;
+                        last_refactor = iters;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- output: x = T y, diagnostics ----------------------------------------------------------------------------------
+    double* x_out = x_out_all + (size_t)prob * c;
+    for (int a = tid; a < c; a += SDP_THREADS) {
+        double s;
+        if (a < np) {
+            const int i = a / 10, la = a - 10 * i;
+            const double* Ta = Tm + (size_t)i * 100;
+            s = 0.0;
+            for (int b = la; b < 10; ++b) s += Ta[10 * la + b] * y[10 * i + b];
+        } else {
+            s = tf[a - np] * y[a];
+        }
+        x_out[a] = s;
+        rhs[a] = s;
+    }
+    __syncthreads();
+    // objective in scaled variables: 1/2 y^T Hs y - gt^T y + const
+    double part = 0.0;
+    for (int a = tid; a < c; a += SDP_THREADS) {
+        double s = 0.0;
+        for (int b = 0; b < c; ++b) s += Hs[(size_t)a * c + b] * y[b];
+        part += y[a] * (0.5 * s - gt[a]);
+    }
+    const double obj = block_sum(part, red, tid) + prm.const_reg + 0.5 * stats[(size_t)c * c + c] * inv_n;
+    double mpart = 0.0;
+    for (int i = tid; i < L; i += SDP_THREADS) mpart += rhs[10 * i];
+    const double msum = block_sum(mpart, red, tid);
+    // min eigenvalues of J + eps I and C + eps I at x (unscaled): evaluate the raw svec maps
+    if (tid == 0) { s_scalar[0] = 1e300; s_scalar[1] = 1e300; }
+    __syncthreads();
+    if (tid < 2 * L) {
+        const int i = tid >> 1, which = tid & 1;
+        const double* mp = plan + (size_t)i * SDP_PLAN_LINK + (which ? 200 : 100);
+        double sv[10], dummy[10];
+        for (int r = 0; r < 10; ++r) {
+            double s = (r == 0 || r == 2 || r == 5 || r == 9) ? prm.eps : 0.0;
+            for (int a = 0; a < 10; ++a) s += mp[10 * r + a] * rhs[10 * i + a];
+            sv[r] = s;
+        }
+        // force the Jacobi path by asking for the eigenvalue without the quick accept: subtract nothing, call with write=false
+        const double mn = project_psd4(sv, dummy, false);
+        // atomicMin on doubles via CAS on the bit pattern is overkill here: serialise through shared memory
+        for (int t = 0; t < 2 * L; ++t) {
+            if (t == tid) s_scalar[which] = fmin(s_scalar[which], mn);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sysid_sdp_info& info = info_all[prob];
+        info.status = status; info.iterations = iters; info.refactorizations = refacts; info.reserved = 0;
+        info.primal_residual = rp; info.dual_residual = rd; info.rho = rho; info.objective = obj;
+        info.min_eig_J = s_scalar[0]; info.min_eig_C = s_scalar[1]; info.mass_residual = msum - prm.total_mass;
+    }
+    (void)s_flag;
+}
+
+inline int sdp_solve_launch(const sysid_sdp_desc& d, const double* stats, int64_t stats_stride, int32_t batch,
+                            double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes,
+                            cudaStream_t st, char* msg, size_t msglen) {
+    if (d.num_links < 1 || d.num_links > SDP_MAXL || d.ndof < 0 || d.ndof > SDP_MAXD) {
+        snprintf(msg, msglen, "num_links %d / ndof %d outside this build's envelope (%d / %d)", d.num_links, d.ndof, SDP_MAXL, SDP_MAXD);
+        return SYSID_ERR_UNSUPPORTED;
+    }
+    if (!d.phi_prior || !d.semi_axes || !d.centers || batch < 1) { snprintf(msg, msglen, "bad sdp descriptor"); return SYSID_ERR_INVALID; }
+    if (d.reg_type != SYSID_REG_CONSTANT_PULLBACK && d.reg_type != SYSID_REG_EUCLIDEAN) {
+        snprintf(msg, msglen, "reg_type %d not supported (the reference marks 'entropic' as non-converging)", d.reg_type);
+        return SYSID_ERR_UNSUPPORTED;
+    }
+    const int L = d.num_links, nd = d.ndof;
+    const size_t plan_n = sdp_plan_doubles(L), ws_n = sdp_ws_doubles(L, nd);
+    const size_t need = sizeof(double) * (plan_n + ws_n * (size_t)batch);
+    if (workspace_bytes < need) { snprintf(msg, msglen, "workspace %zu B < %zu B", workspace_bytes, need); return SYSID_ERR_WORKSPACE; }
+    std::vector<double> plan;
+    double const_reg = 0.0;
+    if (!sdp_host::build_plan(d, plan, const_reg, msg, msglen)) return SYSID_ERR_INVALID;
+    double* dplan = (double*)workspace;
+    cudaError_t e = cudaMemcpyAsync(dplan, plan.data(), sizeof(double) * plan_n, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) { snprintf(msg, msglen, "plan upload failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
+    // the plan vector dies with this frame: pageable-source async copies are staged before returning, but make it explicit
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { snprintf(msg, msglen, "stream sync failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
+    SdpParams prm;
+    prm.L = L; prm.nd = nd; prm.c = 10 * L + 2 * nd; prm.m = SDP_ROWS_PER_LINK * L + 2 * nd;
+    prm.total_mass = d.total_mass; prm.eps = d.epsilon; prm.const_reg = const_reg; prm.tol = d.tol > 0 ? d.tol : 1e-10;
+    prm.max_iters = d.max_iters > 0 ? d.max_iters : SDP_DEFAULT_MAX_ITERS;
+    prm.stats_stride = stats_stride; prm.ws_stride = ws_n;
+    const size_t smem = sizeof(double) * ((size_t)prm.c * prm.c + 5 * (size_t)prm.c + 5 * (size_t)prm.m + 32);
+    e = cudaFuncSetAttribute(sdp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { snprintf(msg, msglen, "smem opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
+    sdp_admm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, dplan + plan_n, x_out, info_out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(msg, msglen, "sdp launch failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
+    return SYSID_OK;
+}
+
+}  // namespace sysid

@@ -1,0 +1,293 @@
+// C-ABI of the B200-native inertial-identification hot path (see include/sysid_b200.h).
+// Host side of the library: model validation/flattening into the kernel-parameter image, launches, error reporting.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sysid_b200.h"
+#include "gram_kernels.cuh"
+#include "sdp_kernels.cuh"
+
+using namespace sysid;
+
+struct sysid_model {
+    DevModel dev;
+    int sm_count;
+};
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) return fail(SYSID_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+int device_sm_count(int* out) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(out, cudaDevAttrMultiProcessorCount, dev));
+    return SYSID_OK;
+}
+
+template <typename K>
+int opt_in_smem(K kernel, size_t bytes) {
+    CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return SYSID_OK;
+}
+
+SampleIO make_io(const double* q, const double* dq, const double* ddq, const double* tau, const double* cnt,
+                 const double* w, int64_t ld) {
+    SampleIO io;
+    io.q = q; io.dq = dq; io.ddq = ddq; io.tau = tau; io.cnt = cnt; io.weights = w; io.ld = ld;
+    return io;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sysid_abi_version(void) { return SYSID_ABI_VERSION; }
+
+const char* sysid_last_error(void) { return g_err; }
+
+void sysid_get_limits(sysid_limits* out) {
+    if (!out) return;
+    out->max_bodies = MAXB; out->max_nv = MAXV; out->max_ee = MAXEE; out->max_depth = MAXCH; out->max_cols_padded = CW;
+}
+
+int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
+    if (!d || !out) return fail(SYSID_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (!d->parent || !d->jtype || !d->axis || !d->place_R || !d->place_p) return fail(SYSID_ERR_INVALID, "null tree array");
+    if (d->njoints < 2) return fail(SYSID_ERR_INVALID, "tree needs at least the universe and a root joint");
+    if (d->njoints > MAXJ) return fail(SYSID_ERR_UNSUPPORTED, "njoints %d exceeds this build's envelope (%d)", d->njoints, MAXJ);
+    if (d->n_ee < 0 || d->n_ee > MAXEE) return fail(SYSID_ERR_UNSUPPORTED, "n_ee %d exceeds this build's envelope (%d)", d->n_ee, MAXEE);
+    if (d->n_ee > 0 && (!d->ee_joint || !d->ee_offset)) return fail(SYSID_ERR_INVALID, "null end-effector array");
+    if (d->jtype[1] != SYSID_JT_FREEFLYER || d->parent[1] != 0)
+        return fail(SYSID_ERR_UNSUPPORTED, "joint 1 must be the free-flyer root (floating_base=True is the accelerated path)");
+    sysid_model* m = new (std::nothrow) sysid_model;
+    if (!m) return fail(SYSID_ERR_INVALID, "out of host memory");
+    std::memset(&m->dev, 0, sizeof(DevModel));
+    DevModel& M = m->dev;
+    M.njoints = d->njoints; M.nb = d->njoints - 1; M.n_ee = d->n_ee;
+    M.nv = 6 + (M.nb - 1); M.nq = 7 + (M.nb - 1); M.nd = M.nb - 1; M.nparams = 10 * M.nb;
+    for (int j = 0; j < d->njoints; ++j) {
+        M.parent[j] = d->parent[j];
+        M.jtype[j] = d->jtype[j];
+        for (int k = 0; k < 3; ++k) { M.axis[j][k] = d->axis[3 * j + k]; M.pp[j][k] = d->place_p[3 * j + k]; }
+        for (int k = 0; k < 9; ++k) M.pR[j][k] = d->place_R[9 * j + k];
+        if (j >= 2) {
+            if (d->jtype[j] < SYSID_JT_RX || d->jtype[j] > SYSID_JT_RU) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "joint %d: only revolute joints below the free-flyer root", j); }
+            if (d->parent[j] < 1 || d->parent[j] >= j) { delete m; return fail(SYSID_ERR_INVALID, "joint %d: parent %d breaks the depth-first numbering", j, d->parent[j]); }
+            if (d->jtype[j] == SYSID_JT_RU) {
+                const double nrm = std::sqrt(M.axis[j][0] * M.axis[j][0] + M.axis[j][1] * M.axis[j][1] + M.axis[j][2] * M.axis[j][2]);
+                if (!(std::fabs(nrm - 1.0) < 1e-9)) { delete m; return fail(SYSID_ERR_INVALID, "joint %d: axis is not unit length", j); }
+            }
+        }
+    }
+    for (int k = 0; k < 3; ++k) M.gravity[k] = d->gravity[k];
+    for (int k = 0; k < d->n_ee; ++k) {
+        const int jf = d->ee_joint[k];
+        if (jf < 1 || jf >= d->njoints) { delete m; return fail(SYSID_ERR_INVALID, "end effector %d: joint %d out of range", k, jf); }
+        M.ee_joint[k] = jf;
+        for (int e = 0; e < 3; ++e) M.ee_off[k][e] = d->ee_offset[3 * k + e];
+        int len = 0;
+        for (int c = jf; c > 1; c = M.parent[c]) {
+            if (len >= MAXCH) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "end effector %d: chain longer than %d joints", k, MAXCH); }
+            M.chain[k][len++] = c;
+        }
+        M.chain_len[k] = len;
+    }
+    for (int a = 0; a < d->n_ee; ++a)
+        for (int b = 0; b < d->n_ee; ++b) {
+            int ns = 0;
+            while (ns < M.chain_len[a] && ns < M.chain_len[b] &&
+                   M.chain[a][M.chain_len[a] - 1 - ns] == M.chain[b][M.chain_len[b] - 1 - ns]) ++ns;
+            M.nshared[a][b] = ns;
+        }
+    int rc = device_sm_count(&m->sm_count);
+    if (rc != SYSID_OK) { delete m; return rc; }
+    *out = m;
+    return SYSID_OK;
+}
+
+void sysid_model_destroy(sysid_model* model) { delete model; }
+
+int sysid_model_dims(const sysid_model* model, sysid_dims* out) {
+    if (!model || !out) return fail(SYSID_ERR_INVALID, "null argument");
+    const DevModel& M = model->dev;
+    out->nq = M.nq; out->nv = M.nv; out->nbodies = M.nb; out->ndof = M.nd; out->nparams = M.nparams;
+    out->ncols = M.nparams + 2 * M.nd; out->n_ee = M.n_ee;
+    return SYSID_OK;
+}
+
+int sysid_regressor_batch(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                          int64_t N, int64_t ld, double* Y_out, void* stream) {
+    if (!model || !q || !dq || !ddq || !Y_out) return fail(SYSID_ERR_INVALID, "null argument");
+    if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
+    if (N == 0) return SYSID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevModel& M = model->dev;
+    CUDA_TRY(cudaMemsetAsync(Y_out, 0, sizeof(double) * (size_t)N * M.nv * M.nparams, st));
+    int rc = opt_in_smem(sample_batch_kernel<0>, DBG_SMEM_BYTES);
+    if (rc) return rc;
+    BatchArgs a{};
+    a.io = make_io(q, dq, ddq, nullptr, nullptr, nullptr, ld);
+    a.N = N; a.friction = 0; a.Y = Y_out;
+    // the raw regressor does not depend on contacts: run with n_ee = 0 in a local copy of the model image,
+    // so the (null) contact channel is never read
+    DevModel Mloc = M;
+    Mloc.n_ee = 0;
+    const unsigned grid = (unsigned)((N + SB_SAMPLES - 1) / SB_SAMPLES);
+    sample_batch_kernel<0><<<grid, DBG_THREADS, DBG_SMEM_BYTES, st>>>(Mloc, a);
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+int sysid_projected_batch(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                          const double* tau, const double* contact, int64_t N, int64_t ld, int32_t friction,
+                          double* A_out, double* b_out, double* P_out, void* stream) {
+    if (!model || !q || !dq || !ddq || !tau || !A_out || !b_out) return fail(SYSID_ERR_INVALID, "null argument");
+    if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
+    if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
+    if (N == 0) return SYSID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = opt_in_smem(sample_batch_kernel<1>, DBG_SMEM_BYTES);
+    if (rc) return rc;
+    BatchArgs a{};
+    a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
+    a.N = N; a.friction = friction ? 1 : 0; a.A = A_out; a.b = b_out; a.P = P_out;
+    const unsigned grid = (unsigned)((N + SB_SAMPLES - 1) / SB_SAMPLES);
+    sample_batch_kernel<1><<<grid, DBG_THREADS, DBG_SMEM_BYTES, st>>>(model->dev, a);
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+size_t sysid_stats_len(const sysid_model* model, int32_t friction) {
+    if (!model) return 0;
+    const size_t c = (size_t)model->dev.nparams + (friction ? 2 * (size_t)model->dev.nd : 0);
+    return c * c + c + 2;
+}
+
+size_t sysid_gram_workspace_bytes(const sysid_model* model) {
+    if (!model) return 0;
+    return sizeof(double) * (size_t)model->sm_count * PARTIAL_DOUBLES;
+}
+
+size_t sysid_gram_from_stack_workspace_bytes(int32_t c) {
+    (void)c;
+    int sms = 0;
+    if (device_sm_count(&sms) != SYSID_OK) return 0;
+    return sizeof(double) * (size_t)sms * PARTIAL_DOUBLES;
+}
+
+int sysid_gram_accumulate(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                          const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
+                          int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+    if (!model || !q || !dq || !ddq || !tau || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
+    if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
+    if (N == 0) return SYSID_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const DevModel& M = model->dev;
+    const long long nsb = (N + SB_SAMPLES - 1) / SB_SAMPLES;
+    const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
+    if (workspace_bytes < sizeof(double) * (size_t)grid * PARTIAL_DOUBLES)
+        return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, sizeof(double) * (size_t)grid * PARTIAL_DOUBLES);
+    int rc = opt_in_smem(gram_fused_kernel, GRAM_SMEM_BYTES);
+    if (rc) return rc;
+    GramArgs a{};
+    a.io = make_io(q, dq, ddq, tau, contact, weights, ld);
+    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace;
+    gram_fused_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    CUDA_TRY(cudaGetLastError());
+    const int c = M.nparams + (friction ? 2 * M.nd : 0);
+    const int total = (c + 1) * (c + 2) / 2;
+    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, (double)M.nv, 0.0, stats,
+                                                             (long long*)info);
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+    if (!A || !b || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (c < 1 || c + 1 > CW) return fail(SYSID_ERR_UNSUPPORTED, "c = %d outside [1, %d]", c, CW - 1);
+    if (rows < 0) return fail(SYSID_ERR_INVALID, "bad rows");
+    if (rows == 0) return SYSID_OK;
+    int sms = 0;
+    int rc = device_sm_count(&sms);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nchunks = (rows + TILE_ROWS - 1) / TILE_ROWS;
+    const int grid = (int)(nchunks < sms ? nchunks : sms);
+    if (workspace_bytes < sizeof(double) * (size_t)grid * PARTIAL_DOUBLES) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+    const size_t smem = sizeof(double) * TILE_DOUBLES;
+    rc = opt_in_smem(gram_stack_kernel, smem);
+    if (rc) return rc;
+    StackArgs a{A, b, rows, c, (double*)workspace};
+    gram_stack_kernel<<<grid, GRAM_THREADS, smem, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    const int total = (c + 1) * (c + 2) / 2;
+    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, 0.0, (double)rows, stats, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+size_t sysid_predict_rmse_workspace_bytes(const sysid_model* model) {
+    if (!model) return 0;
+    return sizeof(double) * (size_t)model->sm_count * RMSE_PARTIAL;
+}
+
+int sysid_predict_rmse(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                       const double* tau, const double* contact, int64_t N, int64_t ld, const double* phi,
+                       double* out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!model || !q || !dq || !ddq || !tau || !phi || !out || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
+    if (N <= 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nsb = (N + SB_SAMPLES - 1) / SB_SAMPLES;
+    const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
+    if (workspace_bytes < sizeof(double) * (size_t)grid * RMSE_PARTIAL) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+    int rc = opt_in_smem(rmse_kernel, GRAM_SMEM_BYTES);
+    if (rc) return rc;
+    RmseArgs a{};
+    a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
+    a.N = N; a.phi = phi; a.partial = (double*)workspace;
+    rmse_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(model->dev, a);
+    CUDA_TRY(cudaGetLastError());
+    rmse_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, grid, model->dev.nd, N, out);
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ stage 3
+size_t sysid_sdp_workspace_bytes(int32_t num_links, int32_t ndof) { return sdp_workspace_bytes(num_links, ndof); }
+
+int sysid_sdp_solve(const sysid_sdp_desc* desc, const double* stats, int64_t stats_stride, int32_t batch,
+                    double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!desc || !stats || !x_out || !info_out || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    char msg[256] = "";
+    int rc = sdp_solve_launch(*desc, stats, stats_stride, batch, x_out, info_out, workspace, workspace_bytes,
+                              (cudaStream_t)stream, msg, sizeof(msg));
+    if (rc != SYSID_OK) return fail(rc, "%s", msg);
+    return SYSID_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,203 @@
+"""Device-level operators: thin, allocation-explicit wrappers over the C-ABI for torch CUDA tensors.
+
+Every function here launches hand-written sm_100a kernels through libsysid_b200.so on the current
+torch CUDA stream.  Inputs are channel-major fp64 CUDA tensors of shape (channels, N), exactly the
+arrays the reference's read_data produces (reference demo/solo_identification.py:9-33).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import FlatModel
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("system_identification_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chan(t, channels, name):
+    if t.dtype != torch.float64 or not t.is_cuda or t.dim() != 2 or t.shape[0] != channels or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a CUDA float64 tensor of shape ({channels}, N) with unit inner stride, got "
+                         f"{tuple(t.shape)} {t.dtype} {t.device}")
+    return t
+
+
+def to_device(a, device=None):
+    """numpy/torch (channels, N) of any float dtype -> contiguous CUDA fp64 (exact widening of float32 logs)."""
+    _require_cuda()
+    if isinstance(a, np.ndarray):
+        a = torch.from_numpy(np.ascontiguousarray(a))
+    return a.to(device=device or "cuda", dtype=torch.float64, non_blocking=True).contiguous()
+
+
+class DeviceModel:
+    """Owns the immutable library handle for one FlatModel (reference: the pinocchio model/data pair
+    built in SystemIdentification.__init__, src/sys_identification.py:16-22)."""
+
+    def __init__(self, flat: FlatModel):
+        _require_cuda()
+        self.flat = flat
+        self.lib = _lib.load()
+        self.handle = _lib.create_model(flat)
+        d = _lib.Dims()
+        _lib.check(self.lib.sysid_model_dims(self.handle, C.byref(d)))
+        self.nq, self.nv, self.nb, self.nd, self.nparams, self.n_ee = d.nq, d.nv, d.nbodies, d.ndof, d.nparams, d.n_ee
+        self._ws = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.sysid_model_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def ncols(self, friction=True):
+        return self.nparams + (2 * self.nd if friction else 0)
+
+    def stats_len(self, friction=True):
+        c = self.ncols(friction)
+        return c * c + c + 2
+
+    def _workspace(self, key, nbytes, device):
+        buf = self._ws.get((key, device))
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=device)
+            self._ws[(key, device)] = buf
+        return buf
+
+    # ---------------------------------------------------------------------------------- stage 1
+    def regressor_batch(self, q, dq, ddq):
+        """pin.computeJointTorqueRegressor for every column: returns (N, nv, 10*nb)."""
+        q = _chan(q, self.nq, "q"); dq = _chan(dq, self.nv, "dq"); ddq = _chan(ddq, self.nv, "ddq")
+        N = q.shape[1]
+        ld = self._common_ld(q, dq, ddq)
+        Y = torch.empty((N, self.nv, self.nparams), dtype=torch.float64, device=q.device)
+        _lib.check(self.lib.sysid_regressor_batch(self.handle, _ptr(q), _ptr(dq), _ptr(ddq), N, ld, _ptr(Y), _stream()))
+        return Y
+
+    def projected_batch(self, q, dq, ddq, tau, cnt, friction=True, want_P=False):
+        """Per-sample [P Y | P S^T diag(dq) | P S^T diag(sign dq)] (N, nv, c), P S^T tau (N, nv) and optionally P."""
+        q = _chan(q, self.nq, "q"); dq = _chan(dq, self.nv, "dq"); ddq = _chan(ddq, self.nv, "ddq")
+        tau = _chan(tau, self.nd, "tau"); cnt = _chan(cnt, self.n_ee, "contact")
+        N = q.shape[1]
+        ld = self._common_ld(q, dq, ddq, tau, cnt)
+        c = self.ncols(friction)
+        A = torch.empty((N, self.nv, c), dtype=torch.float64, device=q.device)
+        b = torch.empty((N, self.nv), dtype=torch.float64, device=q.device)
+        P = torch.empty((N, self.nv, self.nv), dtype=torch.float64, device=q.device) if want_P else None
+        _lib.check(self.lib.sysid_projected_batch(self.handle, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(tau), _ptr(cnt), N, ld,
+                                                  1 if friction else 0, _ptr(A), _ptr(b), _ptr(P), _stream()))
+        return (A, b, P) if want_P else (A, b)
+
+    # ---------------------------------------------------------------------------------- stage 2
+    def gram_accumulate(self, q, dq, ddq, tau, cnt, friction=True, weights=None, stats=None, info=None):
+        """Fused regressor -> projector -> Gram.  Returns stats = [G (c x c) | r (c) | s | n]; ADDS into `stats` if given."""
+        q = _chan(q, self.nq, "q"); dq = _chan(dq, self.nv, "dq"); ddq = _chan(ddq, self.nv, "ddq")
+        tau = _chan(tau, self.nd, "tau"); cnt = _chan(cnt, self.n_ee, "contact")
+        N = q.shape[1]
+        ld = self._common_ld(q, dq, ddq, tau, cnt)
+        if stats is None:
+            stats = torch.zeros(self.stats_len(friction), dtype=torch.float64, device=q.device)
+        if weights is not None and (weights.dtype != torch.float64 or weights.numel() != N or not weights.is_contiguous()):
+            raise ValueError("weights: expected contiguous float64 of length N")
+        nbytes = self.lib.sysid_gram_workspace_bytes(self.handle)
+        ws = self._workspace("gram", nbytes, q.device)
+        _lib.check(self.lib.sysid_gram_accumulate(self.handle, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(tau), _ptr(cnt), N, ld,
+                                                  _ptr(weights), 1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws),
+                                                  ws.numel(), _stream()))
+        return stats
+
+    def predict_rmse(self, q, dq, ddq, tau, cnt, phi):
+        """(total mean-square, per-joint RMSE) of reference print_tau_prediction_rmse (src/sys_identification.py:421-437)."""
+        q = _chan(q, self.nq, "q"); dq = _chan(dq, self.nv, "dq"); ddq = _chan(ddq, self.nv, "ddq")
+        tau = _chan(tau, self.nd, "tau"); cnt = _chan(cnt, self.n_ee, "contact")
+        N = q.shape[1]
+        ld = self._common_ld(q, dq, ddq, tau, cnt)
+        phi = phi.to(device=q.device, dtype=torch.float64).contiguous()
+        if phi.numel() != self.nparams:
+            raise ValueError(f"phi: expected {self.nparams} parameters")
+        out = torch.empty(1 + self.nd, dtype=torch.float64, device=q.device)
+        nbytes = self.lib.sysid_predict_rmse_workspace_bytes(self.handle)
+        ws = self._workspace("rmse", nbytes, q.device)
+        _lib.check(self.lib.sysid_predict_rmse(self.handle, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(tau), _ptr(cnt), N, ld, _ptr(phi),
+                                               _ptr(out), _ptr(ws), ws.numel(), _stream()))
+        return out
+
+    @staticmethod
+    def _common_ld(*ts):
+        ld = ts[0].stride(0)
+        N = ts[0].shape[1]
+        for t in ts:
+            if t.shape[1] != N:
+                raise ValueError("all sample arrays must have the same number of columns")
+            if t.stride(0) != ld:
+                raise ValueError("all sample arrays must share one leading dimension (slice them from equally-shaped parents)")
+        return ld
+
+
+def gram_from_stack(A, b, stats=None):
+    """stats of an already stacked system: A (rows, c), b (rows) CUDA fp64 (reference Solver(regressor, tau_vec, ...))."""
+    _require_cuda()
+    lib = _lib.load()
+    if A.dtype != torch.float64 or not A.is_cuda or A.dim() != 2 or not A.is_contiguous():
+        raise ValueError("A: expected contiguous CUDA float64 (rows, c)")
+    rows, c = A.shape
+    b = b.to(device=A.device, dtype=torch.float64).contiguous()
+    if b.numel() != rows:
+        raise ValueError("b: length must equal the rows of A")
+    if stats is None:
+        stats = torch.zeros(c * c + c + 2, dtype=torch.float64, device=A.device)
+    nbytes = lib.sysid_gram_from_stack_workspace_bytes(c)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    _lib.check(lib.sysid_gram_from_stack(_ptr(A), _ptr(b), rows, c, _ptr(stats), _ptr(ws), ws.numel(), _stream()))
+    return stats
+
+
+def sdp_solve(stats, num_links, ndof, phi_prior, ellipsoids, total_mass, lambda_reg=1e-1, tol=1e-10, max_iters=0,
+              reg_type="constant_pullback", epsilon=1e-6, batch=1):
+    """Persistent-kernel ADMM solve of reference Solver.solve_fully_consistent (src/solver.py:123-210).
+    stats: CUDA fp64, (batch, c*c+c+2) or flat for batch=1.  Returns (x (batch, c) CUDA, info numpy structured array)."""
+    _require_cuda()
+    lib = _lib.load()
+    if reg_type not in _lib.REG_TYPES:
+        raise ValueError(f"reg_type {reg_type!r} is not supported on this path")
+    c = 10 * num_links + 2 * ndof
+    slen = c * c + c + 2
+    stats = stats.contiguous()
+    if stats.dtype != torch.float64 or not stats.is_cuda or stats.numel() != batch * slen:
+        raise ValueError(f"stats: expected CUDA float64 with {batch}*{slen} elements")
+    phi0 = np.ascontiguousarray(np.asarray(phi_prior).astype(np.float64))
+    sa = np.ascontiguousarray(np.array([e["semi_axes"] for e in ellipsoids], dtype=np.float64).reshape(-1))
+    ce = np.ascontiguousarray(np.array([e["center"] for e in ellipsoids], dtype=np.float64).reshape(-1))
+    if phi0.size != 10 * num_links or sa.size != 3 * num_links or ce.size != 3 * num_links:
+        raise ValueError("phi_prior / bounding_ellipsoids do not match num_links")
+    d = _lib.SdpDesc()
+    d.num_links = num_links; d.ndof = ndof
+    d.phi_prior = phi0.ctypes.data_as(C.POINTER(C.c_double))
+    d.semi_axes = sa.ctypes.data_as(C.POINTER(C.c_double))
+    d.centers = ce.ctypes.data_as(C.POINTER(C.c_double))
+    d.total_mass = float(total_mass); d.lambda_reg = float(lambda_reg); d.reg_type = _lib.REG_TYPES[reg_type]
+    d.epsilon = float(epsilon); d.tol = float(tol); d.max_iters = int(max_iters)
+    x = torch.empty((batch, c), dtype=torch.float64, device=stats.device)
+    info = torch.zeros(batch * _lib.SDP_INFO_DTYPE.itemsize, dtype=torch.uint8, device=stats.device)
+    one = lib.sysid_sdp_workspace_bytes(num_links, ndof)
+    plan_bytes = 8 * 320 * num_links
+    nbytes = plan_bytes + (one - plan_bytes) * batch
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=stats.device)
+    _lib.check(lib.sysid_sdp_solve(C.byref(d), _ptr(stats), slen, batch, _ptr(x), _ptr(info), _ptr(ws), ws.numel(), _stream()))
+    info_np = info.cpu().numpy().view(_lib.SDP_INFO_DTYPE)
+    return x, info_np

@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's SystemIdentification class
+(reference src/sys_identification.py:10-490): same constructor, getters, per-sample producers and
+printers, so demo/solo_identification.py, demo/spot_identification.py and spot_identification.py
+run unmodified against `src.sys_identification` (a re-export of this module).
+
+What changes underneath: no pinocchio/urdf_parser_py/trimesh.  The URDF is flattened once on the
+host (urdf.py) and uploaded through the C-ABI; every regressor / projector / RMSE evaluation runs in
+the sm_100a kernels of libsysid_b200.so.  There is no CPU fallback for those.
+
+New, batched entry points (not in the reference): `identify`, `gram`, `tau_prediction_rmse`.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import yaml
+
+from .model import FlatModel
+from .urdf import load_robot
+
+# body.obj / torso_link_23dof_rev_1_0.STL are absent from the reference checkout (.MISSING_LARGE_BLOBS)
+MESH_FALLBACKS = {
+    "package://spot_description/meshes/base/visual/body.obj": "package://spot_description/meshes/base/collision/body_collision.obj",
+    "meshes/torso_link_23dof_rev_1_0.STL": "meshes/torso_link.STL",
+}
+
+
+class SystemIdentification(object):
+    def __init__(self, urdf_file, config_file, floating_base):
+        self._urdf_path = urdf_file
+        self._floating_base = floating_base
+        with open(config_file, "r") as file:
+            config = yaml.safe_load(file)
+        robot_config = config.get("robot", {})
+        # reference rule for mesh paths: <repo>/files/<package path> (src/sys_identification.py:255-257);
+        # here <repo>/files is the grand-parent directory of the URDF, which is the same place for the demos
+        files_root = os.path.dirname(os.path.dirname(os.path.abspath(urdf_file)))
+        flat = load_robot(urdf_file, robot_config, floating_base=floating_base, files_root=files_root,
+                          mesh_fallbacks=MESH_FALLBACKS)
+        self._init_from_flat(flat)
+
+    @classmethod
+    def from_flat_model(cls, flat: FlatModel):
+        """Build from a flattened descriptor (system_identification_b200/robots/*.json) instead of URDF+YAML."""
+        self = cls.__new__(cls)
+        self._urdf_path = None
+        self._floating_base = flat.floating_base
+        self._init_from_flat(flat)
+        return self
+
+    def _init_from_flat(self, flat: FlatModel):
+        self._flat = flat
+        self._device_model = None
+        self.nq = flat.nq
+        self.nv = flat.nv
+        self._base_dof = 6
+        self.joints_dof = self.nv - self._base_dof
+        self._S = np.zeros((self.joints_dof, self.nv))
+        self._S[:, self._base_dof:] = np.eye(self.joints_dof)
+        self._robot_name = flat.name
+        self._robot_mass = flat.robot_mass
+        self._link_names = list(flat.link_names)
+        self._end_eff_frame_names = list(flat.ee_names)
+        self._nb_ee = len(self._end_eff_frame_names)
+        self._num_inertial_params = 10
+        self._num_links = len(self._link_names)
+        if self._num_links != flat.nbodies:
+            raise ValueError(f"len(link_names) = {self._num_links} must equal the number of moving bodies {flat.nbodies}")
+        self._phi_prior = np.zeros((self._num_inertial_params * self._num_links), dtype=np.float32)
+        self.B_v = np.eye(self.joints_dof)
+        self.B_c = np.eye(self.joints_dof)
+        self._bounding_ellipsoids = list(flat.ellipsoids)
+        self._last_key = None
+        self._last_tau_key = None
+        self._last_out = None
+
+    # ------------------------------------------------------------------ device plumbing
+    @property
+    def flat_model(self):
+        return self._flat
+
+    @property
+    def device_model(self):
+        if self._device_model is None:
+            from .ops import DeviceModel
+            self._device_model = DeviceModel(self._flat)
+        return self._device_model
+
+    def _one_sample(self, q, dq, ddq, tau, cnt):
+        """Per-sample compat path: one launch of the projected-batch kernel with N = 1.  The demos call
+        get_proj_regressor_torque and get_proj_friction_regressors with the same sample back to back;
+        the second call is served from the first one's result."""
+        import torch
+        from .ops import to_device
+        q = np.asarray(q); dq = np.asarray(dq); ddq = np.asarray(ddq); cnt = np.asarray(cnt)
+        tau = np.zeros(self.joints_dof) if tau is None else np.asarray(tau)
+        key = (q.tobytes(), dq.tobytes(), ddq.tobytes(), cnt.tobytes())
+        if self._last_key == key and self._last_tau_key == tau.tobytes():
+            return self._last_out
+        dm = self.device_model
+        packed = np.concatenate([q.astype(np.float64), dq.astype(np.float64), ddq.astype(np.float64),
+                                 tau.astype(np.float64), cnt.astype(np.float64)])
+        dev = to_device(packed.reshape(-1, 1))
+        o = 0
+        parts = []
+        for n in (self.nq, self.nv, self.nv, self.joints_dof, self._nb_ee):
+            parts.append(dev[o:o + n]); o += n
+        A, b, P = dm.projected_batch(*parts, friction=True, want_P=True)
+        out = (A[0].cpu().numpy(), b[0].cpu().numpy(), P[0].cpu().numpy())
+        self._last_key, self._last_tau_key, self._last_out = key, tau.tobytes(), out
+        return out
+
+    # ------------------------------------------------------------------ reference getters
+    def get_robot_mass(self):
+        return self._robot_mass
+
+    def get_num_links(self):
+        return self._num_links
+
+    def get_bounding_ellipsoids(self):
+        return self._bounding_ellipsoids
+
+    def get_phi_prior(self):
+        # float32 vector in the reference's per-link order [m, h_x, h_y, h_z, I_xx, I_xy, I_xz, I_yy, I_yz, I_zz]
+        self._phi_prior[:] = self._flat.phi_prior
+        return self._phi_prior
+
+    def get_physical_consistency(self, phi):
+        """Minimum eigenvalues of I_bar, the 6x6 spatial inertia, the 4x4 pseudo inertia and the CoM matrix, and
+        tr(J Q), per link (reference src/sys_identification.py:324-389; float32 matrices as there)."""
+        out = ([], [], [], [], [])
+        for idx in range(self._num_links):
+            p = np.asarray(phi[10 * idx:10 * idx + 10])
+            m, h = p[0], np.array(p[1:4])
+            I_bar = np.array([[p[4], p[5], p[6]], [p[5], p[7], p[8]], [p[6], p[8], p[9]]])
+            ell = self._bounding_ellipsoids[idx]
+            s, c = np.asarray(ell["semi_axes"]), np.asarray(ell["center"])
+            hx = np.array([[0, -h[2], h[1]], [h[2], 0, -h[0]], [-h[1], h[0], 0]])
+            I6 = np.zeros((6, 6), dtype=np.float32)
+            I6[0:3, 0:3] = I_bar; I6[0:3, 3:] = hx; I6[3:, 0:3] = hx.T; I6[3:, 3:] = m * np.eye(3)
+            J = np.zeros((4, 4), dtype=np.float32)
+            J[:3, :3] = 0.5 * np.trace(I_bar) * np.eye(3) - I_bar; J[:3, 3] = h; J[3, :3] = h; J[3, 3] = m
+            Qd = np.linalg.inv(np.diag(s) ** 2)
+            Qf = np.zeros((4, 4), dtype=np.float32)
+            Qf[:3, :3] = Qd; Qf[:3, 3] = Qd @ c; Qf[3, :3] = Qd @ c; Qf[3, 3] = 1 - c @ Qd @ c
+            Cm = np.zeros((4, 4), dtype=np.float32)
+            Cm[0, 0] = m; Cm[0, 1:] = h - m * c; Cm[1:, 0] = h - m * c; Cm[1:, 1:] = m * np.diag(s) ** 2
+            out[0].append(np.min(np.linalg.eigvals(I_bar)))
+            out[1].append(np.min(np.linalg.eigvals(I6)))
+            out[2].append(np.min(np.linalg.eigvals(J)))
+            out[3].append(np.min(np.linalg.eigvals(Cm)))
+            out[4].append(np.trace(J @ Qf))
+        return out
+
+    def get_full_regressor_force(self, q, dq, ddq, tau, ee_force, cnt):
+        raise NotImplementedError(
+            "get_full_regressor_force (reference src/sys_identification.py:391-399) has no caller in the reference and "
+            "needs measured foot forces that no .dat layout carries; it is outside the accelerated path (SURVEY.md #11)")
+
+    # ------------------------------------------------------------------ per-sample producers (reference :401-418)
+    def get_proj_regressor_torque(self, q, dq, ddq, tau, cnt):
+        A, b, _ = self._one_sample(q, dq, ddq, tau, cnt)
+        return A[:, :self._num_inertial_params * self._num_links].copy(), b.copy()
+
+    def get_proj_friction_regressors(self, q, dq, ddq, cnt):
+        # the friction blocks do not depend on tau: reuse the launch of the matching regressor call if there was one
+        key = (np.asarray(q).tobytes(), np.asarray(dq).tobytes(), np.asarray(ddq).tobytes(), np.asarray(cnt).tobytes())
+        A = self._last_out[0] if key == self._last_key else self._one_sample(q, dq, ddq, None, cnt)[0]
+        p, d = self._num_inertial_params * self._num_links, self.joints_dof
+        return A[:, p:p + d].copy(), A[:, p + d:p + 2 * d].copy()
+
+    # ------------------------------------------------------------------ batched entry points (new)
+    def _upload(self, q, dq, ddq, tau, cnt):
+        from .ops import to_device
+        return tuple(to_device(np.asarray(a)) for a in (q, dq, ddq, tau, cnt))
+
+    def gram(self, q, dq, ddq, tau, cnt, friction=True, weights=None):
+        """Fused regressor+projector+Gram over all columns of the five (channels x N) arrays -> device stats tensor."""
+        dev = self._upload(q, dq, ddq, tau, cnt)
+        return self.device_model.gram_accumulate(*dev, friction=friction, weights=weights)
+
+    def tau_prediction_rmse(self, q, dq, ddq, torque, cnt, phi):
+        """(total, per-joint) with the reference's formulas: total = mean_i ||e_i||^2 (no root), per joint = RMSE."""
+        import torch
+        dev = self._upload(q, dq, ddq, torque, cnt)
+        out = self.device_model.predict_rmse(*dev, torch.as_tensor(np.asarray(phi, dtype=np.float64))).cpu().numpy()
+        return float(out[0]), out[1:].copy()
+
+    def identify(self, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=1000, reg_type="constant_pullback",
+                 friction=True, return_info=False):
+        """End-to-end identification of one log: what the demo scripts' main() computes between read_data and the
+        printers (reference demo/solo_identification.py:67-88), in two kernel launches + one solve."""
+        from .identify import identify as _identify
+        return _identify(self, q, dq, ddq, tau, cnt, lambda_reg=lambda_reg, tol=tol, max_iters=max_iters,
+                         reg_type=reg_type, friction=friction, return_info=return_info)
+
+    # ------------------------------------------------------------------ printers (reference :421-490)
+    def print_tau_prediction_rmse(self, q, dq, ddq, torque, cnt, phi, param_name):
+        rmse_total, joint_tau_rmse = self.tau_prediction_rmse(q, dq, ddq, torque, cnt, phi)
+        print("\n--------------------Torque Prediction Errors--------------------")
+        print(f'RMSE for joint torques prediction using {param_name} parameters: total= {rmse_total}\nper_joints={joint_tau_rmse}')
+
+    _ROWS = (("mass (kg)", None), ("c_x (m)", 0), ("c_y (m)", 1), ("c_z (m)", 2),
+             ("I_xx (kg.m^2)", 0), ("I_xy (kg.m^2)", 1), ("I_xz (kg.m^2)", 2),
+             ("I_yy (kg.m^2)", 3), ("I_yz (kg.m^2)", 4), ("I_zz (kg.m^2)", 5))
+
+    def print_inertial_params(self, prior, identified):
+        self._cell_width = 13
+        w = self._cell_width
+        totals = [0, 0]
+        header = "|" + "|".join(f"{t:<{w}}" for t in ("Parameter", "A priori", "Identified", "Change", "error %")) + "|"
+        for i in range(self._num_links):
+            title = f'Inertial Parameters of "{self._link_names[i]}"'
+            left = (69 - len(title)) // 2
+            print(f'\n{"-" * left} {title} {"-" * (69 - len(title) - left)}')
+            print(header)
+            k = 10 * i
+            masses = (prior[k], identified[k])
+            coms = (prior[k + 1:k + 4] / masses[0], identified[k + 1:k + 4] / masses[1])
+            inert = (prior[k + 4:k + 10], identified[k + 4:k + 10])
+            for r, (label, sel) in enumerate(self._ROWS):
+                src = masses if r == 0 else (coms if r < 4 else inert)
+                a, b = (src[0], src[1]) if sel is None else (src[0][sel], src[1][sel])
+                self._print_table(label, a, b)
+            totals[0] += masses[0]
+            totals[1] += masses[1]
+        print(f'\nRobot total mass: {totals[0]} ---- Identified total mass: {totals[1]}')
+
+    def _print_table(self, description, prior, ident):
+        precision = 6
+        w = self._cell_width
+        change = ident - prior
+        error = np.divide(change, np.abs(prior), where=prior != 0) * 100
+        error = np.where(np.abs(prior) <= 1e-8, np.nan, error)
+        print(f'|{description:<{w}}|{prior:>{w}.{precision}f}|{ident:>{w}.{precision}f}|{change:>{w}.{precision}f}|{error:>{w}.{1}f}|')
