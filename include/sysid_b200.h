@@ -133,16 +133,17 @@ typedef struct sysid_sdp_desc {
     double lambda_reg;            /* reference default 1e-1 */
     int32_t reg_type;             /* SYSID_REG_* */
     double epsilon;               /* LMI margin, reference 1e-6 */
-    double tol;                   /* reference default 1e-10 (MOSEK rel-gap); here the ADMM residual tolerance scale */
-    int32_t max_iters;            /* ADMM iteration cap (0 = library default) */
+    double tol;                   /* reference default 1e-10 (MOSEK rel-gap); here KKT residuals are driven below 10 * tol (relative) */
+    int32_t max_iters;            /* cap on Newton steps (reference: MOSEK iterations, default 1000; 0 = library default) */
 } sysid_sdp_desc;
 
 typedef struct sysid_sdp_info {
-    int32_t status;               /* 0 optimal, SYSID_ERR_NOT_OPTIMAL otherwise */
-    int32_t iterations;
-    int32_t refactorizations;
+    int32_t status;               /* 0 optimal, 1 optimal-inaccurate (residuals within 1e3 x tolerance at the iteration cap;
+                                     accepted like cvxpy's OPTIMAL_INACCURATE), SYSID_ERR_NOT_OPTIMAL otherwise */
+    int32_t iterations;           /* Newton steps */
+    int32_t refactorizations;     /* augmented-Lagrangian (multiplier) updates */
     int32_t reserved;
-    double primal_residual, dual_residual, rho, objective;
+    double primal_residual, dual_residual, rho, objective;   /* rho = final penalty sigma */
     double min_eig_J, min_eig_C;  /* smallest eigenvalue over links of J+eps I and C+eps I at the solution */
     double mass_residual;
 } sysid_sdp_info;

@@ -164,14 +164,17 @@ def _barrier_terms(prob, x, extra_t=None):
     if extra_t is not None:
         F = F + extra_t * np.eye(4)
         lin = lin + extra_t
+    if not (np.all(np.isfinite(F)) and np.all(np.isfinite(lin))) or np.any(lin <= 0):
+        return None
     try:
         Ls = np.linalg.cholesky(F)
+        Finv = np.linalg.inv(F)
     except np.linalg.LinAlgError:
         return None
-    if np.any(lin <= 0):
+    dg = np.diagonal(Ls, axis1=1, axis2=2)
+    if not np.all(np.isfinite(dg)) or np.any(dg <= 0):
         return None
-    val = -2.0 * np.sum(np.log(np.diagonal(Ls, axis1=1, axis2=2))) - np.sum(np.log(lin))
-    Finv = np.linalg.inv(F)
+    val = -2.0 * np.sum(np.log(dg)) - np.sum(np.log(lin))
     nt = c + (1 if extra_t is not None else 0)
     grad = np.zeros(nt); Hs = np.zeros((nt, nt))
     # LMI part: d/dx_a = -tr(Finv T_a); d2 = tr(Finv T_a Finv T_b)
@@ -230,6 +233,8 @@ def _newton_centering(fun, x, aeq, beq, max_newton=60, tol=1e-13):
                 return x, steps, False
         x = xn
         steps += 1
+    else:
+        return x, steps, False
     return x, steps, True
 
 
@@ -258,7 +263,7 @@ def _scaled_problem(prob: SdpProblem, T):
                       num_links=prob.num_links, ndof=prob.ndof)
 
 
-def solve_barrier(prob: SdpProblem, x0=None, mu=8.0, t0=1.0, gap_tol=1e-13, verbose=False):
+def solve_barrier(prob: SdpProblem, x0=None, mu=8.0, t0=1.0, gap_tol=1e-12, verbose=False):
     """Returns (x, info).  Raises ValueError('The problem did not solve to optimality.') like
     src/solver.py:209-210 when no strictly feasible point exists."""
     c = prob.nx
@@ -308,6 +313,7 @@ def solve_barrier(prob: SdpProblem, x0=None, mu=8.0, t0=1.0, gap_tol=1e-13, verb
             y = z[:c]
     m_total = 4 * sp.lmi_T.shape[0] + sp.Ain.shape[0]
     tt = t0
+    y_good, t_good = None, None
     while True:
         def fun(yy, tt=tt):
             out = _barrier_terms(sp, yy)
@@ -315,11 +321,20 @@ def solve_barrier(prob: SdpProblem, x0=None, mu=8.0, t0=1.0, gap_tol=1e-13, verb
                 return None
             val, grad, Hs, _, _ = out
             return (tt * (0.5 * yy @ sp.H @ yy - sp.g @ yy) + val, tt * (sp.H @ yy - sp.g) + grad, tt * sp.H + Hs)
-        y, k, ok = _newton_centering(fun, y, sp.aeq, sp.beq)
+        y_new, k, ok = _newton_centering(fun, y, sp.aeq, sp.beq)
         n_newton += k
         if verbose:
-            print(f"  barrier t={tt:.3e} newton={k} gap={m_total / tt:.3e}")
-        if m_total / tt < gap_tol:
+            print(f"  barrier t={tt:.3e} newton={k} ok={ok} gap={m_total / tt:.3e}")
+        if not ok:
+            # fp64 ran out on the central path (active LMIs make F^-1 ~ t): keep the last centred point
+            if y_good is None:
+                raise ValueError("The problem did not solve to optimality.")
+            y, tt = y_good, t_good
+            break
+        y = y_new
+        y_good, t_good = y, tt
+        fval = abs(0.5 * y @ sp.H @ y - sp.g @ y + sp.const)
+        if m_total / tt < gap_tol * max(1.0, fval):
             break
         tt *= mu
     x = T @ y

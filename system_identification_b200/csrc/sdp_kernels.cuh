@@ -4,11 +4,13 @@
 //   s.t.   J(phi_i) + eps I >= 0,  C(phi_i) + eps I >= 0  (4x4 LMIs),  m_i >= 0,  tr(J(phi_i) Q_i) >= 0,
 //          sum_i m_i = total_mass,  b_v >= 0,  b_c >= 0.
 //
-// Method: ADMM on the block-Jacobi-scaled problem (x = T y, T_i = chol(H_ii)^-T per link, 1/sqrt(H_kk) for friction;
-// cond(H) ~1e14 raw -> ~20 scaled).  Every LMI is an svec'd 10-row block with ONE scale factor (keeps the PSD cone
-// invariant), so the z-update is 2L independent 4x4 eigen-projections (cyclic Jacobi) plus clamps; the y-update is one
-// dense mat-vec with W = K^-1 - (K^-1 a)(K^-1 a)^T / (a^T K^-1 a), K = H~ + rho A^T A, held in shared memory
-// (the single mass equality is eliminated exactly).  rho is re-balanced from the residuals and K re-inverted in place.
+// Method: semismooth-Newton augmented Lagrangian on the block-Jacobi-scaled problem (x = T y, T_i = chol(H_ii)^-T per
+// link, 1/sqrt(H_kk) for friction; cond(H) ~1e14 raw -> ~20-250 scaled).  Every LMI is an svec'd 10-row block with ONE
+// scale factor (keeps the PSD cone invariant).  Each function evaluation is 2L independent 4x4 eigen-decompositions
+// (cyclic Jacobi) plus clamps; each Newton step inverts K = H~ + sigma A^T D A in shared memory (D = Clarke Jacobian of the
+// cone projection, block diagonal) with the single mass equality eliminated exactly.  A first version used plain ADMM
+// (the north-star sketch): it needs 1e2 iterations when no LMI is active but 1e4..>4e4 when one is (Spot/G1 synthetic
+// logs), whereas this method takes 7..70 Newton steps on the same problems (profiles/README.md).
 #pragma once
 #include <cmath>
 #include <cstdio>
@@ -28,8 +30,8 @@ constexpr int SDP_MAXC = 10 * SDP_MAXL + 2 * SDP_MAXD;     // 154
 constexpr int SDP_ROWS_PER_LINK = 22;                      // 10 (J) + 10 (C) + m>=0 + tr(JQ)>=0
 constexpr int SDP_MAXM = SDP_ROWS_PER_LINK * SDP_MAXL + 2 * SDP_MAXD;   // 310
 constexpr int SDP_PLAN_LINK = 320;                         // doubles per link in the plan: M(100) Jmap(100) Cmap(100) q(10) Mphi0(10)
-constexpr int SDP_CHECK = 25;                              // residual check period (iterations)
-constexpr int SDP_DEFAULT_MAX_ITERS = 40000;
+constexpr int SDP_DEFAULT_MAX_ITERS = 1000;                 // Newton steps (the reference's default max_iters)
+constexpr int SDP_STATUS_INACCURATE = 1;                  // residuals within 1e3 x tolerance at the iteration cap (cvxpy's OPTIMAL_INACCURATE)
 
 struct SdpParams {
     int L, nd, c, m;
@@ -184,49 +186,25 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
     return s;
 }
 
-// PSD projection of a symmetric 4x4 given/returned in svec form (off-diagonals carry sqrt(2)); also returns min eigenvalue.
-__device__ inline double project_psd4(const double* in, double* out, bool write) {
-    const double IS2 = 0.70710678118654752440, SQ2 = 1.41421356237309504880;
-    double a[4][4];
+// Eigen-decomposition of a symmetric 4x4 given in svec form (off-diagonals carry sqrt(2)) by cyclic Jacobi.
+// ev[e] = eigenvalue e, V[4 * row + e] = component `row` of eigenvector e.
+__device__ inline void eig_sym4(const double* in, double ev[4], double V[16]) {
+    const double IS2 = 0.70710678118654752440;
+    double a[4][4], v[4][4];
     a[0][0] = in[0]; a[1][0] = a[0][1] = in[1] * IS2; a[1][1] = in[2];
     a[2][0] = a[0][2] = in[3] * IS2; a[2][1] = a[1][2] = in[4] * IS2; a[2][2] = in[5];
     a[3][0] = a[0][3] = in[6] * IS2; a[3][1] = a[1][3] = in[7] * IS2; a[3][2] = a[2][3] = in[8] * IS2; a[3][3] = in[9];
-    // quick accept: Cholesky succeeds with strictly positive pivots => already in the cone
-    {
-        bool pd = true;
-        double l[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                double s = a[i][j];
-#pragma unroll
-                for (int k = 0; k < j; ++k) s -= l[i][k] * l[j][k];
-                if (i == j) { if (s > 0.0) l[i][i] = sqrt(s); else { pd = false; l[i][i] = 1.0; } }
-                else l[i][j] = s / l[j][j];
-            }
-        }
-        if (pd && !write) {
-            // caller only wants to know the cone membership cheaply; min eigenvalue bound not needed
-        }
-        if (pd && write) {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) out[k] = in[k];
-            return 1.0;   // positive => interior
-        }
-    }
-    double v[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
-    for (int sweep = 0; sweep < 30; ++sweep) {
+    for (int sweep = 0; sweep < 12; ++sweep) {
         double off = 0.0, tot = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) { tot += a[i][j] * a[i][j]; if (i != j) off += a[i][j] * a[i][j]; }
-        if (off <= 1e-32 * tot) break;
+        if (off <= 1e-29 * tot) break;
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
@@ -245,21 +223,12 @@ __device__ inline double project_psd4(const double* in, double* out, bool write)
                 }
             }
     }
-    double mn = fmin(fmin(a[0][0], a[1][1]), fmin(a[2][2], a[3][3]));
-    if (write) {
-        double w[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) w[k] = fmax(a[k][k], 0.0);
-        const int SI[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, SJ[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+    for (int k = 0; k < 4; ++k) {
+        ev[k] = a[k][k];
 #pragma unroll
-        for (int r = 0; r < 10; ++r) {
-            double s = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) s += w[k] * v[SI[r]][k] * v[SJ[r]][k];
-            out[r] = (SI[r] == SJ[r]) ? s : s * SQ2;
-        }
+        for (int r = 0; r < 4; ++r) V[4 * r + k] = v[r][k];
     }
-    return mn;
 }
 
 // In-place inverse of the SPD matrix A (n x n, leading dimension ld, in shared memory) by Gauss-Jordan.
@@ -284,7 +253,7 @@ __device__ inline void spd_inverse_inplace(double* A, int n, int ld, double* col
 
 // ------------------------------------------------------------------------------------------------ the solver
 __global__ void __launch_bounds__(SDP_THREADS, 1)
-sdp_admm_kernel(const SdpParams prm, const double* __restrict__ plan, const double* __restrict__ stats_all,
+sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const double* __restrict__ stats_all,
                 double* __restrict__ ws_all, double* __restrict__ x_out_all, sysid_sdp_info* __restrict__ info_all) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -297,20 +266,26 @@ sdp_admm_kernel(const SdpParams prm, const double* __restrict__ plan, const doub
     double* Tm = Am + (size_t)L * SDP_ROWS_PER_LINK * 10;   // L*100, T_i row-major (upper triangular)
     double* tf = Tm + (size_t)L * 100;                 // 2nd friction scales
     // shared memory carve-up
-    double* W = sm;                                    // c*c
+    double* W = sm;                                    // c*c  Newton matrix, inverted in place
     double* gt = W + c * c;                            // c   scaled linear term
-    double* w0 = gt + c;                               // c
-    double* at = w0 + c;                               // c   scaled equality vector
+    double* at = gt + c;                               // c   scaled equality vector
     double* y = at + c;                                // c
-    double* rhs = y + c;                               // c
-    double* z = rhs + c;                               // m
-    double* lam = z + m;                               // m
+    double* yt = y + c;                                // c   trial point / K^-1 grad
+    double* hy = yt + c;                               // c   Hs y
+    double* grad = hy + c;                             // c
+    double* dy = grad + c;                             // c   Newton direction (also the pivot-column buffer of the inverse)
+    double* Ka = dy + c;                               // c   K^-1 at, then Hs dy
+    double* rhs = Ka + c;                              // c   x = T y at the end
+    double* lam = rhs + c;                             // m   multiplier
     double* c0 = lam + m;                              // m
-    double* tv = c0 + m;                               // m  scratch (t1, then v + lam/rho)
-    double* zprev = tv + m;                            // m
-    double* red = zprev + m;                           // 32
+    double* gy = c0 + m;                               // m   g(y) = A y + c0 at the last evaluated point
+    double* wv = gy + m;                               // m   lam - sigma g(y)
+    double* pw = wv + m;                               // m   Proj_K(wv)
+    double* tv = pw + m;                               // m   scratch
+    double* evals = tv + m;                            // 2L*4
+    double* evecs = evals + 8 * L;                     // 2L*16 (row-major V, columns = eigenvectors)
+    double* red = evecs + 32 * L;                      // 32
     __shared__ double s_scalar[8];
-    __shared__ int s_flag;
 
     const double n_rows = stats[(size_t)c * c + c + 1];
     const double inv_n = 1.0 / n_rows;
@@ -433,53 +408,6 @@ sdp_admm_kernel(const SdpParams prm, const double* __restrict__ plan, const doub
     for (int k = tid; k < 2 * nd; k += SDP_THREADS) c0[L * SDP_ROWS_PER_LINK + k] = 0.0;
     __syncthreads();
 
-    double rho = 1.0;
-    const double alpha = 1.6;
-    int refacts = 0;
-
-    // K^-1 and the equality elimination; result in W, w0
-    auto factor = [&](double rho_) {
-        for (int e = tid; e < c * c; e += SDP_THREADS) {
-            const int a = e / c, b = e - a * c;
-            double s = Hs[e];
-            if (a < np && b < np) {
-                const int ia = a / 10;
-                if (ia == b / 10) {
-                    const double* Ai = Am + (size_t)ia * SDP_ROWS_PER_LINK * 10;
-                    const int la = a - 10 * ia, lb = b - 10 * ia;
-                    double t = 0.0;
-#pragma unroll
-                    for (int r = 0; r < SDP_ROWS_PER_LINK; ++r) t += Ai[10 * r + la] * Ai[10 * r + lb];
-                    s += rho_ * t;
-                }
-            } else if (a == b) {
-                s += rho_;
-            }
-            W[e] = s;
-        }
-        __syncthreads();
-        spd_inverse_inplace(W, c, c, rhs, tid);
-        // Ka = W at (into rhs), denom = at . Ka
-        for (int a = warp; a < c; a += SDP_THREADS / 32) {
-            double s = 0.0;
-            for (int b = lane; b < c; b += 32) s += W[a * c + b] * at[b];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) rhs[a] = s;
-        }
-        __syncthreads();
-        double part = 0.0;
-        for (int a = tid; a < c; a += SDP_THREADS) part += at[a] * rhs[a];
-        const double denom = block_sum(part, red, tid);
-        const double inv_d = 1.0 / denom;
-        for (int e = tid; e < c * c; e += SDP_THREADS) {
-            const int a = e / c, b = e - a * c;
-            W[e] -= rhs[a] * rhs[b] * inv_d;
-        }
-        for (int a = tid; a < c; a += SDP_THREADS) w0[a] = rhs[a] * prm.total_mass * inv_d;
-        __syncthreads();
-    };
-
     auto apply_A = [&](const double* yy, int r) -> double {   // (A yy)[r] + c0[r]
         if (r < L * SDP_ROWS_PER_LINK) {
             const int i = r / SDP_ROWS_PER_LINK;
@@ -502,102 +430,215 @@ sdp_admm_kernel(const SdpParams prm, const double* __restrict__ plan, const doub
         }
         return t[L * SDP_ROWS_PER_LINK + (a - np)];
     };
-    auto project = [&](const double* in, double* out) {
-        // LMI blocks: 2L tasks spread over warps' lane 0; linear rows: clamps
-        for (int k = warp; k < 2 * L; k += SDP_THREADS / 32) {
-            if (lane == 0) {
-                const int i = k >> 1, off = i * SDP_ROWS_PER_LINK + 10 * (k & 1);
-                project_psd4(in + off, out + off, true);
-            }
-        }
-        for (int r = tid; r < m; r += SDP_THREADS) {
-            bool lin = (r >= L * SDP_ROWS_PER_LINK) || ((r % SDP_ROWS_PER_LINK) >= 20);
-            if (lin) out[r] = fmax(in[r], 0.0);
-        }
-    };
+    // =========================== semismooth-Newton augmented Lagrangian ===========================================
+    //   g(y) = A y + c0 in K (product of PSD(4) cones in svec form and half-lines);  multiplier lam in K.
+    //   L_sigma(y) = f(y) + (|Proj_K(lam - sigma g(y))|^2 - |lam|^2) / (2 sigma),   f(y) = 1/2 y^T Hs y - gt^T y
+    //   inner: Newton on L_sigma restricted to at^T y = total_mass, generalized Hessian Hs + sigma A^T D A with
+    //          D in the Clarke Jacobian of Proj_K (from the 4x4 eigen-decompositions);  outer: lam <- Proj_K(lam - sigma g(y)).
+    double sigma = 1.0;
+    const double eps = fmax(10.0 * prm.tol, 1e-11);
 
-    factor(rho);
-    // init: y = 0-ish start: z = Proj(c0) , lam = 0
-    for (int r = tid; r < m; r += SDP_THREADS) { lam[r] = 0.0; tv[r] = c0[r]; }
-    __syncthreads();
-    project(tv, z);
-    __syncthreads();
-
-    int iters = 0, status = SYSID_ERR_NOT_OPTIMAL;
-    double rp = 0.0, rd = 0.0;
-    int last_refactor = 0;
-    const double eps_rel = fmax(10.0 * prm.tol, 1e-11), eps_abs = eps_rel * 1e-2;
-    while (iters < prm.max_iters) {
-        const bool check = ((iters + 1) % SDP_CHECK) == 0;
-        // (a) rhs = gt + A^T (rho (z - c0) - lam)
-        for (int r = tid; r < m; r += SDP_THREADS) { tv[r] = rho * (z[r] - c0[r]) - lam[r]; if (check) zprev[r] = z[r]; }
+    // evaluate at the point yy: gy = A yy + c0, w = lam - sigma gy, eigen-decompose the LMI blocks of w, pw = Proj_K(w).
+    // Returns |pw|^2 (block-uniform).
+    auto evaluate = [&](const double* yy) -> double {
+        for (int r = tid; r < m; r += SDP_THREADS) { const double gv = apply_A(yy, r); gy[r] = gv; wv[r] = lam[r] - sigma * gv; }
         __syncthreads();
-        for (int a = tid; a < c; a += SDP_THREADS) rhs[a] = gt[a] + apply_At(tv, a);
-        __syncthreads();
-        // (b) y = W rhs + w0
-        for (int a = warp; a < c; a += SDP_THREADS / 32) {
-            double s = 0.0;
-            for (int b = lane; b < c; b += 32) s += W[a * c + b] * rhs[b];
+        {   // 2L eigen-problems: lanes 0 and 1 of each warp work in lockstep on blocks `warp` and `warp + 16`
+            const int k = warp + (SDP_THREADS / 32) * lane;
+            if (lane < 2 && k < 2 * L) {
+                const int off = (k >> 1) * SDP_ROWS_PER_LINK + 10 * (k & 1);
+                double ev[4], V[16];
+                eig_sym4(wv + off, ev, V);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) y[a] = s + w0[a];
-        }
-        __syncthreads();
-        // (c) v = alpha (A y + c0) + (1 - alpha) z ; tv = v + lam / rho ; keep A y + c0 in rhs-sized? reuse: store Ay in zprev? no
-        double l_rp = 0.0, l_ay = 0.0;
-        for (int r = tid; r < m; r += SDP_THREADS) {
-            const double ay = apply_A(y, r);
-            const double v = alpha * ay + (1.0 - alpha) * z[r];
-            tv[r] = v + lam[r] / rho;
-            // stash v in lam temporarily? need lam; keep v recomputable: lam_new = lam + rho (v - z_new) = rho (tv - z_new)
-            if (check) { l_ay += ay * ay; }
-        }
-        __syncthreads();
-        // (d) z = Proj(tv) ; lam = rho (tv - z)
-        project(tv, z);
-        __syncthreads();
-        for (int r = tid; r < m; r += SDP_THREADS) lam[r] = rho * (tv[r] - z[r]);
-        ++iters;
-        if (check) {
-            double l_z = 0.0, l_lamn = 0.0;
-            for (int r = tid; r < m; r += SDP_THREADS) {
-                const double ay = apply_A(y, r);
-                const double d = ay - z[r];
-                l_rp += d * d; l_z += z[r] * z[r];
-                tv[r] = z[r] - zprev[r];
-            }
-            __syncthreads();
-            double l_rd = 0.0;
-            for (int a = tid; a < c; a += SDP_THREADS) {
-                const double d = rho * apply_At(tv, a);
-                const double al = apply_At(lam, a);
-                l_rd += d * d; l_lamn += al * al;
-            }
-            const double s_rp = block_sum(l_rp, red, tid), s_ay = block_sum(l_ay, red, tid), s_z = block_sum(l_z, red, tid);
-            const double s_rd = block_sum(l_rd, red, tid), s_ln = block_sum(l_lamn, red, tid);
-            rp = sqrt(s_rp); rd = sqrt(s_rd);
-            const double pn = fmax(sqrt(s_ay), sqrt(s_z)), dn = sqrt(s_ln);
-            const double tol_p = eps_abs * sqrt((double)m) + eps_rel * pn;
-            const double tol_d = eps_abs * sqrt((double)c) + eps_rel * dn;
-            if (rp <= tol_p && rd <= tol_d) { status = SYSID_OK; break; }
-            if (iters - last_refactor >= 2 * SDP_CHECK) {
-                const double rpn = rp / fmax(pn, 1e-300), rdn = rd / fmax(dn, 1e-300);
-                if (rpn > 5.0 * rdn || rdn > 5.0 * rpn) {
-                    double f = sqrt(rpn / fmax(rdn, 1e-300));
-                    f = fmin(fmax(f, 0.1), 10.0);
-                    const double new_rho = fmin(fmax(rho * f, 1e-6), 1e6);
-                    if (new_rho != rho) {
-                        rho = new_rho;
-                        __syncthreads();
-                        factor(rho);
-                        ++refacts;
-                        last_refactor = iters;
-                    }
+                for (int e = 0; e < 4; ++e) evals[4 * k + e] = ev[e];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) evecs[16 * k + e] = V[e];
+                const double SQ2 = 1.41421356237309504880;
+                const int SI[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, SJ[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+#pragma unroll
+                for (int r = 0; r < 10; ++r) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) s += fmax(ev[e], 0.0) * V[4 * SI[r] + e] * V[4 * SJ[r] + e];
+                    pw[off + r] = (SI[r] == SJ[r]) ? s : s * SQ2;
                 }
             }
         }
+        for (int r = tid; r < m; r += SDP_THREADS) {
+            const bool lin = (r >= L * SDP_ROWS_PER_LINK) || ((r % SDP_ROWS_PER_LINK) >= 20);
+            if (lin) pw[r] = fmax(wv[r], 0.0);
+        }
         __syncthreads();
+        double part = 0.0;
+        for (int r = tid; r < m; r += SDP_THREADS) part += pw[r] * pw[r];
+        return block_sum(part, red, tid);
+    };
+
+    // W <- (Hs + sigma A^T D A)^-1 at the current evaluation point (uses wv / evals / evecs)
+    auto newton_matrix_inverse = [&]() {
+        for (int e = tid; e < c * c; e += SDP_THREADS) W[e] = Hs[e];
+        __syncthreads();
+        // one warp per link: lane a (< 10) owns column a of the link's 10 x 10 diagonal block
+        for (int i = warp; i < L; i += SDP_THREADS / 32) {
+            double colacc[10];
+#pragma unroll
+            for (int b = 0; b < 10; ++b) colacc[b] = 0.0;
+            const int a = (lane < 10) ? lane : 0;
+            const double* Ai = Am + (size_t)i * SDP_ROWS_PER_LINK * 10;
+            for (int which = 0; which < 2; ++which) {
+                const int k = 2 * i + which;
+                const double* V = evecs + 16 * k;
+                const double* ev = evals + 4 * k;
+                // Ht = V^T smat(A_k[:, a]) V   (symmetric 4x4, 10 unique entries in svec order WITHOUT the sqrt2 weights)
+                double Hm[4][4];
+                {
+                    const double IS2 = 0.70710678118654752440;
+                    const double* col = Ai + (size_t)(10 * which) * 10 + a;
+                    Hm[0][0] = col[0]; Hm[1][0] = Hm[0][1] = col[10] * IS2; Hm[1][1] = col[20];
+                    Hm[2][0] = Hm[0][2] = col[30] * IS2; Hm[2][1] = Hm[1][2] = col[40] * IS2; Hm[2][2] = col[50];
+                    Hm[3][0] = Hm[0][3] = col[60] * IS2; Hm[3][1] = Hm[1][3] = col[70] * IS2; Hm[3][2] = Hm[2][3] = col[80] * IS2; Hm[3][3] = col[90];
+                }
+                double HV[4][4], Ht[10];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) HV[r][q] = Hm[r][0] * V[q] + Hm[r][1] * V[4 + q] + Hm[r][2] * V[8 + q] + Hm[r][3] * V[12 + q];
+                const int SI[10] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3}, SJ[10] = {0, 0, 1, 0, 1, 2, 0, 1, 2, 3};
+#pragma unroll
+                for (int r = 0; r < 10; ++r) {
+                    const int p = SI[r], q = SJ[r];
+                    double s = V[p] * HV[0][q] + V[4 + p] * HV[1][q] + V[8 + p] * HV[2][q] + V[12 + p] * HV[3][q];
+                    // weight: Omega_pq (x2 for off-diagonal pairs), folded in as sqrt so that the block is Ht_a . Ht_b
+                    const double lp = ev[p], lq = ev[q];
+                    double om;
+                    if (fabs(lp - lq) > 1e-14 * fmax(1.0, fmax(fabs(lp), fabs(lq)))) om = (fmax(lp, 0.0) - fmax(lq, 0.0)) / (lp - lq);
+                    else om = (lp > 0.0) ? 1.0 : 0.0;
+                    Ht[r] = s * sqrt(om * ((p == q) ? 1.0 : 2.0));
+                }
+#pragma unroll
+                for (int b = 0; b < 10; ++b) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int r = 0; r < 10; ++r) s += Ht[r] * __shfl_sync(0xffffffffu, Ht[r], b);
+                    colacc[b] += s;
+                }
+            }
+#pragma unroll
+            for (int rr = 20; rr < 22; ++rr) {
+                if (wv[i * SDP_ROWS_PER_LINK + rr] > 0.0) {
+                    const double va = Ai[10 * rr + a];
+#pragma unroll
+                    for (int b = 0; b < 10; ++b) colacc[b] += va * Ai[10 * rr + b];
+                }
+            }
+            if (lane < 10) {
+#pragma unroll
+                for (int b = 0; b < 10; ++b) W[(size_t)(10 * i + b) * c + 10 * i + a] += sigma * colacc[b];
+            }
+        }
+        for (int k = tid; k < 2 * nd; k += SDP_THREADS)
+            if (wv[L * SDP_ROWS_PER_LINK + k] > 0.0) W[(size_t)(np + k) * c + np + k] += sigma;
+        __syncthreads();
+        spd_inverse_inplace(W, c, c, dy, tid);
+    };
+
+    auto matvec_smem = [&](const double* Mx, const double* v, double* out) {      // out = Mx v, Mx c x c in shared memory
+        for (int a = warp; a < c; a += SDP_THREADS / 32) {
+            double s = 0.0;
+            for (int b = lane; b < c; b += 32) s += Mx[a * c + b] * v[b];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) out[a] = s;
+        }
+        __syncthreads();
+    };
+    auto dot_c = [&](const double* u, const double* v) -> double {
+        double part = 0.0;
+        for (int a = tid; a < c; a += SDP_THREADS) part += u[a] * v[a];
+        return block_sum(part, red, tid);
+    };
+
+    // ---- start: y = minimum-norm point on the mass equality, lam = 0 -------------------------------------------------
+    const double ata = dot_c(at, at);
+    for (int a = tid; a < c; a += SDP_THREADS) y[a] = at[a] * prm.total_mass / ata;
+    for (int r = tid; r < m; r += SDP_THREADS) lam[r] = 0.0;
+    __syncthreads();
+    for (int a = warp; a < c; a += SDP_THREADS / 32) {       // hy = Hs y  (Hs in global memory / L2)
+        double s = 0.0;
+        for (int b = lane; b < c; b += 32) s += Hs[(size_t)a * c + b] * y[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) hy[a] = s;
     }
+    __syncthreads();
+    const double gnorm = sqrt(dot_c(gt, gt));
+
+    int iters = 0, refacts = 0, status = SYSID_ERR_NOT_OPTIMAL;
+    double rp = 1.0, rd = 1.0, kkt_prev = 1.0;
+    double pw2 = evaluate(y);
+    for (int outer = 0; outer < 200 && iters < prm.max_iters; ++outer) {
+        const double tol_in = fmax(0.5 * eps * (1.0 + gnorm), 1e-2 * fmin(1.0, kkt_prev));
+        for (int inner = 0; inner < 40 && iters < prm.max_iters; ++inner) {
+            // grad = hy - gt - A^T pw ; projected onto the null space of at
+            for (int a = tid; a < c; a += SDP_THREADS) grad[a] = hy[a] - gt[a] - apply_At(pw, a);
+            __syncthreads();
+            const double nu = dot_c(at, grad) / ata;
+            double part = 0.0;
+            for (int a = tid; a < c; a += SDP_THREADS) { const double d = grad[a] - nu * at[a]; part += d * d; }
+            rd = sqrt(block_sum(part, red, tid));
+            if (rd <= tol_in) break;
+            newton_matrix_inverse();
+            matvec_smem(W, grad, yt);                      // yt = K^-1 grad
+            matvec_smem(W, at, Ka);                        // Ka = K^-1 at
+            const double a_v1 = dot_c(at, yt), a_Ka = dot_c(at, Ka);
+            for (int a = tid; a < c; a += SDP_THREADS) dy[a] = -(yt[a] - Ka[a] * (a_v1 / a_Ka));
+            __syncthreads();
+            for (int a = warp; a < c; a += SDP_THREADS / 32) {    // Ka <- Hs dy (reuse buffer)
+                double s = 0.0;
+                for (int b = lane; b < c; b += 32) s += Hs[(size_t)a * c + b] * dy[b];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) Ka[a] = s;
+            }
+            __syncthreads();
+            const double gd = dot_c(grad, dy), q2 = dot_c(dy, Ka);
+            double lin = 0.0;
+            {
+                double part2 = 0.0;
+                for (int a = tid; a < c; a += SDP_THREADS) part2 += (hy[a] - gt[a]) * dy[a];
+                lin = block_sum(part2, red, tid);
+            }
+            const double val0 = pw2 / (2.0 * sigma);          // f(y) cancels on both sides of the Armijo test
+            double t = 1.0;
+            bool accepted = false;
+            for (int ls = 0; ls < 40; ++ls) {
+                for (int a = tid; a < c; a += SDP_THREADS) yt[a] = y[a] + t * dy[a];
+                __syncthreads();
+                const double pw2_t = evaluate(yt);
+                const double val_t = t * lin + 0.5 * t * t * q2 + pw2_t / (2.0 * sigma);
+                if (val_t <= val0 + 1e-4 * t * gd + 1e-14 * (fabs(val0) + 1.0)) { pw2 = pw2_t; accepted = true; break; }
+                t *= 0.5;
+            }
+            ++iters;
+            if (!accepted) { pw2 = evaluate(y); break; }      // no descent at fp64 resolution: hand over to the multiplier update
+            for (int a = tid; a < c; a += SDP_THREADS) { y[a] = yt[a]; hy[a] += t * Ka[a]; }
+            __syncthreads();
+        }
+        // multiplier update lam <- Proj_K(lam - sigma g(y)) = pw ; KKT residual |lam_new - lam| / sigma
+        double part = 0.0, pg = 0.0;
+        for (int r = tid; r < m; r += SDP_THREADS) { const double d = pw[r] - lam[r]; part += d * d; pg += gy[r] * gy[r]; }
+        __syncthreads();
+        rp = sqrt(block_sum(part, red, tid)) / sigma;
+        const double gyn = sqrt(block_sum(pg, red, tid));
+        for (int r = tid; r < m; r += SDP_THREADS) lam[r] = pw[r];
+        ++refacts;
+        __syncthreads();
+        if (rp <= eps * (1.0 + gyn) && rd <= eps * (1.0 + gnorm)) { status = SYSID_OK; break; }
+        if (rp > 0.25 * kkt_prev) sigma = fmin(sigma * 10.0, 1e6);
+        kkt_prev = rp;
+        pw2 = evaluate(y);
+    }
+    if (status != SYSID_OK && rp <= 1e3 * eps * (1.0 + gnorm) && rd <= 1e3 * eps * (1.0 + gnorm)) status = SDP_STATUS_INACCURATE;
     __syncthreads();
     // ---- output: x = T y, diagnostics ----------------------------------------------------------------------------------
     double* x_out = x_out_all + (size_t)prob * c;
@@ -627,33 +668,31 @@ sdp_admm_kernel(const SdpParams prm, const double* __restrict__ plan, const doub
     for (int i = tid; i < L; i += SDP_THREADS) mpart += rhs[10 * i];
     const double msum = block_sum(mpart, red, tid);
     // min eigenvalues of J + eps I and C + eps I at x (unscaled): evaluate the raw svec maps
-    if (tid == 0) { s_scalar[0] = 1e300; s_scalar[1] = 1e300; }
-    __syncthreads();
     if (tid < 2 * L) {
         const int i = tid >> 1, which = tid & 1;
         const double* mp = plan + (size_t)i * SDP_PLAN_LINK + (which ? 200 : 100);
-        double sv[10], dummy[10];
+        double sv[10], ev4[4], V4[16];
         for (int r = 0; r < 10; ++r) {
             double s = (r == 0 || r == 2 || r == 5 || r == 9) ? prm.eps : 0.0;
             for (int a = 0; a < 10; ++a) s += mp[10 * r + a] * rhs[10 * i + a];
             sv[r] = s;
         }
-        // force the Jacobi path by asking for the eigenvalue without the quick accept: subtract nothing, call with write=false
-        const double mn = project_psd4(sv, dummy, false);
-        // atomicMin on doubles via CAS on the bit pattern is overkill here: serialise through shared memory
-        for (int t = 0; t < 2 * L; ++t) {
-            if (t == tid) s_scalar[which] = fmin(s_scalar[which], mn);
-            __syncwarp();
-        }
+        eig_sym4(sv, ev4, V4);
+        tv[tid] = fmin(fmin(ev4[0], ev4[1]), fmin(ev4[2], ev4[3]));
+    }
+    __syncthreads();
+    if (tid == 0) {
+        double mj = 1e300, mc = 1e300;
+        for (int t = 0; t < 2 * L; ++t) { if (t & 1) mc = fmin(mc, tv[t]); else mj = fmin(mj, tv[t]); }
+        s_scalar[0] = mj; s_scalar[1] = mc;
     }
     __syncthreads();
     if (tid == 0) {
         sysid_sdp_info& info = info_all[prob];
         info.status = status; info.iterations = iters; info.refactorizations = refacts; info.reserved = 0;
-        info.primal_residual = rp; info.dual_residual = rd; info.rho = rho; info.objective = obj;
+        info.primal_residual = rp; info.dual_residual = rd; info.rho = sigma; info.objective = obj;
         info.min_eig_J = s_scalar[0]; info.min_eig_C = s_scalar[1]; info.mass_residual = msum - prm.total_mass;
     }
-    (void)s_flag;
 }
 
 inline int sdp_solve_launch(const sysid_sdp_desc& d, const double* stats, int64_t stats_stride, int32_t batch,
@@ -686,10 +725,10 @@ inline int sdp_solve_launch(const sysid_sdp_desc& d, const double* stats, int64_
     prm.total_mass = d.total_mass; prm.eps = d.epsilon; prm.const_reg = const_reg; prm.tol = d.tol > 0 ? d.tol : 1e-10;
     prm.max_iters = d.max_iters > 0 ? d.max_iters : SDP_DEFAULT_MAX_ITERS;
     prm.stats_stride = stats_stride; prm.ws_stride = ws_n;
-    const size_t smem = sizeof(double) * ((size_t)prm.c * prm.c + 5 * (size_t)prm.c + 5 * (size_t)prm.m + 32);
-    e = cudaFuncSetAttribute(sdp_admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = sizeof(double) * ((size_t)prm.c * prm.c + 9 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + 32);
+    e = cudaFuncSetAttribute(sdp_alm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { snprintf(msg, msglen, "smem opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
-    sdp_admm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, dplan + plan_n, x_out, info_out);
+    sdp_alm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, dplan + plan_n, x_out, info_out);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msglen, "sdp launch failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
     return SYSID_OK;

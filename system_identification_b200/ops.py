@@ -169,7 +169,7 @@ def gram_from_stack(A, b, stats=None):
 
 def sdp_solve(stats, num_links, ndof, phi_prior, ellipsoids, total_mass, lambda_reg=1e-1, tol=1e-10, max_iters=0,
               reg_type="constant_pullback", epsilon=1e-6, batch=1):
-    """Persistent-kernel ADMM solve of reference Solver.solve_fully_consistent (src/solver.py:123-210).
+    """Persistent-kernel (semismooth-Newton augmented Lagrangian) solve of reference Solver.solve_fully_consistent (src/solver.py:123-210).
     stats: CUDA fp64, (batch, c*c+c+2) or flat for batch=1.  Returns (x (batch, c) CUDA, info numpy structured array)."""
     _require_cuda()
     lib = _lib.load()

@@ -3,14 +3,14 @@ methods, so the demos' `Solver(Y_proj, tau_proj, num_links, phi_prior, total_mas
 B_v=..., B_c=...).solve_fully_consistent()` runs unmodified against `src.solver`.
 
 No cvxpy, no MOSEK: the stacked system is reduced to its Gram statistics on the GPU
-(sysid_gram_from_stack) and the LMI-constrained fit runs as a persistent ADMM kernel (sysid_sdp_solve).
+(sysid_gram_from_stack) and the LMI-constrained fit runs as one persistent semismooth-Newton augmented-Lagrangian kernel (sysid_sdp_solve).
 `Solver.from_stats` skips the stack entirely (used by the fused identify() path).
 """
 from __future__ import annotations
 
 import numpy as np
 
-ADMM_ITERS_PER_IPM_ITER = 40   # the reference's max_iters counts MOSEK interior-point iterations (default 1000)
+NEWTON_STEPS_PER_IPM_ITER = 1   # the reference's max_iters caps MOSEK interior-point iterations; here it caps Newton steps
 
 
 class _Value:
@@ -106,11 +106,12 @@ class Solver():
             raise ValueError("reg_type 'entropic' is marked non-converging in the reference (src/solver.py:164-172) and is not supported")
         stats = self._device_stats()
         x, info = sdp_solve(stats, self._num_links, self.ndof, self._phi_prior, self._bounding_ellipsoids, self.total_mass,
-                            lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * ADMM_ITERS_PER_IPM_ITER,
+                            lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER,
                             reg_type=reg_type)
         self.info = {k: info[0][k].item() for k in info.dtype.names}
-        self._problem = _Value("optimal" if self.info["status"] == 0 else "not_optimal")
-        if self.info["status"] != 0:
+        # 0 = optimal, 1 = optimal_inaccurate (accepted, as the reference accepts cp.OPTIMAL_INACCURATE, src/solver.py:206)
+        self._problem = _Value({0: "optimal", 1: "optimal_inaccurate"}.get(self.info["status"], "not_optimal"))
+        if self.info["status"] not in (0, 1):
             print("The problem did not solve to optimality. Status:", self._problem.value, self.info)
             raise ValueError("The problem did not solve to optimality.")
         x = x[0].cpu().numpy()
