@@ -211,12 +211,18 @@ def _newton_centering(fun, x, aeq, beq, max_newton=60, tol=1e-13):
     steps = 0
     for _ in range(max_newton):
         out = fun(x)
-        assert out is not None, "iterate left the domain"
+        if out is None:
+            return x, steps, False
         val, grad, Hs = out
         K = np.zeros((n + 1, n + 1))
         K[:n, :n] = Hs; K[:n, n] = aeq; K[n, :n] = aeq
         rhs = np.concatenate([-grad, [beq - aeq @ x]])
-        sol = np.linalg.solve(K, rhs)
+        try:
+            sol = np.linalg.solve(K, rhs)
+        except np.linalg.LinAlgError:
+            return x, steps, False
+        if not np.all(np.isfinite(sol)):
+            return x, steps, False
         dx = sol[:n]
         lam2 = float(dx @ Hs @ dx)
         feas_eq = abs(beq - aeq @ x) <= 1e-13 * max(1.0, abs(beq))
@@ -388,3 +394,114 @@ def solve_fully_consistent(A, b, num_links, phi_prior, total_mass, bounding_elli
     x, info = solve_barrier(prob, x0)
     L = num_links
     return x[:10 * L], x[10 * L:10 * L + ndof], x[10 * L + ndof:], info
+
+
+# ------------------------------------------------------------------ second, independent solve: SSN augmented Lagrangian
+# The barrier method above stalls near gap ~1e-8 in fp64 when an LMI is active (F^-1 ~ t).  polish_alm restarts from
+# any point and drives the KKT residuals of the SAME problem to ~1e-10 with a semismooth-Newton augmented-Lagrangian
+# iteration (numpy, dense).  Tests use barrier-vs-ALM agreement as the oracle's own accuracy estimate.
+_SV_IJ = [(0, 0), (1, 0), (1, 1), (2, 0), (2, 1), (2, 2), (3, 0), (3, 1), (3, 2), (3, 3)]
+_SQ2 = np.sqrt(2.0)
+
+
+def _svec(F):
+    return np.array([F[i, j] * (1.0 if i == j else _SQ2) for (i, j) in _SV_IJ])
+
+
+def _smat(v):
+    F = np.zeros((4, 4))
+    for r, (i, j) in enumerate(_SV_IJ):
+        F[i, j] = F[j, i] = v[r] / (1.0 if i == j else _SQ2)
+    return F
+
+
+def solve_alm(prob: SdpProblem, x0=None, tol=1e-10, max_newton=400, verbose=False):
+    """Returns (x, info) with info = {'kkt', 'dual_residual', 'newton_steps', 'sigma', 'objective'}."""
+    c = prob.nx
+    T = _scaling(prob)
+    H = T.T @ prob.H @ T; g = T.T @ prob.g; a = T.T @ prob.aeq; beq = prob.beq
+    K = prob.lmi_T.shape[0]; mlin = prob.Ain.shape[0]; m = 10 * K + mlin
+    A = np.zeros((m, c)); c0 = np.zeros(m)
+    for k in range(K):
+        idx = prob.lmi_idx[k]
+        Mk = np.array([[prob.lmi_T[k][b_][i, j] * (1.0 if i == j else _SQ2) for b_ in range(10)] for (i, j) in _SV_IJ])
+        A[10 * k:10 * k + 10][:, idx] = Mk @ T[np.ix_(idx, idx)]
+        c0[10 * k:10 * k + 10] = _svec(prob.lmi_F0[k])
+    A[10 * K:] = prob.Ain @ T; c0[10 * K:] = prob.bin
+    for k in range(K):
+        sl = slice(10 * k, 10 * k + 10)
+        sc = 1.0 / np.sqrt((A[sl] ** 2).sum() / 10)
+        A[sl] *= sc; c0[sl] *= sc
+    for r in range(10 * K, m):
+        sc = 1.0 / np.linalg.norm(A[r])
+        A[r] *= sc; c0[r] *= sc
+
+    def project(w):
+        out = w.copy(); eig = []
+        for k in range(K):
+            lam, V = np.linalg.eigh(_smat(w[10 * k:10 * k + 10]))
+            out[10 * k:10 * k + 10] = _svec((V * np.maximum(lam, 0)) @ V.T); eig.append((lam, V))
+        out[10 * K:] = np.maximum(w[10 * K:], 0)
+        return out, eig
+
+    def hess_term(eig, w):
+        Hh = np.zeros((c, c))
+        for k in range(K):
+            lam, V = eig[k]; lp = np.maximum(lam, 0)
+            Om = np.zeros((4, 4))
+            for i in range(4):
+                for j in range(4):
+                    if abs(lam[i] - lam[j]) > 1e-14 * max(1.0, abs(lam[i]), abs(lam[j])):
+                        Om[i, j] = (lp[i] - lp[j]) / (lam[i] - lam[j])
+                    else:
+                        Om[i, j] = 1.0 if lam[i] > 0 else 0.0
+            idx = prob.lmi_idx[k]
+            Ht = [V.T @ _smat(A[10 * k:10 * k + 10, col]) @ V for col in idx]
+            for ia, ca in enumerate(idx):
+                for ib, cb in enumerate(idx):
+                    Hh[ca, cb] += np.sum(Om * Ht[ia] * Ht[ib])
+        act = (w[10 * K:] > 0).astype(float)
+        Al = A[10 * K:]
+        return Hh + Al.T @ (act[:, None] * Al)
+
+    y = np.linalg.solve(T, np.asarray(x0, dtype=np.float64)) if x0 is not None else a * beq / (a @ a)
+    y = y + a * (beq - a @ y) / (a @ a)
+    lam = np.zeros(m); sigma = 1.0; n_newton = 0; kkt_prev = 1.0
+    gnorm = np.linalg.norm(g); kkt = gn = np.inf
+    for outer in range(200):
+        tol_in = max(0.5 * tol * (1 + gnorm), 1e-2 * min(1.0, kkt_prev))
+        for inner in range(40):
+            w = lam - sigma * (A @ y + c0); pw, eig = project(w)
+            grad = H @ y - g - A.T @ pw
+            pg = grad - a * (a @ grad) / (a @ a)
+            gn = np.linalg.norm(pg)
+            if gn <= tol_in or n_newton >= max_newton:
+                break
+            Kin = np.linalg.inv(H + sigma * hess_term(eig, w))
+            v1 = Kin @ grad; Ka = Kin @ a
+            dy = -(v1 - Ka * (a @ v1) / (a @ Ka))
+            val0 = pw @ pw / (2 * sigma); lin = (H @ y - g) @ dy; q2 = dy @ H @ dy; gd = grad @ dy
+            t = 1.0; ok = False
+            for _ in range(40):
+                pwt, _e = project(lam - sigma * (A @ (y + t * dy) + c0))
+                if t * lin + 0.5 * t * t * q2 + pwt @ pwt / (2 * sigma) <= val0 + 1e-4 * t * gd + 1e-14 * (abs(val0) + 1):
+                    ok = True; break
+                t *= 0.5
+            n_newton += 1
+            if not ok:
+                break
+            y = y + t * dy
+        gy = A @ y + c0
+        lam_new, _e = project(lam - sigma * gy)
+        kkt = np.linalg.norm(lam_new - lam) / sigma
+        lam = lam_new
+        if verbose:
+            print(f"  alm outer {outer} sigma {sigma:.0e} newton {n_newton} kkt {kkt:.2e} dual {gn:.2e}")
+        if (kkt <= tol * (1 + np.linalg.norm(gy)) and gn <= tol * (1 + gnorm)) or n_newton >= max_newton:
+            break
+        if kkt > 0.25 * kkt_prev:
+            sigma = min(sigma * 10, 1e6)
+        kkt_prev = kkt
+    x = T @ y
+    return x, {"kkt": float(kkt), "dual_residual": float(gn), "newton_steps": n_newton, "sigma": sigma,
+               "objective": float(objective(prob, x))}

@@ -1,0 +1,266 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (ctypes -> libsysid_b200.so), against the oracle on
+the same seeded inputs, against the committed golden fixtures, and -- at BASELINE.json's full sizes -- through
+size-independent properties.  Tolerances: regressor 1e-10 relative (north_star), Gram 1e-12 relative Frobenius
+(SURVEY section 8d), identified parameters 1e-4 relative, torque-prediction RMSE 0.5 %."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+TOL_Y = 1e-10          # max-abs entry error / max-abs entry, per sample (north_star)
+TOL_GRAM = 1e-12       # relative Frobenius
+TOL_PHI = 1e-4         # global l2 and per-link-block l2, relative
+TOL_RMSE = 5e-3
+
+
+def _dev(flat):
+    from system_identification_b200.ops import DeviceModel
+    return DeviceModel(flat)
+
+
+def _up(data):
+    from system_identification_b200.ops import to_device
+    return tuple(to_device(a) for a in data)
+
+
+def _loaded_native():
+    with open("/proc/self/maps") as f:
+        return "libsysid_b200.so" in f.read()
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_regressor_vs_oracle_and_golden(name):
+    flat, data = H.small_log(name, 48)
+    g = np.load(os.path.join(H.GOLDEN_DIR, f"{name}_N48.npz"))
+    assert np.array_equal(g["q"], data[0])                         # same seeded inputs as the fixture
+    dm = _dev(flat)
+    q, dq, ddq, tau, cnt = _up((g["q"], g["dq"], g["ddq"], g["tau"], g["cnt"]))
+    Y = dm.regressor_batch(q, dq, ddq).cpu().numpy()
+    assert _loaded_native()
+    Yo, _, _, _ = H.oracle_blocks(flat, tuple(a[:, :12] for a in (g["q"], g["dq"], g["ddq"], g["tau"], g["cnt"])))
+    for i in range(12):
+        assert np.abs(Y[i] - Yo[i]).max() <= TOL_Y * np.abs(Yo[i]).max()
+    assert np.array_equal(Y[:12] == 0, Yo == 0)                    # same structural zeros
+    assert np.abs(Y[:6] - g["Y"]).max() <= TOL_Y * np.abs(g["Y"]).max()
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_projected_blocks_vs_golden(name):
+    flat = H.flat_model(name)
+    g = np.load(os.path.join(H.GOLDEN_DIR, f"{name}_N48.npz"))
+    dm = _dev(flat)
+    dev = _up((g["q"], g["dq"], g["ddq"], g["tau"], g["cnt"]))
+    A, b, P = dm.projected_batch(*dev, friction=True, want_P=True)
+    A, b, P = A.cpu().numpy(), b.cpu().numpy(), P.cpu().numpy()
+    assert np.abs(P - g["P"]).max() <= 1e-12
+    assert np.abs(P - np.transpose(P, (0, 2, 1))).max() <= 1e-14
+    nv = flat.nv
+    assert np.abs(A[:4].reshape(4 * nv, -1) - g["A_first"]).max() <= TOL_Y * np.abs(g["A_first"]).max()
+    assert np.abs(b.reshape(-1) - g["b"]).max() <= TOL_Y * np.abs(g["b"]).max()
+    # without friction columns
+    A2, b2 = dm.projected_batch(*dev, friction=False)
+    assert A2.shape[-1] == 130 and torch.equal(A2, torch.as_tensor(A[..., :130]).cuda())
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_fused_gram_vs_golden_and_stack_path(name):
+    from system_identification_b200.ops import gram_from_stack
+    flat = H.flat_model(name)
+    g = np.load(os.path.join(H.GOLDEN_DIR, f"{name}_N48.npz"))
+    dm = _dev(flat)
+    dev = _up((g["q"], g["dq"], g["ddq"], g["tau"], g["cnt"]))
+    c = 154
+    G, r, s, n = H.split_stats(dm.gram_accumulate(*dev).cpu().numpy(), c)
+    assert H.rel(G, g["G"]) <= TOL_GRAM and H.rel(r, g["r"]) <= TOL_GRAM and abs(s - g["s"]) <= TOL_GRAM * g["s"]
+    assert n == g["n"] == 48 * 18 and np.array_equal(G, G.T)
+    # compat path: Gram of the per-sample blocks stacked on the device == fused Gram
+    A, b = dm.projected_batch(*dev, friction=True)
+    G2, r2, s2, n2 = H.split_stats(gram_from_stack(A.reshape(-1, c).contiguous(), b.reshape(-1)).cpu().numpy(), c)
+    assert H.rel(G2, G) <= TOL_GRAM and H.rel(r2, r) <= TOL_GRAM and n2 == n
+    # no-friction variant: 130 columns, tau column right after the body columns
+    G3, r3, s3, n3 = H.split_stats(dm.gram_accumulate(*dev, friction=False).cpu().numpy(), 130)
+    assert H.rel(G3, g["G"][:130, :130]) <= TOL_GRAM and H.rel(r3, g["r"][:130]) <= TOL_GRAM and abs(s3 - s) <= 1e-12 * s
+
+
+def test_gram_edge_cases_ragged_empty_accumulate_weights_nan():
+    flat, data = H.small_log("solo12", 101, seed=41)             # 101 = 3 super-batches + ragged tail, not a multiple of 4
+    dm = _dev(flat)
+    dev = _up(data)
+    full = dm.gram_accumulate(*dev)
+    # streaming accumulation over uneven chunks equals one call (the call ADDS into stats)
+    acc = torch.zeros_like(full)
+    for lo, hi in [(0, 1), (1, 34), (34, 34), (34, 101)]:
+        if hi > lo:
+            dm.gram_accumulate(*(a[:, lo:hi] for a in dev), stats=acc)
+    assert H.rel(acc.cpu().numpy(), full.cpu().numpy()) <= 1e-13
+    # integer weights == repeating samples
+    w = torch.zeros(101, dtype=torch.float64, device="cuda"); w[[3, 50, 100]] = torch.tensor([2.0, 1.0, 3.0], dtype=torch.float64, device="cuda")
+    ws = dm.gram_accumulate(*dev, weights=w).cpu().numpy()
+    idx = [3, 3, 50, 100, 100, 100]
+    rep = dm.gram_accumulate(*(a[:, idx].contiguous() for a in dev)).cpu().numpy()
+    assert H.rel(ws, rep) <= 1e-13
+    # a NaN sample is skipped and counted, the rest is unchanged
+    bad = [a.clone() for a in dev]
+    bad[1][4, 7] = float("nan")
+    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    st = dm.gram_accumulate(*bad, info=info).cpu().numpy()
+    keep = [i for i in range(101) if i != 7]
+    ref = dm.gram_accumulate(*(a[:, keep].contiguous() for a in dev)).cpu().numpy()
+    assert info.cpu().tolist() == [0, 1] and np.all(np.isfinite(st)) and H.rel(st, ref) <= 1e-13
+    # all-flight and all-stance contact patterns, contact state 2 (quirk Q5)
+    q, dq, ddq, tau, cnt = data
+    for pattern in (np.zeros_like(cnt), np.ones_like(cnt), 2 * np.ones_like(cnt)):
+        d2 = (q[:, :8], dq[:, :8], ddq[:, :8], tau[:, :8], pattern[:, :8])
+        _, Po, Ao, bo = H.oracle_blocks(flat, d2)
+        _, _, P = dm.projected_batch(*_up(d2), want_P=True)
+        assert np.abs(P.cpu().numpy() - Po).max() <= 1e-12
+
+
+def test_api_errors_are_reported_not_thrown_across_the_abi():
+    from system_identification_b200 import _lib
+    from system_identification_b200.ops import DeviceModel
+    flat = H.flat_model("solo12")
+    dm = DeviceModel(flat)
+    q = torch.zeros((19, 4), dtype=torch.float64, device="cuda")
+    with pytest.raises(ValueError):
+        dm.regressor_batch(q[:18], q[:18], q[:18])
+    lib = _lib.load()
+    rc = lib.sysid_regressor_batch(dm.handle, None, None, None, 4, 4, None, None)
+    assert rc == -1 and b"null" in lib.sysid_last_error()
+    import copy
+    big = copy.deepcopy(flat)
+    big.parent = np.concatenate([flat.parent, [13]]).astype(np.int32); big.jtype = np.concatenate([flat.jtype, [1]]).astype(np.int32)
+    big.axis = np.vstack([flat.axis, [1, 0, 0]]); big.place_R = np.concatenate([flat.place_R, np.eye(3)[None]]); big.place_p = np.vstack([flat.place_p, [0, 0, 0]])
+    with pytest.raises(_lib.SysidError) as e:
+        _lib.create_model(big)
+    assert e.value.code == -2                                       # outside the compiled envelope
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_sdp_solve_vs_oracle_fixture(name):
+    from system_identification_b200.ops import sdp_solve
+    flat = H.flat_model(name)
+    g = np.load(os.path.join(H.GOLDEN_DIR, f"{name}_N48.npz"))
+    stats = torch.from_numpy(np.concatenate([g["sdp_G"].reshape(-1), g["sdp_r"], [g["sdp_s"], g["sdp_n"]]])).cuda()
+    x, info = sdp_solve(stats, 13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass)
+    x = x[0].cpu().numpy()
+    assert info[0]["status"] == 0
+    xo = g["sdp_x_alm"]
+    assert H.rel(x, xo) <= TOL_PHI and H.rel(x[:130], xo[:130]) <= TOL_PHI
+    for i in range(13):
+        assert H.rel(x[10 * i:10 * i + 10], xo[10 * i:10 * i + 10]) <= TOL_PHI
+    assert H.rel(x, g["sdp_x_barrier"]) <= TOL_PHI                  # and the barrier solve, independently
+    assert abs(info[0]["objective"] - g["sdp_obj"]) <= 1e-7 * max(1.0, abs(g["sdp_obj"]))
+    assert abs(info[0]["mass_residual"]) <= 1e-9 and info[0]["min_eig_J"] > -1e-7 and info[0]["min_eig_C"] > -1e-7
+    assert np.all(x[130:] > -1e-8)
+
+
+def test_sdp_active_lmi_euclidean_batched_and_failure():
+    from system_identification_b200.ops import sdp_solve
+    from oracle import sdp as osdp
+    flat = H.flat_model("solo12")
+    g = np.load(os.path.join(H.GOLDEN_DIR, "solo12_N48.npz"))
+    G, r, s, n = g["sdp_G"], g["sdp_r"], float(g["sdp_s"]), float(g["sdp_n"])
+    stats = torch.from_numpy(np.concatenate([G.reshape(-1), r, [s, n]])).cuda()
+    for lam, reg in [(1e-3, "constant_pullback"), (1e-2, "euclidean")]:
+        prob = osdp.build_problem(G, r, s, n, 13, flat.phi_prior, flat.robot_mass, flat.ellipsoids, 12, lambda_reg=lam, reg_type=reg)
+        xo, _ = osdp.solve_alm(prob)
+        x, info = sdp_solve(stats, 13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass, lambda_reg=lam, reg_type=reg)
+        assert info[0]["status"] in (0, 1) and H.rel(x[0].cpu().numpy(), xo) <= TOL_PHI
+    # batch of 3 scaled problems == 3 separate solves
+    batch = torch.stack([stats, stats * 1.0, stats]).contiguous()
+    batch[1, :154 * 154 + 154 + 1] *= 1.5                            # a different (still PSD) Gram
+    xb, ib = sdp_solve(batch, 13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass, batch=3)
+    x1, _ = sdp_solve(batch[1].contiguous(), 13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass)
+    assert torch.allclose(xb[1], x1[0], rtol=0, atol=1e-9) and torch.allclose(xb[0], xb[2], rtol=0, atol=0)
+    assert all(int(s_) == 0 for s_ in ib["status"])
+    # infeasible: negative total mass -> not optimal -> ValueError through the reference-shaped Solver
+    from src.solver import Solver
+    sol = Solver.from_stats(stats, 13, flat.phi_prior, -1.0, flat.ellipsoids, ndof=12)
+    with pytest.raises(ValueError, match="did not solve to optimality"):
+        sol.solve_fully_consistent()
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_end_to_end_identify_vs_oracle(name):
+    """identify() (fused path) == reference-shaped path (per-sample API -> stack -> Solver) == oracle, on one log."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    from oracle import dynamics as dy, sdp as osdp
+    from src.solver import Solver
+    from src.sys_identification import SystemIdentification
+    flat = H.flat_model(name)
+    si = SystemIdentification.from_flat_model(flat)
+    dm = si.device_model
+
+    def regress(q, dq, ddq, cnt):
+        dev = _up((q, dq, ddq, np.zeros((12, q.shape[1])), cnt))
+        Y = dm.regressor_batch(*dev[:3]).cpu().numpy()
+        _, _, P = dm.projected_batch(*dev, want_P=True)
+        return Y, P.cpu().numpy()
+    data, _, _, _ = H.identifiable_log(flat, 300, 91, regress)
+    phi, bv, bc, info = si.identify(*data, return_info=True)
+    # oracle on the oracle's own stack
+    t = H.oracle_tree(flat)
+    A, b = dy.stacked_system(t, *data, flat.ee_names)
+    prob = osdp.build_problem(A.T @ A, A.T @ b, float(b @ b), A.shape[0], 13, flat.phi_prior, flat.robot_mass, flat.ellipsoids, 12)
+    xo, io = osdp.solve_alm(prob)
+    x = np.concatenate([phi, bv, bc])
+    assert H.rel(x, xo) <= TOL_PHI
+    for i in range(13):
+        assert H.rel(phi[10 * i:10 * i + 10], xo[10 * i:10 * i + 10]) <= TOL_PHI
+    # torque-prediction metric within 0.5 % of the oracle's, for prior and identified parameters
+    for p in (flat.phi_prior.astype(float), phi):
+        tot, pj = si.tau_prediction_rmse(*data, p)
+        tot_o, pj_o = dy.tau_prediction_rmse(t, *(a[:, :60] for a in data), p, flat.ee_names)
+        tot_s, pj_s = si.tau_prediction_rmse(*(a[:, :60] for a in data), p)
+        assert abs(tot_s - tot_o) <= TOL_RMSE * tot_o and np.abs(pj_s - pj_o).max() <= TOL_RMSE * pj_o.max()
+    # reference-shaped path on a prefix: the demo's loops, vstack, Solver(...).solve_fully_consistent()
+    n = 40
+    Ys, Ts, Bv, Bc = [], [], [], []
+    q, dq, ddq, tau, cnt = (a[:, :n] for a in data)
+    for i in range(n):
+        y, tp = si.get_proj_regressor_torque(q[:, i], dq[:, i], ddq[:, i], tau[:, i], cnt[:, i])
+        b_v, b_c = si.get_proj_friction_regressors(q[:, i], dq[:, i], ddq[:, i], cnt[:, i])
+        Ys.append(y); Ts.append(tp); Bv.append(b_v); Bc.append(b_c)
+    Ys, Ts, Bv, Bc = np.vstack(Ys), np.hstack(Ts), np.vstack(Bv), np.vstack(Bc)
+    assert np.abs(np.hstack([Ys, Bv, Bc]) - A[:18 * n]).max() <= TOL_Y * np.abs(A[:18 * n]).max()
+    sol = Solver(Ys, Ts, 13, si.get_phi_prior(), si.get_robot_mass(), si.get_bounding_ellipsoids(), B_v=Bv, B_c=Bc)
+    phi_s = sol.solve_fully_consistent()
+    phi_f = si.identify(q, dq, ddq, tau, cnt)
+    assert H.rel(phi_s, phi_f) <= 1e-6 and phi_s.shape == (130,) and sol._b_v.value.shape == (12,)
+
+
+def test_full_size_properties_20k():
+    """BASELINE configs at N = 20 000: properties that do not need the oracle at that size."""
+    flat, data = H.small_log("spot", 20000)
+    dm = _dev(flat)
+    dev = _up(data)
+    c = 154
+    st = dm.gram_accumulate(*dev)
+    G, r, s, n = H.split_stats(st.cpu().numpy(), c)
+    assert n == 18 * 20000 and np.array_equal(G, G.T) and np.linalg.eigvalsh(G).min() >= -1e-9 * np.abs(G).max()
+    # additivity over shards (the multi-GPU reduction in miniature) and determinism
+    halves = dm.gram_accumulate(*(a[:, :9000] for a in dev))
+    dm.gram_accumulate(*(a[:, 9000:] for a in dev), stats=halves)
+    assert H.rel(halves.cpu().numpy(), st.cpu().numpy()) <= 1e-13
+    assert torch.equal(dm.gram_accumulate(*dev), st)
+    # linearity in tau: r(tau1 + tau2) = r(tau1) + r(tau2); G does not depend on tau
+    tau2 = torch.roll(dev[3], 7, dims=1)
+    r1 = dm.gram_accumulate(*dev)[c * c:c * c + c]
+    r2 = dm.gram_accumulate(dev[0], dev[1], dev[2], tau2, dev[4])[c * c:c * c + c]
+    r12 = dm.gram_accumulate(dev[0], dev[1], dev[2], (dev[3] + tau2).contiguous(), dev[4])[c * c:c * c + c]
+    assert H.rel((r1 + r2).cpu().numpy(), r12.cpu().numpy()) <= 1e-12
+    # phi^T G phi - 2 phi^T r + s == N * 18/... == sum of squared residuals == rmse pass (checksum of checksums)
+    phi = torch.from_numpy(flat.phi_prior.astype(np.float64)).cuda()
+    x = torch.cat([phi, torch.zeros(24, dtype=torch.float64, device="cuda")])
+    Gt = st[:c * c].view(c, c)
+    ssr = float(x @ Gt @ x - 2 * x @ st[c * c:c * c + c] + st[c * c + c])
+    out = dm.predict_rmse(*dev, phi).cpu().numpy()
+    # the rmse pass only sees joint rows; the Gram sees all 18: compare through a second Gram restricted check instead
+    assert ssr > 0 and out[0] > 0 and out[0] * 20000 <= ssr * (1 + 1e-9)
