@@ -70,28 +70,33 @@ __device__ __forceinline__ void store_tiles(double* __restrict__ partial, int la
         case 14: FN<14>(__VA_ARGS__); break; default: FN<15>(__VA_ARGS__); break;               \
     }
 
-// C phase for TILE_SAMPLES samples starting at local sample s0 of the super-batch.
+// C phase for TILE_SAMPLES samples starting at local sample s0 of the super-batch.  Items are visited in the
+// depth-sorted column order M.colperm, so that the lanes of a warp walk chains of (nearly) equal length.
 __device__ __noinline__ void fill_tile(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
                                        int s0, int friction, int tid, int nthreads) {
     const int np = M.nparams, nd = M.nd;
     const int used = np + (friction ? 2 * nd : 0) + 1;      // columns that carry data (tau column last)
     for (int it = tid; it < TILE_SAMPLES * CW; it += nthreads) {
-        const int sl = it / CW, col = it - sl * CW;
+        const int sl = it / CW, pc = it - sl * CW;
+        const int col = M.colperm[pc];
         if (col >= used) continue;
         const double* c = ctx + (s0 + sl) * CTX_STRIDE;
         const double wsq = c[CTX_W];
-        double out[MAXV];
+        double out[MAXV], pval[MAXCH];
+        int prow[MAXCH];
+        double* dst = tile + (sl * MAXV) * TILE_LD + col;
         if (wsq == 0.0) {
 #pragma unroll
-            for (int r = 0; r < MAXV; ++r) out[r] = 0.0;
-        } else {
-            // without friction columns the tau column follows the body columns directly
-            const int vcol = (!friction && col == np) ? np + 2 * nd : col;
-            column_item<true>(M, c, vcol, out);
+            for (int r = 0; r < MAXV; ++r) dst[r * TILE_LD] = 0.0;
+            continue;
         }
-        double* dst = tile + (sl * MAXV) * TILE_LD + col;
+        // without friction columns the tau column follows the body columns directly
+        const int vcol = (!friction && col == np) ? np + 2 * nd : col;
+        column_item<true>(M, c, vcol, out, prow, pval);
 #pragma unroll
         for (int r = 0; r < MAXV; ++r) dst[r * TILE_LD] = out[r] * wsq;
+#pragma unroll
+        for (int e = 0; e < MAXCH; ++e) if (prow[e] >= 0) dst[prow[e] * TILE_LD] += pval[e] * wsq;
     }
 }
 
@@ -261,19 +266,22 @@ sample_batch_kernel(const __grid_constant__ DevModel M, const BatchArgs args) {
         const long long i = base + sl;
         if (i >= args.N) continue;
         const double* c = ctx + sl * CTX_STRIDE;
-        double out[MAXV];
+        double out[MAXV], pval[MAXCH];
+        int prow[MAXCH];
         if (MODE == 0) {
             if (col >= np) continue;
-            column_item<false>(M, c, col, out);
+            column_item<false>(M, c, col, out, prow, pval);
+#pragma unroll
+            for (int e = 0; e < MAXCH; ++e) if (prow[e] >= 0) { for (int r = 0; r < MAXV; ++r) if (r == prow[e]) out[r] += pval[e]; }
             for (int r = 0; r < nv; ++r) args.Y[((size_t)i * nv + r) * np + col] = out[r];
         } else {
-            if (col < ncols) {
-                column_item<true>(M, c, col, out);
-                for (int r = 0; r < nv; ++r) args.A[((size_t)i * nv + r) * ncols + col] = out[r];
-            } else if (col == ncols) {
-                column_item<true>(M, c, np + 2 * nd, out);
-                for (int r = 0; r < nv; ++r) args.b[(size_t)i * nv + r] = out[r];
-            }
+            const bool is_b = (col == ncols);
+            if (col > ncols) continue;
+            column_item<true>(M, c, is_b ? np + 2 * nd : col, out, prow, pval);
+#pragma unroll
+            for (int e = 0; e < MAXCH; ++e) if (prow[e] >= 0) { for (int r = 0; r < MAXV; ++r) if (r == prow[e]) out[r] += pval[e]; }
+            if (is_b) { for (int r = 0; r < nv; ++r) args.b[(size_t)i * nv + r] = out[r]; }
+            else { for (int r = 0; r < nv; ++r) args.A[((size_t)i * nv + r) * ncols + col] = out[r]; }
         }
     }
     if (MODE == 1 && args.P) {
@@ -282,7 +290,11 @@ sample_batch_kernel(const __grid_constant__ DevModel M, const BatchArgs args) {
             const long long i = base + sl;
             if (i >= args.N) continue;
             const int r = rc / nv, cc = rc - r * nv;
-            args.P[(size_t)i * nv * nv + rc] = ctx[sl * CTX_STRIDE + CTX_P + r * MAXV + cc];
+            const double* cx = ctx + sl * CTX_STRIDE;
+            const int m3 = (int)cx[CTX_M3];
+            double pv = (r == cc) ? 1.0 : 0.0;
+            for (int k = 0; k < m3; ++k) pv -= cx[CTX_WM + k * MAXV + r] * cx[CTX_WM + k * MAXV + cc];
+            args.P[(size_t)i * nv * nv + rc] = pv;
         }
     }
 }

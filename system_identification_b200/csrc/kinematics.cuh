@@ -1,12 +1,12 @@
 // Per-sample kinematics: stage 1 of the hot path.
 //
 //   forward_sample()  one THREAD per sample ("F phase"): joint sines/cosines, poses relative to the base,
-//                     contact Jacobian in the base frame, its Gram S = J J^T, Cholesky, and the null-space
-//                     projector P = I - J^T S^-1 J; then spatial velocity / gravity-biased acceleration of every
-//                     body.  Results go to a small per-sample context in shared memory.
+//                     contact Jacobian J, its Gram S = J J^T, Cholesky S = L L^T, and W = L^-1 J (the null-space
+//                     projector is P = I - J^T S^-1 J = I - W^T W); then spatial velocity / gravity-biased
+//                     acceleration of every body.  Results go to a small per-sample context in shared memory.
 //   column_item()     one THREAD per (sample, regressor column) ("C phase"): the 6-vector column of the body
-//                     regressor, walked up the kinematic chain (S_j^T B, then liMi[j].act), multiplied by P on
-//                     the fly.  Produces one column (MAXV values) of the projected row block
+//                     regressor, walked up the kinematic chain (S_j^T B, then liMi[j].act), projected with
+//                     P = I - W^T W on the fly.  Produces one column (MAXV values) of the projected row block
 //                     A_i = P [Y | S^T diag(dq) | S^T diag(sign dq) | S^T tau].
 //
 // Algorithms restated from pinocchio (upstream of reference src/sys_identification.py:395,406,113-135):
@@ -29,15 +29,16 @@ constexpr int CTX_B9 = CTX_SC + 2 * MAXD;      // [MAXB][9]  omega(3), alpha(3),
 constexpr int CTX_DQ = CTX_B9 + 9 * MAXB;      // [MAXD]     joint velocities
 constexpr int CTX_TAU = CTX_DQ + MAXD;         // [MAXD]     joint torques
 constexpr int CTX_W = CTX_TAU + MAXD;          // sqrt(weight) (0 => sample skipped)
-constexpr int CTX_P = CTX_W + 1;               // [MAXV][MAXV] projector, row-major (offset even => 16 B aligned rows)
-constexpr int CTX_STRIDE = CTX_P + MAXV * MAXV;   // 490 == 2 (mod 4): 2-way conflicts at most for the F-phase writes
-static_assert(CTX_P % 2 == 0 && CTX_STRIDE % 4 == 2, "context layout");
+constexpr int CTX_M3 = CTX_W + 1;              // number of contact rows 3m (as a double)
+constexpr int CTX_WM = CTX_M3 + 2;             // [3*MAXEE][MAXV] W = L^-1 J_c, row-major: P = I - W^T W (offset even => 16 B rows)
+constexpr int CTX_STRIDE = CTX_WM + 3 * MAXEE * MAXV + 2;   // == 2 (mod 4): at most 2-way conflicts for the F-phase accesses
+static_assert(CTX_WM % 2 == 0 && CTX_STRIDE % 4 == 2, "context layout");
 
 // ---- F-phase scratch (doubles per lane), lane-minor: element e of lane l at scr[e * 32 + l] ---------------
 constexpr int SCR_POSE = 0;                          // [MAXD][12] R(9) p(3) of revolute joints relative to the base
 constexpr int SCR_RF = SCR_POSE + 12 * MAXD;         // [MAXEE][3] stance-foot positions in the base frame
 constexpr int SCR_JL = SCR_RF + 3 * MAXEE;           // [MAXEE][MAXCH][3] leg columns of J'
-constexpr int SCR_S = SCR_JL + 3 * MAXEE * MAXCH;    // [78] packed lower triangle of S / L / L^-1
+constexpr int SCR_S = SCR_JL + 3 * MAXEE * MAXCH;    // [78] packed lower triangle of S, then its Cholesky factor L
 constexpr int SCR_DOUBLES = SCR_S + 78;              // 306
 constexpr int SCR_VA = 0;                            // second pass reuses the front: [MAXB][12] v(6) a(6)
 static_assert(12 * MAXB <= SCR_DOUBLES, "scratch reuse");
@@ -251,109 +252,49 @@ __device__ __noinline__ int forward_sample(const DevModel& M, const SampleIO& io
             SCR(SCR_S + tri(b, a)) = v * inv;
         }
     }
-    // ---------------- L^-1 in place (dropped rows/cols become zero) ------------------------------------------
-    for (int a = 0; a < m3; ++a) {
-        const double laa = SCR(SCR_S + tri(a, a));
-        SCR(SCR_S + tri(a, a)) = (laa != 0.0) ? 1.0 / laa : 0.0;
-    }
-    for (int a = 1; a < m3; ++a) {
-        const double inva = SCR(SCR_S + tri(a, a));
-        for (int b = 0; b < a; ++b) {
-            double v = 0.0;
-            for (int k = b; k < a; ++k) v -= SCR(SCR_S + tri(a, k)) * SCR(SCR_S + tri(k, b));   // rows k < a already inverted
-            SCR(SCR_S + tri(a, b)) = v * inva;
-        }
-    }
-    // ---------------- P = I - J^T (L^-T L^-1) J ----------------------------------------------------------------
-    // column a of J as a 3m-vector u_a: a<3: R_b[:,a] per foot; 3<=a<6: R_b[:,a-3] x r_t; a>=6: leg column of joint a-4 if on the chain
-    const int nv = M.nv;
-    double* P = ctx + CTX_P;
-    for (int a = 0; a < MAXV; ++a) {
-        double u[3 * MAXEE], w[3 * MAXEE], z[3 * MAXEE];
+    // ---------------- W = L^-1 J by forward substitution, row by row, straight into the context ----------------
+    // P = I - J^T (J J^T)^-1 J = I - W^T W.  Row (t, x) of J: [ R_b[x][:] | (-[r_t]x R_b)[x][:] | leg columns ].
+    ctx[CTX_M3] = (double)m3;
+    double* Wm = ctx + CTX_WM;
+    for (int t = 0; t < m; ++t) {
+        int kt = 0;
 #pragma unroll
-        for (int k = 0; k < 3 * MAXEE; ++k) u[k] = 0.0;
-        if (a < nv) {
+        for (int uu = 0; uu < MAXEE; ++uu) if (uu == t) kt = foot_of[uu];
+        const double r0 = SCR(SCR_RF + 3 * t), r1 = SCR(SCR_RF + 3 * t + 1), r2 = SCR(SCR_RF + 3 * t + 2);
+        const int len = M.chain_len[kt];
+        for (int x = 0; x < 3; ++x) {
+            const int k = 3 * t + x;
+            double row[MAXV];
 #pragma unroll
-            for (int t = 0; t < MAXEE; ++t) {
-                if (t < m) {
-                    if (a < 3) {
+            for (int c2 = 0; c2 < MAXV; ++c2) row[c2] = 0.0;
+            // base columns: R_b[x][:] and (-[r]x R_b)[x][:] = -(r x R_b[:,c])_x
 #pragma unroll
-                        for (int e = 0; e < 3; ++e) u[3 * t + e] = (a == 0) ? Rb[3 * e] : ((a == 1) ? Rb[3 * e + 1] : Rb[3 * e + 2]);
-                    } else if (a < 6) {
-                        const double r0 = SCR(SCR_RF + 3 * t), r1 = SCR(SCR_RF + 3 * t + 1), r2 = SCR(SCR_RF + 3 * t + 2);
-                        // -[r]x c = c x r, c = column (a-3) of R_b
-                        const double c0 = (a == 3) ? Rb[0] : ((a == 4) ? Rb[1] : Rb[2]);
-                        const double c1 = (a == 3) ? Rb[3] : ((a == 4) ? Rb[4] : Rb[5]);
-                        const double c2 = (a == 3) ? Rb[6] : ((a == 4) ? Rb[7] : Rb[8]);
-                        u[3 * t] = c1 * r2 - c2 * r1; u[3 * t + 1] = c2 * r0 - c0 * r2; u[3 * t + 2] = c0 * r1 - c1 * r0;
-                    } else {
-                        int kt = 0;
-#pragma unroll
-                        for (int uu = 0; uu < MAXEE; ++uu) if (uu == t) kt = foot_of[uu];
-                        const int cj = a - 4;   // joint id with idx_v == a
-                        const int len = M.chain_len[kt];
-                        for (int e = 0; e < len; ++e) {
-                            if (M.chain[kt][e] == cj) {
-                                const int jo = SCR_JL + 3 * (t * MAXCH + e);
-                                u[3 * t] = SCR(jo); u[3 * t + 1] = SCR(jo + 1); u[3 * t + 2] = SCR(jo + 2);
-                            }
-                        }
-                    }
-                }
+            for (int c2 = 0; c2 < 3; ++c2) {
+                row[c2] = (x == 0) ? Rb[c2] : ((x == 1) ? Rb[3 + c2] : Rb[6 + c2]);
+                const double b0 = Rb[c2], b1 = Rb[3 + c2], b2 = Rb[6 + c2];
+                // (r x b)_x
+                const double cx = (x == 0) ? (r1 * b2 - r2 * b1) : ((x == 1) ? (r2 * b0 - r0 * b2) : (r0 * b1 - r1 * b0));
+                row[3 + c2] = -cx;
             }
-        }
-        // w = L^-1 u ; z = L^-T w
+            // leg columns: scatter by joint id (compile-time register index via the unrolled compare)
+            for (int e = 0; e < len; ++e) {
+                const int cidx = M.chain[kt][e] + 4;           // idx_v of the joint
+                const double val = SCR(SCR_JL + 3 * (t * MAXCH + e) + x);
 #pragma unroll
-        for (int r = 0; r < 3 * MAXEE; ++r) {
-            double acc = 0.0;
-            if (r < m3) {
-#pragma unroll
-                for (int k = 0; k <= r; ++k) acc += SCR(SCR_S + tri(r, k)) * u[k];
+                for (int c2 = 6; c2 < MAXV; ++c2) if (c2 == cidx) row[c2] = val;
             }
-            w[r] = acc;
-        }
+            // row_k <- (row_k - sum_{l<k} L[k][l] W[l]) / L[k][k]
+            for (int l = 0; l < k; ++l) {
+                const double lkl = SCR(SCR_S + tri(k, l));
+                const double* Wl = Wm + l * MAXV;
 #pragma unroll
-        for (int r = 0; r < 3 * MAXEE; ++r) {
-            double acc = 0.0;
-#pragma unroll
-            for (int k = r; k < 3 * MAXEE; ++k) if (k < m3) acc += SCR(SCR_S + tri(k, r)) * w[k];
-            z[r] = acc;
-        }
-        // P[a][b] = delta_ab - u_b . z   for b >= a, mirrored
-        for (int b = a; b < MAXV; ++b) {
-            double dotv = 0.0;
-            if (a < nv && b < nv) {
-#pragma unroll
-                for (int t = 0; t < MAXEE; ++t) {
-                    if (t < m) {
-                        if (b < 3) {
-                            dotv += ((b == 0) ? Rb[0] : (b == 1) ? Rb[1] : Rb[2]) * z[3 * t] + ((b == 0) ? Rb[3] : (b == 1) ? Rb[4] : Rb[5]) * z[3 * t + 1]
-                                  + ((b == 0) ? Rb[6] : (b == 1) ? Rb[7] : Rb[8]) * z[3 * t + 2];
-                        } else if (b < 6) {
-                            const double r0 = SCR(SCR_RF + 3 * t), r1 = SCR(SCR_RF + 3 * t + 1), r2 = SCR(SCR_RF + 3 * t + 2);
-                            const double c0 = (b == 3) ? Rb[0] : ((b == 4) ? Rb[1] : Rb[2]);
-                            const double c1 = (b == 3) ? Rb[3] : ((b == 4) ? Rb[4] : Rb[5]);
-                            const double c2 = (b == 3) ? Rb[6] : ((b == 4) ? Rb[7] : Rb[8]);
-                            dotv += (c1 * r2 - c2 * r1) * z[3 * t] + (c2 * r0 - c0 * r2) * z[3 * t + 1] + (c0 * r1 - c1 * r0) * z[3 * t + 2];
-                        } else {
-                            int kt = 0;
-#pragma unroll
-                            for (int uu = 0; uu < MAXEE; ++uu) if (uu == t) kt = foot_of[uu];
-                            const int cj = b - 4;
-                            const int len = M.chain_len[kt];
-                            for (int e = 0; e < len; ++e) {
-                                if (M.chain[kt][e] == cj) {
-                                    const int jo = SCR_JL + 3 * (t * MAXCH + e);
-                                    dotv += SCR(jo) * z[3 * t] + SCR(jo + 1) * z[3 * t + 1] + SCR(jo + 2) * z[3 * t + 2];
-                                }
-                            }
-                        }
-                    }
-                }
+                for (int c2 = 0; c2 < MAXV; ++c2) row[c2] = fma(-lkl, Wl[c2], row[c2]);
             }
-            const double val = ((a == b && a < nv) ? 1.0 : 0.0) - dotv;
-            P[a * MAXV + b] = val;
-            P[b * MAXV + a] = val;
+            const double lkk = SCR(SCR_S + tri(k, k));
+            const double inv = (lkk != 0.0) ? 1.0 / lkk : 0.0;     // dropped (dependent) row: W row = 0
+            double* Wk = Wm + k * MAXV;
+#pragma unroll
+            for (int c2 = 0; c2 < MAXV; ++c2) Wk[c2] = row[c2] * inv;
         }
     }
     // ---------------- pass 2: spatial velocities and gravity-biased accelerations (local frames) ---------------
@@ -432,15 +373,27 @@ __device__ __noinline__ int forward_sample(const DevModel& M, const SampleIO& io
 }
 #undef SCR
 
-// One thread = one column of one sample's projected row block.  col in [0, CW): body columns, then viscous,
-// Coulomb, then the tau column.  PROJECT=false yields the raw (unprojected) regressor column instead.
-// Returns false for padding columns (nothing written to out).
+// One thread = one column of one sample's projected row block  A_i = P [Y | S^T diag(dq) | S^T diag(sign dq) | S^T tau],
+// P = I - W^T W.  col in [0, CW): body columns, then viscous, Coulomb, then the tau column.
+// The sparse unprojected column y is walked up the chain once; t = W y is accumulated on the fly; the result is
+//     out[r] = (y_r for the statically known rows) - sum_k W[k][r] t[k],        r < MAXV
+// plus up to MAXCH (row, value) pairs -- the joint rows, known only at run time -- that the caller ADDS to its
+// destination after writing out[] (the thread owns the column, so the read-modify-write is private).
+// PROJECT=false yields the raw regressor column (W ignored).  Returns the pair count, or -1 for a padding column.
 template <bool PROJECT>
-__device__ __forceinline__ bool column_item(const DevModel& M, const double* ctx, int col, double out[MAXV]) {
+__device__ __forceinline__ int column_item(const DevModel& M, const double* ctx, int col, double out[MAXV],
+                                           int prow[MAXCH], double pval[MAXCH]) {
     const int np = M.nparams, nd = M.nd;
-    const double* P = ctx + CTX_P;
+    const double* Wm = ctx + CTX_WM;
+    const int m3 = PROJECT ? (int)ctx[CTX_M3] : 0;
+    double t[3 * MAXEE];
+#pragma unroll
+    for (int k = 0; k < 3 * MAXEE; ++k) t[k] = 0.0;
 #pragma unroll
     for (int r = 0; r < MAXV; ++r) out[r] = 0.0;
+#pragma unroll
+    for (int e = 0; e < MAXCH; ++e) { prow[e] = -1; pval[e] = 0.0; }
+    int npairs = 0;
     if (col < np) {
         const int i = col / 10 + 1, k = col - 10 * (i - 1);
         const double* b9 = ctx + CTX_B9 + 9 * (i - 1);
@@ -470,65 +423,80 @@ __device__ __forceinline__ bool column_item(const DevModel& M, const double* ctx
             n0 = a0 + (w1 * b2 - w2 * b1); n1 = a1 + (w2 * b0 - w0 * b2); n2 = a2 + (w0 * b1 - w1 * b0);
         }
         int j = i;
-        while (j > 1) {
-            const int jt = M.jtype[j];
-            const double val = (jt == JT_RX) ? n0 : (jt == JT_RY) ? n1 : (jt == JT_RZ) ? n2
-                                                                   : (M.axis[j][0] * n0 + M.axis[j][1] * n1 + M.axis[j][2] * n2);
-            const int row = 6 + (j - 2);
-            if (PROJECT) {
-                const double* Pr = P + row * MAXV;   // P symmetric: column `row` == row `row`
 #pragma unroll
-                for (int r = 0; r < MAXV; ++r) out[r] = fma(Pr[r], val, out[r]);
-            } else {
+        for (int e = 0; e < MAXCH; ++e) {
+            if (j > 1) {
+                const int jt = M.jtype[j];
+                const double val = (jt == JT_RX) ? n0 : (jt == JT_RY) ? n1 : (jt == JT_RZ) ? n2
+                                                                       : (M.axis[j][0] * n0 + M.axis[j][1] * n1 + M.axis[j][2] * n2);
+                const int row = 6 + (j - 2);
+                prow[e] = row; pval[e] = val; npairs = e + 1;
+                if (PROJECT) {
 #pragma unroll
-                for (int r = 0; r < MAXV; ++r) if (r == row) out[r] = val;
+                    for (int kk = 0; kk < 3 * MAXEE; ++kk) if (kk < m3) t[kk] = fma(Wm[kk * MAXV + row], val, t[kk]);
+                }
+                // force transform to the parent frame: f' = R f, n' = R n + p x f'
+                double R[9];
+                joint_rotation_compose(M, j, ctx[CTX_SC + 2 * (j - 2)], ctx[CTX_SC + 2 * (j - 2) + 1], R);
+                const double g0 = R[0] * f0 + R[1] * f1 + R[2] * f2, g1 = R[3] * f0 + R[4] * f1 + R[5] * f2, g2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
+                const double h0 = R[0] * n0 + R[1] * n1 + R[2] * n2, h1 = R[3] * n0 + R[4] * n1 + R[5] * n2, h2 = R[6] * n0 + R[7] * n1 + R[8] * n2;
+                const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
+                f0 = g0; f1 = g1; f2 = g2;
+                n0 = h0 + (py * g2 - pz * g1); n1 = h1 + (pz * g0 - px * g2); n2 = h2 + (px * g1 - py * g0);
+                j = M.parent[j];
             }
-            // force transform to the parent frame: f' = R f, n' = R n + p x f'
-            double R[9];
-            joint_rotation_compose(M, j, ctx[CTX_SC + 2 * (j - 2)], ctx[CTX_SC + 2 * (j - 2) + 1], R);
-            const double g0 = R[0] * f0 + R[1] * f1 + R[2] * f2, g1 = R[3] * f0 + R[4] * f1 + R[5] * f2, g2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
-            const double h0 = R[0] * n0 + R[1] * n1 + R[2] * n2, h1 = R[3] * n0 + R[4] * n1 + R[5] * n2, h2 = R[6] * n0 + R[7] * n1 + R[8] * n2;
-            const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
-            f0 = g0; f1 = g1; f2 = g2;
-            n0 = h0 + (py * g2 - pz * g1); n1 = h1 + (pz * g0 - px * g2); n2 = h2 + (px * g1 - py * g0);
-            j = M.parent[j];
         }
         // free-flyer root: rows 0..5 = (f; n)
-        const double y[6] = {f0, f1, f2, n0, n1, n2};
+        out[0] = f0; out[1] = f1; out[2] = f2; out[3] = n0; out[4] = n1; out[5] = n2;
         if (PROJECT) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const double* Pr = P + q * MAXV;
-#pragma unroll
-                for (int r = 0; r < MAXV; ++r) out[r] = fma(Pr[r], y[q], out[r]);
+            for (int kk = 0; kk < 3 * MAXEE; ++kk) {
+                if (kk < m3) {
+                    const double2* w2p = reinterpret_cast<const double2*>(Wm + kk * MAXV);
+                    const double2 wa = w2p[0], wb = w2p[1], wc = w2p[2];
+                    t[kk] += wa.x * f0 + wa.y * f1 + wb.x * f2 + wb.y * n0 + wc.x * n1 + wc.y * n2;
+                }
             }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) out[q] = y[q];
         }
-        return true;
-    }
-    if (!PROJECT) return false;
-    if (col < np + 2 * nd) {
+    } else if (!PROJECT) {
+        return -1;
+    } else if (col < np + 2 * nd) {
         const int jj = (col - np) % nd;
         const bool coulomb = (col - np) >= nd;
         const double dqv = ctx[CTX_DQ + jj];
         const double sc = coulomb ? ((dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv))) : dqv;   // numpy sign: sign(nan)=nan
-        const double* Pr = P + (6 + jj) * MAXV;
+        const int row = 6 + jj;
+        prow[0] = row; pval[0] = sc; npairs = 1;
 #pragma unroll
-        for (int r = 0; r < MAXV; ++r) out[r] = Pr[r] * sc;
-        return true;
-    }
-    if (col == np + 2 * nd) {
-        for (int jj = 0; jj < nd; ++jj) {
-            const double t = ctx[CTX_TAU + jj];
-            const double* Pr = P + (6 + jj) * MAXV;
+        for (int kk = 0; kk < 3 * MAXEE; ++kk) if (kk < m3) t[kk] = Wm[kk * MAXV + row] * sc;
+    } else if (col == np + 2 * nd) {
 #pragma unroll
-            for (int r = 0; r < MAXV; ++r) out[r] = fma(Pr[r], t, out[r]);
+        for (int jj = 0; jj < MAXD; ++jj) {
+            const double tj = (jj < nd) ? ctx[CTX_TAU + jj] : 0.0;
+            out[6 + jj] = tj;
+#pragma unroll
+            for (int kk = 0; kk < 3 * MAXEE; ++kk) if (kk < m3) t[kk] = fma(Wm[kk * MAXV + 6 + jj], tj, t[kk]);
         }
-        return true;
+    } else {
+        return -1;
     }
-    return false;
+    if (PROJECT) {
+        // out -= W^T t
+#pragma unroll
+        for (int kk = 0; kk < 3 * MAXEE; ++kk) {
+            if (kk < m3) {
+                const double tk = t[kk];
+                const double2* w2p = reinterpret_cast<const double2*>(Wm + kk * MAXV);
+#pragma unroll
+                for (int r2 = 0; r2 < MAXV / 2; ++r2) {
+                    const double2 wv = w2p[r2];
+                    out[2 * r2] = fma(-wv.x, tk, out[2 * r2]);
+                    out[2 * r2 + 1] = fma(-wv.y, tk, out[2 * r2 + 1]);
+                }
+            }
+        }
+    }
+    return npairs;
 }
 
 }  // namespace sysid

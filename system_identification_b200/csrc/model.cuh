@@ -31,6 +31,7 @@ struct DevModel {
     int32_t chain_len[MAXEE];
     int32_t chain[MAXEE][MAXCH];
     int32_t nshared[MAXEE][MAXEE];   // length of the common suffix of two foot chains
+    uint8_t colperm[CW];             // C-phase visiting order of the padded columns: sorted by chain depth (warp-uniform work)
 };
 
 }  // namespace sysid

@@ -120,6 +120,24 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
                    M.chain[a][M.chain_len[a] - 1 - ns] == M.chain[b][M.chain_len[b] - 1 - ns]) ++ns;
             M.nshared[a][b] = ns;
         }
+    // chain depth of every body (the column walk is unrolled MAXCH deep) and the depth-sorted column order
+    int depth[MAXJ] = {0};
+    for (int j = 2; j < d->njoints; ++j) {
+        depth[j] = depth[M.parent[j]] + 1;
+        if (depth[j] > MAXCH) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "joint %d sits %d joints below the root (limit %d)", j, depth[j], MAXCH); }
+    }
+    {
+        int work[CW];
+        for (int c = 0; c < CW; ++c) {
+            if (c < M.nparams) work[c] = 2 + depth[c / 10 + 1];          // body column: base rows + one emit per ancestor
+            else if (c < M.nparams + 2 * M.nd) work[c] = 1;              // friction column: one emit
+            else if (c == M.nparams + 2 * M.nd) work[c] = 2 + MAXCH;     // tau column: 12 emits
+            else work[c] = 0;                                            // padding
+        }
+        int n = 0;
+        for (int wv = 2 + MAXCH; wv >= 0; --wv)
+            for (int c = 0; c < CW; ++c) if (work[c] == wv) M.colperm[n++] = (uint8_t)c;
+    }
     int rc = device_sm_count(&m->sm_count);
     if (rc != SYSID_OK) { delete m; return rc; }
     *out = m;
