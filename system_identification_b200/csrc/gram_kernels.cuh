@@ -25,6 +25,7 @@ constexpr int TILE_LD = 164;                   // == 4 (mod 16): conflict-free D
 constexpr int TILE_DOUBLES = TILE_ROWS * TILE_LD;
 static_assert(TILE_ROWS % 4 == 0, "k-steps of 4 rows");
 static_assert(SCR_DOUBLES * SCR_LANES <= TILE_DOUBLES, "F-phase scratch aliases the tile");
+static_assert(sizeof(double) * (TILE_DOUBLES + SB_SAMPLES * CTX_STRIDE) + 1024 <= 232448, "shared memory budget");
 constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * (TILE_DOUBLES + SB_SAMPLES * CTX_STRIDE) + 64;
 constexpr int PARTIAL_DOUBLES = GRAM_NTILES * 64 + 8;   // per CTA: tiles, then [wsum, flag0 count, flag1 count]
 

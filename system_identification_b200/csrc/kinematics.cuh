@@ -24,24 +24,24 @@
 namespace sysid {
 
 // ---- per-sample context (doubles), sample-major in shared memory -----------------------------------------
-constexpr int CTX_SC = 0;                      // [MAXD][2]  sin, cos of each revolute joint
-constexpr int CTX_B9 = CTX_SC + 2 * MAXD;      // [MAXB][9]  omega(3), alpha(3), acc(3) of each body
+constexpr int CTX_POSE = 0;                    // [MAXD][12] R(9) p(3) of every revolute joint frame relative to the base
+constexpr int CTX_B9 = CTX_POSE + 12 * MAXD;   // [MAXB][9]  omega(3), alpha(3), acc(3) of each body (local frame)
 constexpr int CTX_DQ = CTX_B9 + 9 * MAXB;      // [MAXD]     joint velocities
 constexpr int CTX_TAU = CTX_DQ + MAXD;         // [MAXD]     joint torques
 constexpr int CTX_W = CTX_TAU + MAXD;          // sqrt(weight) (0 => sample skipped)
 constexpr int CTX_M3 = CTX_W + 1;              // number of contact rows 3m (as a double)
 constexpr int CTX_WM = CTX_M3 + 2;             // [3*MAXEE][MAXV] W = L^-1 J_c, row-major: P = I - W^T W (offset even => 16 B rows)
 constexpr int CTX_STRIDE = CTX_WM + 3 * MAXEE * MAXV + 2;   // == 2 (mod 4): at most 2-way conflicts for the F-phase accesses
-static_assert(CTX_WM % 2 == 0 && CTX_STRIDE % 4 == 2, "context layout");
+static_assert(CTX_POSE % 2 == 0 && CTX_WM % 2 == 0 && CTX_STRIDE % 4 == 2, "context layout");
 
-// ---- F-phase scratch (doubles per lane), lane-minor: element e of lane l at scr[e * 32 + l] ---------------
-constexpr int SCR_POSE = 0;                          // [MAXD][12] R(9) p(3) of revolute joints relative to the base
-constexpr int SCR_RF = SCR_POSE + 12 * MAXD;         // [MAXEE][3] stance-foot positions in the base frame
-constexpr int SCR_JL = SCR_RF + 3 * MAXEE;           // [MAXEE][MAXCH][3] leg columns of J'
+// ---- F-phase scratch (doubles per lane), lane-minor: element e of lane l at scr[e * SCR_LANES + l] --------
+constexpr int SCR_SC = 0;                            // [MAXD][2] sin, cos of the revolute joints
+constexpr int SCR_RF = SCR_SC + 2 * MAXD;            // [MAXEE][3] stance-foot lever arms R_b r_k
+constexpr int SCR_JL = SCR_RF + 3 * MAXEE;           // [MAXEE][MAXCH][3] leg columns of J
 constexpr int SCR_S = SCR_JL + 3 * MAXEE * MAXCH;    // [78] packed lower triangle of S, then its Cholesky factor L
-constexpr int SCR_DOUBLES = SCR_S + 78;              // 306
-constexpr int SCR_VA = 0;                            // second pass reuses the front: [MAXB][12] v(6) a(6)
-static_assert(12 * MAXB <= SCR_DOUBLES, "scratch reuse");
+constexpr int SCR_DOUBLES = SCR_S + 78;              // 186
+constexpr int SCR_VA = SCR_RF;                       // second pass reuses everything after the sines: [MAXB][12] v(6) a(6)
+static_assert(SCR_VA + 12 * MAXB <= SCR_DOUBLES, "scratch reuse");
 constexpr int SCR_LANES = 32;
 
 struct SampleIO {
@@ -101,29 +101,29 @@ __device__ __noinline__ int forward_sample(const DevModel& M, const SampleIO& io
         double s, c;
         sincos(th, &s, &c);
         finite_probe += th;
-        ctx[CTX_SC + 2 * (j - 2)] = s;
-        ctx[CTX_SC + 2 * (j - 2) + 1] = c;
+        SCR(SCR_SC + 2 * (j - 2)) = s;
+        SCR(SCR_SC + 2 * (j - 2) + 1) = c;
         double R[9];
         joint_rotation_compose(M, j, s, c, R);
         const int lam = M.parent[j];
-        const int o = SCR_POSE + 12 * (j - 2);
+        double* pose = ctx + CTX_POSE + 12 * (j - 2);
         if (lam == 1) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) SCR(o + k) = R[k];
+            for (int k = 0; k < 9; ++k) pose[k] = R[k];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) SCR(o + 9 + k) = M.pp[j][k];
+            for (int k = 0; k < 3; ++k) pose[9 + k] = M.pp[j][k];
         } else {
-            const int po = SCR_POSE + 12 * (lam - 2);
+            const double* pp_ = ctx + CTX_POSE + 12 * (lam - 2);
             double PR[9], Pp[3];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) PR[k] = SCR(po + k);
+            for (int k = 0; k < 9; ++k) PR[k] = pp_[k];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) Pp[k] = SCR(po + 9 + k);
+            for (int k = 0; k < 3; ++k) Pp[k] = pp_[9 + k];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) SCR(o + 3 * r + k) = PR[3 * r] * R[k] + PR[3 * r + 1] * R[3 + k] + PR[3 * r + 2] * R[6 + k];
-                SCR(o + 9 + r) = Pp[r] + PR[3 * r] * M.pp[j][0] + PR[3 * r + 1] * M.pp[j][1] + PR[3 * r + 2] * M.pp[j][2];
+                for (int k = 0; k < 3; ++k) pose[3 * r + k] = PR[3 * r] * R[k] + PR[3 * r + 1] * R[3 + k] + PR[3 * r + 2] * R[6 + k];
+                pose[9 + r] = Pp[r] + PR[3 * r] * M.pp[j][0] + PR[3 * r + 1] * M.pp[j][1] + PR[3 * r + 2] * M.pp[j][2];
             }
         }
     }
@@ -153,28 +153,28 @@ __device__ __noinline__ int forward_sample(const DevModel& M, const SampleIO& io
 #pragma unroll
             for (int e = 0; e < 3; ++e) rf[e] = M.ee_off[k][e];
         } else {
-            const int o = SCR_POSE + 12 * (jf - 2);
+            const double* po = ctx + CTX_POSE + 12 * (jf - 2);
 #pragma unroll
             for (int e = 0; e < 3; ++e)
-                rf[e] = SCR(o + 9 + e) + SCR(o + 3 * e) * M.ee_off[k][0] + SCR(o + 3 * e + 1) * M.ee_off[k][1] + SCR(o + 3 * e + 2) * M.ee_off[k][2];
+                rf[e] = po[9 + e] + po[3 * e] * M.ee_off[k][0] + po[3 * e + 1] * M.ee_off[k][1] + po[3 * e + 2] * M.ee_off[k][2];
         }
 #pragma unroll
         for (int e = 0; e < 3; ++e) SCR(SCR_RF + 3 * t + e) = Rb[3 * e] * rf[0] + Rb[3 * e + 1] * rf[1] + Rb[3 * e + 2] * rf[2];
         const int len = M.chain_len[k];
         for (int e = 0; e < len; ++e) {
             const int cj = M.chain[k][e];
-            const int o = SCR_POSE + 12 * (cj - 2);
+            const double* po = ctx + CTX_POSE + 12 * (cj - 2);
             double ax[3];   // joint axis in the base frame
             const int jt = M.jtype[cj];
             if (jt == JT_RU) {
 #pragma unroll
-                for (int r = 0; r < 3; ++r) ax[r] = SCR(o + 3 * r) * M.axis[cj][0] + SCR(o + 3 * r + 1) * M.axis[cj][1] + SCR(o + 3 * r + 2) * M.axis[cj][2];
+                for (int r = 0; r < 3; ++r) ax[r] = po[3 * r] * M.axis[cj][0] + po[3 * r + 1] * M.axis[cj][1] + po[3 * r + 2] * M.axis[cj][2];
             } else {
                 const int col = jt - JT_RX;
 #pragma unroll
-                for (int r = 0; r < 3; ++r) ax[r] = SCR(o + 3 * r + col);
+                for (int r = 0; r < 3; ++r) ax[r] = po[3 * r + col];
             }
-            const double bx = rf[0] - SCR(o + 9), by = rf[1] - SCR(o + 10), bz = rf[2] - SCR(o + 11);
+            const double bx = rf[0] - po[9], by = rf[1] - po[10], bz = rf[2] - po[11];
             const double a0 = Rb[0] * ax[0] + Rb[1] * ax[1] + Rb[2] * ax[2], a1 = Rb[3] * ax[0] + Rb[4] * ax[1] + Rb[5] * ax[2], a2 = Rb[6] * ax[0] + Rb[7] * ax[1] + Rb[8] * ax[2];
             const double dx = Rb[0] * bx + Rb[1] * by + Rb[2] * bz, dy = Rb[3] * bx + Rb[4] * by + Rb[5] * bz, dz = Rb[6] * bx + Rb[7] * by + Rb[8] * bz;
             const int jo = SCR_JL + 3 * (t * MAXCH + e);
@@ -316,7 +316,7 @@ __device__ __noinline__ int forward_sample(const DevModel& M, const SampleIO& io
         b9[8] = a[2] + (v[3] * v[1] - v[4] * v[0]);
     }
     for (int j = 2; j <= nb; ++j) {
-        const double s = ctx[CTX_SC + 2 * (j - 2)], c = ctx[CTX_SC + 2 * (j - 2) + 1];
+        const double s = SCR(SCR_SC + 2 * (j - 2)), c = SCR(SCR_SC + 2 * (j - 2) + 1);
         double R[9];
         joint_rotation_compose(M, j, s, c, R);
         const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
@@ -422,31 +422,50 @@ __device__ __forceinline__ int column_item(const DevModel& M, const double* ctx,
             }
             n0 = a0 + (w1 * b2 - w2 * b1); n1 = a1 + (w2 * b0 - w0 * b2); n2 = a2 + (w0 * b1 - w1 * b0);
         }
+        // Jacobian-transpose form in the BASE frame: rotate the column wrench to base axes at the body origin,
+        //   F = R_i f,  N = R_i n   (R_i, p_i = pose of body i relative to the base, from the F phase);
+        // the row of ancestor joint j (axis z_j through p_j, both in the base frame) is  z_j . (N + (p_i - p_j) x F),
+        // and the six free-flyer rows are (F, N + p_i x F).  Identical to walking S_j^T B up the chain with liMi[j].act.
+        double F0 = f0, F1 = f1, F2 = f2, N0 = n0, N1 = n1, N2 = n2, bp0 = 0.0, bp1 = 0.0, bp2 = 0.0;
+        if (i > 1) {
+            const double2* pq = reinterpret_cast<const double2*>(ctx + CTX_POSE + 12 * (i - 2));
+            const double2 a01 = pq[0], a23 = pq[1], a45 = pq[2], a67 = pq[3], a8p = pq[4], p12 = pq[5];
+            F0 = a01.x * f0 + a01.y * f1 + a23.x * f2; F1 = a23.y * f0 + a45.x * f1 + a45.y * f2; F2 = a67.x * f0 + a67.y * f1 + a8p.x * f2;
+            N0 = a01.x * n0 + a01.y * n1 + a23.x * n2; N1 = a23.y * n0 + a45.x * n1 + a45.y * n2; N2 = a67.x * n0 + a67.y * n1 + a8p.x * n2;
+            bp0 = a8p.y; bp1 = p12.x; bp2 = p12.y;
+        }
         int j = i;
 #pragma unroll
         for (int e = 0; e < MAXCH; ++e) {
             if (j > 1) {
                 const int jt = M.jtype[j];
-                const double val = (jt == JT_RX) ? n0 : (jt == JT_RY) ? n1 : (jt == JT_RZ) ? n2
-                                                                       : (M.axis[j][0] * n0 + M.axis[j][1] * n1 + M.axis[j][2] * n2);
+                const double* pj = ctx + CTX_POSE + 12 * (j - 2);
+                double z0, z1, z2;
+                if (jt == JT_RU) {
+                    const double u0 = M.axis[j][0], u1 = M.axis[j][1], u2 = M.axis[j][2];
+                    z0 = pj[0] * u0 + pj[1] * u1 + pj[2] * u2; z1 = pj[3] * u0 + pj[4] * u1 + pj[5] * u2; z2 = pj[6] * u0 + pj[7] * u1 + pj[8] * u2;
+                } else {
+                    const int cc = jt - JT_RX;
+                    z0 = pj[cc]; z1 = pj[3 + cc]; z2 = pj[6 + cc];
+                }
+                const double r0 = bp0 - pj[9], r1 = bp1 - pj[10], r2 = bp2 - pj[11];
+                double val = z0 * (N0 + (r1 * F2 - r2 * F1)) + z1 * (N1 + (r2 * F0 - r0 * F2)) + z2 * (N2 + (r0 * F1 - r1 * F0));
+                if (e == 0) {   // the body's own joint: S_i^T B in the body frame, exactly (keeps the structural zeros exact)
+                    val = (jt == JT_RX) ? n0 : (jt == JT_RY) ? n1 : (jt == JT_RZ) ? n2
+                                                             : (M.axis[j][0] * n0 + M.axis[j][1] * n1 + M.axis[j][2] * n2);
+                }
                 const int row = 6 + (j - 2);
                 prow[e] = row; pval[e] = val; npairs = e + 1;
                 if (PROJECT) {
 #pragma unroll
                     for (int kk = 0; kk < 3 * MAXEE; ++kk) if (kk < m3) t[kk] = fma(Wm[kk * MAXV + row], val, t[kk]);
                 }
-                // force transform to the parent frame: f' = R f, n' = R n + p x f'
-                double R[9];
-                joint_rotation_compose(M, j, ctx[CTX_SC + 2 * (j - 2)], ctx[CTX_SC + 2 * (j - 2) + 1], R);
-                const double g0 = R[0] * f0 + R[1] * f1 + R[2] * f2, g1 = R[3] * f0 + R[4] * f1 + R[5] * f2, g2 = R[6] * f0 + R[7] * f1 + R[8] * f2;
-                const double h0 = R[0] * n0 + R[1] * n1 + R[2] * n2, h1 = R[3] * n0 + R[4] * n1 + R[5] * n2, h2 = R[6] * n0 + R[7] * n1 + R[8] * n2;
-                const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
-                f0 = g0; f1 = g1; f2 = g2;
-                n0 = h0 + (py * g2 - pz * g1); n1 = h1 + (pz * g0 - px * g2); n2 = h2 + (px * g1 - py * g0);
                 j = M.parent[j];
             }
         }
-        // free-flyer root: rows 0..5 = (f; n)
+        // free-flyer root: rows 0..5 = (F; N + p_i x F)
+        f0 = F0; f1 = F1; f2 = F2;
+        n0 = N0 + (bp1 * F2 - bp2 * F1); n1 = N1 + (bp2 * F0 - bp0 * F2); n2 = N2 + (bp0 * F1 - bp1 * F0);
         out[0] = f0; out[1] = f1; out[2] = f2; out[3] = n0; out[4] = n1; out[5] = n2;
         if (PROJECT) {
 #pragma unroll
