@@ -122,7 +122,16 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #pragma unroll
     for (int t = 0; t < GRAM_MAX_NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
     const long long nsb = (args.N + SB_SAMPLES - 1) / SB_SAMPLES;
+#ifdef SYSID_PHASE_CLOCKS
+    long long clkF = 0, clkC = 0, clkM = 0, clk0;
+#define PHASE_TICK(acc) { const long long now_ = clock64(); acc += now_ - clk0; clk0 = now_; }
+#else
+#define PHASE_TICK(acc)
+#endif
     __syncthreads();
+#ifdef SYSID_PHASE_CLOCKS
+    clk0 = clock64();
+#endif
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * SB_SAMPLES;
         if (warp == 0) {
@@ -142,17 +151,23 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
             if (lane == 0) { s_wsum += w; s_flag0 += __popc(f0); s_flag1 += __popc(f1); }
         }
         __syncthreads();
+        PHASE_TICK(clkF)
         const int nsub = (int)min((long long)(SB_SAMPLES / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
         for (int sub = 0; sub < nsub; ++sub) {
             fill_tile(M, ctx, tile, sub * TILE_SAMPLES, args.friction, tid, GRAM_THREADS);
             __syncthreads();
+            PHASE_TICK(clkC)
             SYSID_WARP_SWITCH(mma_rows, tile, TILE_ROWS / 4, lane, acc)
             __syncthreads();
+            PHASE_TICK(clkM)
         }
     }
     double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
     SYSID_WARP_SWITCH(store_tiles, partial, lane, acc)
     if (tid == 0) {
+#ifdef SYSID_PHASE_CLOCKS
+        partial[GRAM_NTILES * 64 + 3] = (double)clkF; partial[GRAM_NTILES * 64 + 4] = (double)clkC; partial[GRAM_NTILES * 64 + 5] = (double)clkM;
+#endif
         partial[GRAM_NTILES * 64 + 0] = s_wsum;
         partial[GRAM_NTILES * 64 + 1] = (double)s_flag0;
         partial[GRAM_NTILES * 64 + 2] = (double)s_flag1;
