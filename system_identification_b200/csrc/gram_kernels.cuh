@@ -1,33 +1,53 @@
 // Stage 1+2 kernels: fused regressor -> projector -> Gram accumulation (never writes the stacked regressor),
 // plus the small debug/compat kernels that DO write per-sample blocks (parity tests, per-sample API).
 //
-// Fused kernel, one persistent CTA (512 threads, 16 warps) per SM, ~215 KB shared memory:
-//   F phase  warp 0, one lane per sample, 32 samples ("super-batch"): forward_sample() -> per-sample context
-//   C phase  all threads, one (sample, column) item each: column_item() -> one 18 x 160 projected row block per sample
-//            into the shared tile (4 samples = 72 rows at a time)
-//   M phase  all warps: DMMA (mma.sync m8n8k4 f64) rank-72 update of the 160 x 160 lower-triangular Gram held in
-//            registers (210 8x8 tiles over 16 warps, 13-14 tiles each, tables in gram_tiles.inc)
+// Fused kernel: one persistent, warp-specialised CTA (512 threads) per SM, ~194 KB shared memory.
+//   producers  warps 12..15 (one per SM sub-partition): the F phases of phases.cuh for a super-batch of 16 samples
+//              (per-sample context in shared memory), then per round of 2 samples the tile fill: one
+//              (sample, body, row) item per thread -> the 18 x 160 projected row block of each sample (36 rows)
+//              into one of two tile buffers
+//   consumers  warps 0..11 (three per sub-partition): DMMA (mma.sync m8n8k4 f64) rank-36 update of the 160 x 160
+//              lower-triangular Gram held in registers (210 8x8 tiles, 17-18 per warp, tables in gram_tiles.inc)
+// Producers and consumers hand tile buffers over through named barriers (full / empty per buffer), so the
+// latency-bound kinematics overlaps the FP64-pipe-bound contraction.
 // The tau column rides along as column c of the row block, so [A b]^T [A b] yields G, r = A^T b and s = b^T b at once.
 #pragma once
 #include <cuda_runtime.h>
-#include "kinematics.cuh"
+#include "phases.cuh"
 
 namespace sysid {
 
 #include "gram_tiles.inc"
 
-constexpr int GRAM_THREADS = 512;
-constexpr int GRAM_WARPS = GRAM_THREADS / 32;
-constexpr int SB_SAMPLES = 32;                 // samples per F phase
-constexpr int TILE_SAMPLES = 4;                // samples per C/M round
-constexpr int TILE_ROWS = TILE_SAMPLES * MAXV; // 72 = 18 k-steps of 4
 constexpr int TILE_LD = 164;                   // == 4 (mod 16): conflict-free DMMA fragment loads
+constexpr int PARTIAL_DOUBLES = GRAM_NTILES * 64 + 8;   // per CTA: tiles, then [wsum, flag0 count, flag1 count, 5 x phase clocks]
+
+// fused kernel geometry
+constexpr int GRAM_THREADS = 512;
+constexpr int CONS_WARPS = 12, PROD_WARPS = 4;
+constexpr int NCONS = CONS_WARPS * 32, NPROD = PROD_WARPS * 32;
+static_assert(NCONS + NPROD == GRAM_THREADS, "warp roles");
+constexpr int FSB = 16;                        // samples per super-batch (F phases)
+constexpr int FTS = 2;                         // samples per tile round
+constexpr int FROWS = FTS * MAXV;              // 36 = 9 k-steps of 4
+constexpr int FTILE = FROWS * TILE_LD;
+constexpr int NBUF = 2;
+static_assert(FROWS % 4 == 0 && FSB % FTS == 0, "k-steps of 4 rows");
+constexpr int FUSED_SMEM_DOUBLES = NBUF * FTILE + FSB * CX_STRIDE + FSB * SC_STRIDE;
+constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * FUSED_SMEM_DOUBLES;
+static_assert(GRAM_SMEM_BYTES + 1024 <= 232448, "shared memory budget");
+
+// stacked-matrix / rmse kernels: all 16 warps, 72-row tile
+constexpr int TILE_SAMPLES = 4;
+constexpr int TILE_ROWS = TILE_SAMPLES * MAXV;
 constexpr int TILE_DOUBLES = TILE_ROWS * TILE_LD;
-static_assert(TILE_ROWS % 4 == 0, "k-steps of 4 rows");
-static_assert(SCR_DOUBLES * SCR_LANES <= TILE_DOUBLES, "F-phase scratch aliases the tile");
-static_assert(sizeof(double) * (TILE_DOUBLES + SB_SAMPLES * CTX_STRIDE) + 1024 <= 232448, "shared memory budget");
-constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * (TILE_DOUBLES + SB_SAMPLES * CTX_STRIDE) + 64;
-constexpr int PARTIAL_DOUBLES = GRAM_NTILES * 64 + 8;   // per CTA: tiles, then [wsum, flag0 count, flag1 count]
+constexpr int STACK_WARPS = GRAM_THREADS / 32;
+
+enum { BAR_PROD = 1, BAR_FULL = 2, BAR_EMPTY = 2 + NBUF };
+static_assert(BAR_EMPTY + NBUF <= 16, "named barriers");
+
+__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -35,11 +55,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // rank-(4*ksteps) update of this warp's tiles from `tile` (rows x TILE_LD doubles in shared memory)
-template <int W>
-__device__ __forceinline__ void mma_rows(const double* __restrict__ tile, int ksteps, int lane, double (&acc)[GRAM_MAX_NT][2]) {
-    using T = WarpTiles<W>;
+template <int NW, int W, int MAXNT>
+__device__ __forceinline__ void mma_rows(const double* __restrict__ tile, int ksteps, int lane, double (&acc)[MAXNT][2]) {
+    using T = WarpTiles<NW, W>;
     const double* base = tile + (lane & 3) * TILE_LD + (lane >> 2);
-#pragma unroll 2
+#pragma unroll 3
     for (int ks = 0; ks < ksteps; ++ks) {
         double frag[T::NG];
 #pragma unroll
@@ -49,9 +69,9 @@ __device__ __forceinline__ void mma_rows(const double* __restrict__ tile, int ks
     }
 }
 
-template <int W>
-__device__ __forceinline__ void store_tiles(double* __restrict__ partial, int lane, const double (&acc)[GRAM_MAX_NT][2]) {
-    using T = WarpTiles<W>;
+template <int NW, int W, int MAXNT>
+__device__ __forceinline__ void store_tiles(double* __restrict__ partial, int lane, const double (&acc)[MAXNT][2]) {
+    using T = WarpTiles<NW, W>;
 #pragma unroll
     for (int t = 0; t < T::NT; ++t) {
         double2 v = make_double2(acc[t][0], acc[t][1]);
@@ -59,47 +79,43 @@ __device__ __forceinline__ void store_tiles(double* __restrict__ partial, int la
     }
 }
 
-#define SYSID_WARP_SWITCH(FN, ...)                                                              \
-    switch (warp) {                                                                             \
-        case 0: FN<0>(__VA_ARGS__); break;   case 1: FN<1>(__VA_ARGS__); break;                 \
-        case 2: FN<2>(__VA_ARGS__); break;   case 3: FN<3>(__VA_ARGS__); break;                 \
-        case 4: FN<4>(__VA_ARGS__); break;   case 5: FN<5>(__VA_ARGS__); break;                 \
-        case 6: FN<6>(__VA_ARGS__); break;   case 7: FN<7>(__VA_ARGS__); break;                 \
-        case 8: FN<8>(__VA_ARGS__); break;   case 9: FN<9>(__VA_ARGS__); break;                 \
-        case 10: FN<10>(__VA_ARGS__); break; case 11: FN<11>(__VA_ARGS__); break;               \
-        case 12: FN<12>(__VA_ARGS__); break; case 13: FN<13>(__VA_ARGS__); break;               \
-        case 14: FN<14>(__VA_ARGS__); break; default: FN<15>(__VA_ARGS__); break;               \
+#define SYSID_WARP_SWITCH12(FN, ...)                                                                            \
+    switch (warp) {                                                                                             \
+        case 0: FN<12, 0, CONS_MAXNT>(__VA_ARGS__); break;   case 1: FN<12, 1, CONS_MAXNT>(__VA_ARGS__); break;   \
+        case 2: FN<12, 2, CONS_MAXNT>(__VA_ARGS__); break;   case 3: FN<12, 3, CONS_MAXNT>(__VA_ARGS__); break;   \
+        case 4: FN<12, 4, CONS_MAXNT>(__VA_ARGS__); break;   case 5: FN<12, 5, CONS_MAXNT>(__VA_ARGS__); break;   \
+        case 6: FN<12, 6, CONS_MAXNT>(__VA_ARGS__); break;   case 7: FN<12, 7, CONS_MAXNT>(__VA_ARGS__); break;   \
+        case 8: FN<12, 8, CONS_MAXNT>(__VA_ARGS__); break;   case 9: FN<12, 9, CONS_MAXNT>(__VA_ARGS__); break;   \
+        case 10: FN<12, 10, CONS_MAXNT>(__VA_ARGS__); break; default: FN<12, 11, CONS_MAXNT>(__VA_ARGS__); break; \
     }
+#define SYSID_WARP_SWITCH16(FN, ...)                                                                              \
+    switch (warp) {                                                                                               \
+        case 0: FN<16, 0, STACK_MAXNT>(__VA_ARGS__); break;   case 1: FN<16, 1, STACK_MAXNT>(__VA_ARGS__); break;   \
+        case 2: FN<16, 2, STACK_MAXNT>(__VA_ARGS__); break;   case 3: FN<16, 3, STACK_MAXNT>(__VA_ARGS__); break;   \
+        case 4: FN<16, 4, STACK_MAXNT>(__VA_ARGS__); break;   case 5: FN<16, 5, STACK_MAXNT>(__VA_ARGS__); break;   \
+        case 6: FN<16, 6, STACK_MAXNT>(__VA_ARGS__); break;   case 7: FN<16, 7, STACK_MAXNT>(__VA_ARGS__); break;   \
+        case 8: FN<16, 8, STACK_MAXNT>(__VA_ARGS__); break;   case 9: FN<16, 9, STACK_MAXNT>(__VA_ARGS__); break;   \
+        case 10: FN<16, 10, STACK_MAXNT>(__VA_ARGS__); break; case 11: FN<16, 11, STACK_MAXNT>(__VA_ARGS__); break; \
+        case 12: FN<16, 12, STACK_MAXNT>(__VA_ARGS__); break; case 13: FN<16, 13, STACK_MAXNT>(__VA_ARGS__); break; \
+        case 14: FN<16, 14, STACK_MAXNT>(__VA_ARGS__); break; default: FN<16, 15, STACK_MAXNT>(__VA_ARGS__); break; \
+    }
+constexpr int CONS_MAXNT = WarpTiles<12, -1>::MAX_NT;
+constexpr int STACK_MAXNT = WarpTiles<16, -1>::MAX_NT;
 
-// C phase for TILE_SAMPLES samples starting at local sample s0 of the super-batch.  Items are visited in the
-// depth-sorted column order M.colperm, so that the lanes of a warp walk chains of (nearly) equal length.
-__device__ __noinline__ void fill_tile(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
-                                       int s0, int friction, int tid, int nthreads) {
-    const int np = M.nparams, nd = M.nd;
-    const int used = np + (friction ? 2 * nd : 0) + 1;      // columns that carry data (tau column last)
-    for (int it = tid; it < TILE_SAMPLES * CW; it += nthreads) {
-        const int sl = it / CW, pc = it - sl * CW;
-        const int col = M.colperm[pc];
-        if (col >= used) continue;
-        const double* c = ctx + (s0 + sl) * CTX_STRIDE;
-        const double wsq = c[CTX_W];
-        double out[MAXV], pval[MAXCH];
-        int prow[MAXCH];
-        double* dst = tile + (sl * MAXV) * TILE_LD + col;
-        if (wsq == 0.0) {
-#pragma unroll
-            for (int r = 0; r < MAXV; ++r) dst[r * TILE_LD] = 0.0;
-            continue;
-        }
-        // without friction columns the tau column follows the body columns directly
-        const int vcol = (!friction && col == np) ? np + 2 * nd : col;
-        column_item<true>(M, c, vcol, out, prow, pval);
-#pragma unroll
-        for (int r = 0; r < MAXV; ++r) dst[r * TILE_LD] = out[r] * wsq;
-#pragma unroll
-        for (int e = 0; e < MAXCH; ++e) if (prow[e] >= 0) dst[prow[e] * TILE_LD] += pval[e] * wsq;
-    }
-}
+// All F phases of one super-batch, executed by a group of NT threads (index t) separated by SYNC().
+#define SYSID_F_PHASES(SB, NT, SYNC)                                                                                     \
+    for (int it = t; it < SB * M.nfch; it += NT) phase_chains<SB>(M, args.io, base, args.N, ctx, scr, s_bad, it);        \
+    SYNC();                                                                                                              \
+    for (int it = t; it < SB * MAXEE; it += NT) phase_feet<SB>(M, args.io, base, args.N, ctx, scr, s_bad, it);           \
+    SYNC();                                                                                                              \
+    for (int it = t; it < SB * (MAXEE * (MAXEE + 1) / 2); it += NT) phase_sblocks<SB>(M, base, args.N, ctx, scr, it);    \
+    SYNC();                                                                                                              \
+    for (int it = t; it < SB; it += NT) phase_chol<SB>(base, args.N, ctx, scr, s_bad, it);                               \
+    SYNC();                                                                                                              \
+    for (int it = t; it < SB * MAXV; it += NT) phase_wcols<SB>(M, base, args.N, ctx, scr, it);                           \
+    SYNC();                                                                                                              \
+    phase_proj<SB, NT>(args.io, base, args.N, ctx, scr, s_bad, t, wsum, nflag0, nflag1);                                 \
+    SYNC();
 
 struct GramArgs {
     SampleIO io;
@@ -108,70 +124,96 @@ struct GramArgs {
     double* partial;      // [gridDim][PARTIAL_DOUBLES]
 };
 
-__global__ void __launch_bounds__(GRAM_THREADS, 1)
-gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
-    extern __shared__ __align__(16) double smem[];
-    double* tile = smem;
-    double* ctx = smem + TILE_DOUBLES;
-    double* scratch = smem;                    // aliases the tile: only live during the F phase
-    __shared__ double s_wsum;
-    __shared__ int s_flag0, s_flag1;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { s_wsum = 0.0; s_flag0 = 0; s_flag1 = 0; }
-    double acc[GRAM_MAX_NT][2];
-#pragma unroll
-    for (int t = 0; t < GRAM_MAX_NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    const long long nsb = (args.N + SB_SAMPLES - 1) / SB_SAMPLES;
 #ifdef SYSID_PHASE_CLOCKS
-    long long clkF = 0, clkC = 0, clkM = 0, clk0;
 #define PHASE_TICK(acc) { const long long now_ = clock64(); acc += now_ - clk0; clk0 = now_; }
 #else
 #define PHASE_TICK(acc)
+#endif
+
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
+    extern __shared__ __align__(16) double smem[];
+    double* tiles = smem;
+    double* ctx = smem + NBUF * FTILE;
+    double* scr = ctx + FSB * CX_STRIDE;
+    __shared__ double s_wsum;
+    __shared__ int s_flag0, s_flag1;
+    __shared__ int s_bad[FSB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) { s_wsum = 0.0; s_flag0 = 0; s_flag1 = 0; }
+    if (tid < FSB) s_bad[tid] = 0;
+    const long long nsb = (args.N + FSB - 1) / FSB;
+    // tile rounds this CTA runs: every super-batch is full (FSB / FTS rounds) except possibly the globally last one
+    long long total_rounds = 0;
+    if ((long long)blockIdx.x < nsb) {
+        const long long mine = (nsb - 1 - blockIdx.x) / gridDim.x + 1;
+        total_rounds = mine * (FSB / FTS);
+        if ((nsb - 1) % gridDim.x == blockIdx.x) {
+            const long long last = (args.N - (nsb - 1) * FSB + FTS - 1) / FTS;
+            total_rounds -= (FSB / FTS) - last;
+        }
+    }
+#ifdef SYSID_PHASE_CLOCKS
+    long long clkA = 0, clkB = 0, clkC = 0, clk0;
 #endif
     __syncthreads();
 #ifdef SYSID_PHASE_CLOCKS
     clk0 = clock64();
 #endif
-    for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
-        const long long base = sb * SB_SAMPLES;
-        if (warp == 0) {
-            const long long i = base + lane;
-            double* c = ctx + lane * CTX_STRIDE;
-            int flags = 0;
-            double w = 0.0;
-            if (i < args.N) {
-                flags = forward_sample(M, args.io, i, scratch + lane, c);
-                w = c[CTX_W]; w *= w;
-            } else {
-                c[CTX_W] = 0.0;
-            }
-            const unsigned f0 = __ballot_sync(0xffffffffu, flags & 1), f1 = __ballot_sync(0xffffffffu, flags & 2);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-            if (lane == 0) { s_wsum += w; s_flag0 += __popc(f0); s_flag1 += __popc(f1); }
-        }
-        __syncthreads();
-        PHASE_TICK(clkF)
-        const int nsub = (int)min((long long)(SB_SAMPLES / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
-        for (int sub = 0; sub < nsub; ++sub) {
-            fill_tile(M, ctx, tile, sub * TILE_SAMPLES, args.friction, tid, GRAM_THREADS);
-            __syncthreads();
-            PHASE_TICK(clkC)
-            SYSID_WARP_SWITCH(mma_rows, tile, TILE_ROWS / 4, lane, acc)
-            __syncthreads();
-            PHASE_TICK(clkM)
-        }
-    }
     double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
-    SYSID_WARP_SWITCH(store_tiles, partial, lane, acc)
+    if (warp >= CONS_WARPS) {
+        // ------------------------------------------------------------------ producers
+        const int t = tid - NCONS;
+        double wsum = 0.0;
+        int nflag0 = 0, nflag1 = 0;
+        long long rnd = 0;
+        auto psync = [] { named_sync(BAR_PROD, NPROD); };
+        for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
+            const long long base = sb * FSB;
+            SYSID_F_PHASES(FSB, NPROD, psync)
+            if (t < FSB) s_bad[t] = 0;
+            PHASE_TICK(clkA)
+            const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
+            for (int sub = 0; sub < nsub; ++sub, ++rnd) {
+                const int b = (int)(rnd % NBUF);
+                if (rnd >= NBUF) named_sync(BAR_EMPTY + b, GRAM_THREADS);
+                PHASE_TICK(clkC)
+                phase_fill<FTS, TILE_LD, NPROD>(M, ctx, tiles + b * FTILE, sub * FTS, args.friction, t);
+                __threadfence_block();
+                named_arrive(BAR_FULL + b, GRAM_THREADS);
+                PHASE_TICK(clkB)
+            }
+            psync();      // the next super-batch overwrites the context
+        }
+        if (wsum != 0.0) atomicAdd(&s_wsum, wsum);
+        if (nflag0) atomicAdd(&s_flag0, nflag0);
+        if (nflag1) atomicAdd(&s_flag1, nflag1);
+    } else {
+        // ------------------------------------------------------------------ consumers
+        double acc[CONS_MAXNT][2];
+#pragma unroll
+        for (int t = 0; t < CONS_MAXNT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+        for (long long rnd = 0; rnd < total_rounds; ++rnd) {
+            const int b = (int)(rnd % NBUF);
+            named_sync(BAR_FULL + b, GRAM_THREADS);
+            PHASE_TICK(clkA)
+            const double* tile = tiles + b * FTILE;
+            SYSID_WARP_SWITCH12(mma_rows, tile, FROWS / 4, lane, acc)
+            if (rnd + NBUF < total_rounds) named_arrive(BAR_EMPTY + b, GRAM_THREADS);
+            PHASE_TICK(clkB)
+        }
+        SYSID_WARP_SWITCH12(store_tiles, partial, lane, acc)
+    }
+    __syncthreads();
     if (tid == 0) {
-#ifdef SYSID_PHASE_CLOCKS
-        partial[GRAM_NTILES * 64 + 3] = (double)clkF; partial[GRAM_NTILES * 64 + 4] = (double)clkC; partial[GRAM_NTILES * 64 + 5] = (double)clkM;
-#endif
         partial[GRAM_NTILES * 64 + 0] = s_wsum;
         partial[GRAM_NTILES * 64 + 1] = (double)s_flag0;
         partial[GRAM_NTILES * 64 + 2] = (double)s_flag1;
     }
+#ifdef SYSID_PHASE_CLOCKS
+    if (tid == NCONS) { partial[GRAM_NTILES * 64 + 3] = (double)clkA; partial[GRAM_NTILES * 64 + 4] = (double)clkB; partial[GRAM_NTILES * 64 + 5] = (double)clkC; }
+    if (tid == 0) { partial[GRAM_NTILES * 64 + 6] = (double)clkA; partial[GRAM_NTILES * 64 + 7] = (double)clkB; }
+#endif
 }
 
 // Gram of an already stacked matrix: rows x c (row-major) and b (rows); same M phase, tile filled by plain loads.
@@ -184,9 +226,9 @@ gram_stack_kernel(const StackArgs args) {
     extern __shared__ __align__(16) double smem[];
     double* tile = smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double acc[GRAM_MAX_NT][2];
+    double acc[STACK_MAXNT][2];
 #pragma unroll
-    for (int t = 0; t < GRAM_MAX_NT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    for (int t = 0; t < STACK_MAXNT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
     const int c = args.c;
     const long long nchunks = (args.rows + TILE_ROWS - 1) / TILE_ROWS;
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
@@ -202,11 +244,11 @@ gram_stack_kernel(const StackArgs args) {
             tile[r * TILE_LD + col] = v;
         }
         __syncthreads();
-        SYSID_WARP_SWITCH(mma_rows, tile, TILE_ROWS / 4, lane, acc)
+        SYSID_WARP_SWITCH16(mma_rows, tile, TILE_ROWS / 4, lane, acc)
         __syncthreads();
     }
     double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
-    SYSID_WARP_SWITCH(store_tiles, partial, lane, acc)
+    SYSID_WARP_SWITCH16(store_tiles, partial, lane, acc)
     if (tid == 0) {
         partial[GRAM_NTILES * 64 + 0] = 0.0; partial[GRAM_NTILES * 64 + 1] = 0.0; partial[GRAM_NTILES * 64 + 2] = 0.0;
     }
@@ -255,6 +297,7 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int npart
 // MODE 0: raw regressor Y (N x nv x nparams).  MODE 1: projected A (N x nv x ncols), b (N x nv), optional P.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int DBG_THREADS = 256;
+constexpr int SB_SAMPLES = 32;   // samples per CTA of the per-sample kernels (one lane each in forward_sample)
 constexpr size_t DBG_SMEM_BYTES = sizeof(double) * (SCR_DOUBLES * SCR_LANES + SB_SAMPLES * CTX_STRIDE);
 
 struct BatchArgs {
@@ -321,6 +364,7 @@ sample_batch_kernel(const __grid_constant__ DevModel M, const BatchArgs args) {
 // partial per CTA: [sum_i ||e_i||^2, per-joint sum of squares (MAXD), count]
 // ------------------------------------------------------------------------------------------------------------
 constexpr int RMSE_PARTIAL = MAXD + 2;
+constexpr size_t RMSE_SMEM_BYTES = sizeof(double) * (TILE_DOUBLES + FSB * CX_STRIDE + FSB * SC_STRIDE);
 
 struct RmseArgs {
     SampleIO io; long long N; const double* phi; double* partial;
@@ -331,29 +375,28 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
     extern __shared__ __align__(16) double smem[];
     double* tile = smem;
     double* ctx = smem + TILE_DOUBLES;
-    double* scratch = smem;
+    double* scr = ctx + FSB * CX_STRIDE;
     __shared__ double s_x[CW];
     __shared__ double s_acc[RMSE_PARTIAL];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    __shared__ int s_bad[FSB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
     const int np = M.nparams, nd = M.nd;
     if (tid < CW) s_x[tid] = (tid < np) ? args.phi[tid] : ((tid == np + 2 * nd) ? -1.0 : 0.0);
     if (tid < RMSE_PARTIAL) s_acc[tid] = 0.0;
-    const long long nsb = (args.N + SB_SAMPLES - 1) / SB_SAMPLES;
+    if (tid < FSB) s_bad[tid] = 0;
+    double wsum = 0.0;
+    int nflag0 = 0, nflag1 = 0;
+    const long long nsb = (args.N + FSB - 1) / FSB;
     __syncthreads();
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
-        const long long base = sb * SB_SAMPLES;
-        if (warp == 0) {
-            const long long i = base + lane;
-            double* c = ctx + lane * CTX_STRIDE;
-            if (i < args.N) forward_sample(M, args.io, i, scratch + lane, c);
-            else c[CTX_W] = 0.0;
-        }
-        __syncthreads();
-        const int nsub = (int)min((long long)(SB_SAMPLES / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
+        const long long base = sb * FSB;
+        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads)
+        if (t < FSB) s_bad[t] = 0;
+        const int nsub = (int)min((long long)(FSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
         for (int sub = 0; sub < nsub; ++sub) {
-            fill_tile(M, ctx, tile, sub * TILE_SAMPLES, 1, tid, GRAM_THREADS);
+            phase_fill<TILE_SAMPLES, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * TILE_SAMPLES, 1, t);
             __syncthreads();
-            for (int row = warp; row < TILE_ROWS; row += GRAM_WARPS) {
+            for (int row = warp; row < TILE_ROWS; row += STACK_WARPS) {
                 const int rr = row % MAXV;
                 if (rr < 6 || rr >= M.nv) continue;
                 const long long i = base + sub * TILE_SAMPLES + row / MAXV;
@@ -370,6 +413,7 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
             __syncthreads();
         }
     }
+    (void)wsum; (void)nflag0; (void)nflag1;
     if (tid < RMSE_PARTIAL - 1) args.partial[(size_t)blockIdx.x * RMSE_PARTIAL + tid] = s_acc[tid];
 }
 

@@ -31,7 +31,13 @@ struct DevModel {
     int32_t chain_len[MAXEE];
     int32_t chain[MAXEE][MAXCH];
     int32_t nshared[MAXEE][MAXEE];   // length of the common suffix of two foot chains
-    uint8_t colperm[CW];             // C-phase visiting order of the padded columns: sorted by chain depth (warp-uniform work)
+    uint8_t colperm[CW];             // per-sample debug kernels: visiting order of the padded columns, sorted by chain depth
+    // leaf chains for the chain phase of the fused kernels: fch[c][e] = e-th joint walking from the ROOT towards leaf c
+    // (root excluded); joints [fch_own[c], fch_len[c]) are written by chain c, the shared prefix by an earlier chain
+    int32_t nfch;
+    int32_t fch_len[MAXD];
+    int32_t fch_own[MAXD];
+    int32_t fch[MAXD][MAXCH];
 };
 
 }  // namespace sysid

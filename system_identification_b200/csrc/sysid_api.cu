@@ -138,6 +138,23 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
         for (int wv = 2 + MAXCH; wv >= 0; --wv)
             for (int c = 0; c < CW; ++c) if (work[c] == wv) M.colperm[n++] = (uint8_t)c;
     }
+    // leaf chains (root -> leaf), each joint owned by the first chain that contains it
+    {
+        bool has_child[MAXJ] = {false}, owned[MAXJ] = {false};
+        for (int j = 2; j < d->njoints; ++j) has_child[M.parent[j]] = true;
+        M.nfch = 0;
+        for (int j = 2; j < d->njoints; ++j) {
+            if (has_child[j]) continue;
+            const int c = M.nfch++;
+            int len = depth[j], e = len;
+            for (int k = j; k > 1; k = M.parent[k]) M.fch[c][--e] = k;
+            M.fch_len[c] = len;
+            int own = 0;
+            while (own < len && owned[M.fch[c][own]]) ++own;
+            M.fch_own[c] = own;
+            for (int k = own; k < len; ++k) owned[M.fch[c][k]] = true;
+        }
+    }
     int rc = device_sm_count(&m->sm_count);
     if (rc != SYSID_OK) { delete m; return rc; }
     *out = m;
@@ -224,7 +241,7 @@ int sysid_gram_accumulate(const sysid_model* model, const double* q, const doubl
     if (N == 0) return SYSID_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const DevModel& M = model->dev;
-    const long long nsb = (N + SB_SAMPLES - 1) / SB_SAMPLES;
+    const long long nsb = (N + FSB - 1) / FSB;
     const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
     if (workspace_bytes < sizeof(double) * (size_t)grid * PARTIAL_DOUBLES)
         return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, sizeof(double) * (size_t)grid * PARTIAL_DOUBLES);
@@ -280,15 +297,15 @@ int sysid_predict_rmse(const sysid_model* model, const double* q, const double* 
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N <= 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long nsb = (N + SB_SAMPLES - 1) / SB_SAMPLES;
+    const long long nsb = (N + FSB - 1) / FSB;
     const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
     if (workspace_bytes < sizeof(double) * (size_t)grid * RMSE_PARTIAL) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
-    int rc = opt_in_smem(rmse_kernel, GRAM_SMEM_BYTES);
+    int rc = opt_in_smem(rmse_kernel, RMSE_SMEM_BYTES);
     if (rc) return rc;
     RmseArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
     a.N = N; a.phi = phi; a.partial = (double*)workspace;
-    rmse_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(model->dev, a);
+    rmse_kernel<<<grid, GRAM_THREADS, RMSE_SMEM_BYTES, st>>>(model->dev, a);
     CUDA_TRY(cudaGetLastError());
     rmse_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, grid, model->dev.nd, N, out);
     CUDA_TRY(cudaGetLastError());
