@@ -1,15 +1,17 @@
 // Stage 1+2 kernels: fused regressor -> projector -> Gram accumulation (never writes the stacked regressor),
 // plus the small debug/compat kernels that DO write per-sample blocks (parity tests, per-sample API).
 //
-// Fused kernel: one persistent, warp-specialised CTA (512 threads) per SM, ~194 KB shared memory.
-//   producers  warps 12..15 (one per SM sub-partition): the F phases of phases.cuh for a super-batch of 16 samples
-//              (per-sample context in shared memory), then per round of 2 samples the tile fill: one
-//              (sample, body, row) item per thread -> the 18 x 160 projected row block of each sample (36 rows)
-//              into one of two tile buffers
-//   consumers  warps 0..11 (three per sub-partition): DMMA (mma.sync m8n8k4 f64) rank-36 update of the 160 x 160
-//              lower-triangular Gram held in registers (210 8x8 tiles, 17-18 per warp, tables in gram_tiles.inc)
-// Producers and consumers hand tile buffers over through named barriers (full / empty per buffer), so the
-// latency-bound kinematics overlaps the FP64-pipe-bound contraction.
+// Fused kernel: one persistent CTA (512 threads, 16 warps) per SM, ~200 KB shared memory, phases separated by
+// CTA barriers:
+//   F phases  (phases.cuh) for a super-batch of FSB samples: chains -> feet -> S blocks -> Cholesky -> W columns ->
+//             P = I - W^T W; per-sample context (P, Pluecker axes, poses, body motions) stays in shared memory
+//   per round of FTS samples:
+//     fill    all threads, one (sample, body, row) item each -> the 18 x 160 projected row block of each sample
+//     M       all warps: DMMA (mma.sync m8n8k4 f64) rank-(18 FTS) update of the 160 x 160 lower-triangular Gram held in
+//             registers (210 8x8 tiles, 13-14 per warp, tables in gram_tiles.inc)
+// Why phased and not warp-specialised: on B200 a DFMA warp that shares an SM sub-partition with saturating DMMA warps
+// gets one issue slot per ~80-110 clk (tools/fp64_mix.cu, profiles/fp64_mix_r01.json), so producers starve exactly when
+// consumers are busy; a specialised variant of this kernel measured 24-30 Msamples/s (profiles/phase_clocks_r01_*.txt).
 // The tau column rides along as column c of the row block, so [A b]^T [A b] yields G, r = A^T b and s = b^T b at once.
 #pragma once
 #include <cuda_runtime.h>
@@ -20,34 +22,43 @@ namespace sysid {
 #include "gram_tiles.inc"
 
 constexpr int TILE_LD = 164;                   // == 4 (mod 16): conflict-free DMMA fragment loads
-constexpr int PARTIAL_DOUBLES = GRAM_NTILES * 64 + 8;   // per CTA: tiles, then [wsum, flag0 count, flag1 count, 5 x phase clocks]
+constexpr int PARTIAL_DOUBLES = GRAM_NTILES * 64 + 16;  // per CTA: tiles, then [wsum, flag0 count, flag1 count, phase clocks]
 
-// fused kernel geometry
 constexpr int GRAM_THREADS = 512;
-constexpr int CONS_WARPS = 12, PROD_WARPS = 4;
-constexpr int NCONS = CONS_WARPS * 32, NPROD = PROD_WARPS * 32;
-static_assert(NCONS + NPROD == GRAM_THREADS, "warp roles");
-constexpr int FSB = 16;                        // samples per super-batch (F phases)
-constexpr int FTS = 2;                         // samples per tile round
-constexpr int FROWS = FTS * MAXV;              // 36 = 9 k-steps of 4
+constexpr int GRAM_WARPS = GRAM_THREADS / 32;
+#ifndef SYSID_MMA_UNROLL
+#define SYSID_MMA_UNROLL 2
+#endif
+#ifndef SYSID_FTS
+#define SYSID_FTS 4
+#endif
+#ifndef SYSID_FSB
+#define SYSID_FSB 28
+#endif
+#ifndef SYSID_FILL_CHAINS
+#define SYSID_FILL_CHAINS 1
+#endif
+#ifndef SYSID_RPI
+#define SYSID_RPI 1
+#endif
+constexpr int MMA_UNROLL = SYSID_MMA_UNROLL;
+constexpr int FTS = SYSID_FTS;                 // samples per tile round
+constexpr int FSB = SYSID_FSB;                 // samples per super-batch (F phases)
+constexpr int FILL_RPI = SYSID_RPI;            // rows per fill item
+constexpr int FROWS = FTS * MAXV;
 constexpr int FTILE = FROWS * TILE_LD;
-constexpr int NBUF = 2;
 static_assert(FROWS % 4 == 0 && FSB % FTS == 0, "k-steps of 4 rows");
-constexpr int FUSED_SMEM_DOUBLES = NBUF * FTILE + FSB * CX_STRIDE + FSB * SC_STRIDE;
-constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * FUSED_SMEM_DOUBLES;
+// the F-phase scratch aliases the tile (never live together)
+constexpr int FUSED_FSCR = FSB * (SC_STRIDE + IN_CHANNELS);     // scratch, then the staged inputs
+constexpr int FUSED_FRONT = (FTILE > FUSED_FSCR) ? FTILE : FUSED_FSCR;
+constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * (FUSED_FRONT + FSB * CX_STRIDE);
 static_assert(GRAM_SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 
-// stacked-matrix / rmse kernels: all 16 warps, 72-row tile
+// stacked-matrix / rmse kernels: 72-row tile
 constexpr int TILE_SAMPLES = 4;
 constexpr int TILE_ROWS = TILE_SAMPLES * MAXV;
 constexpr int TILE_DOUBLES = TILE_ROWS * TILE_LD;
-constexpr int STACK_WARPS = GRAM_THREADS / 32;
-
-enum { BAR_PROD = 1, BAR_FULL = 2, BAR_EMPTY = 2 + NBUF };
-static_assert(BAR_EMPTY + NBUF <= 16, "named barriers");
-
-__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+constexpr int RSB = 16;                        // rmse kernel: samples per super-batch
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -59,7 +70,7 @@ template <int NW, int W, int MAXNT>
 __device__ __forceinline__ void mma_rows(const double* __restrict__ tile, int ksteps, int lane, double (&acc)[MAXNT][2]) {
     using T = WarpTiles<NW, W>;
     const double* base = tile + (lane & 3) * TILE_LD + (lane >> 2);
-#pragma unroll 3
+#pragma unroll MMA_UNROLL
     for (int ks = 0; ks < ksteps; ++ks) {
         double frag[T::NG];
 #pragma unroll
@@ -79,42 +90,45 @@ __device__ __forceinline__ void store_tiles(double* __restrict__ partial, int la
     }
 }
 
-#define SYSID_WARP_SWITCH12(FN, ...)                                                                            \
-    switch (warp) {                                                                                             \
-        case 0: FN<12, 0, CONS_MAXNT>(__VA_ARGS__); break;   case 1: FN<12, 1, CONS_MAXNT>(__VA_ARGS__); break;   \
-        case 2: FN<12, 2, CONS_MAXNT>(__VA_ARGS__); break;   case 3: FN<12, 3, CONS_MAXNT>(__VA_ARGS__); break;   \
-        case 4: FN<12, 4, CONS_MAXNT>(__VA_ARGS__); break;   case 5: FN<12, 5, CONS_MAXNT>(__VA_ARGS__); break;   \
-        case 6: FN<12, 6, CONS_MAXNT>(__VA_ARGS__); break;   case 7: FN<12, 7, CONS_MAXNT>(__VA_ARGS__); break;   \
-        case 8: FN<12, 8, CONS_MAXNT>(__VA_ARGS__); break;   case 9: FN<12, 9, CONS_MAXNT>(__VA_ARGS__); break;   \
-        case 10: FN<12, 10, CONS_MAXNT>(__VA_ARGS__); break; default: FN<12, 11, CONS_MAXNT>(__VA_ARGS__); break; \
+// warp-uniform dispatch to the per-warp tile tables
+template <int NW, int MAXNT, int W = 0>
+__device__ __forceinline__ void mma_dispatch(int w, const double* __restrict__ tile, int ksteps, int lane, double (&acc)[MAXNT][2]) {
+    if constexpr (W < NW) {
+        if (w == W) mma_rows<NW, W, MAXNT>(tile, ksteps, lane, acc);
+        else mma_dispatch<NW, MAXNT, W + 1>(w, tile, ksteps, lane, acc);
     }
-#define SYSID_WARP_SWITCH16(FN, ...)                                                                              \
-    switch (warp) {                                                                                               \
-        case 0: FN<16, 0, STACK_MAXNT>(__VA_ARGS__); break;   case 1: FN<16, 1, STACK_MAXNT>(__VA_ARGS__); break;   \
-        case 2: FN<16, 2, STACK_MAXNT>(__VA_ARGS__); break;   case 3: FN<16, 3, STACK_MAXNT>(__VA_ARGS__); break;   \
-        case 4: FN<16, 4, STACK_MAXNT>(__VA_ARGS__); break;   case 5: FN<16, 5, STACK_MAXNT>(__VA_ARGS__); break;   \
-        case 6: FN<16, 6, STACK_MAXNT>(__VA_ARGS__); break;   case 7: FN<16, 7, STACK_MAXNT>(__VA_ARGS__); break;   \
-        case 8: FN<16, 8, STACK_MAXNT>(__VA_ARGS__); break;   case 9: FN<16, 9, STACK_MAXNT>(__VA_ARGS__); break;   \
-        case 10: FN<16, 10, STACK_MAXNT>(__VA_ARGS__); break; case 11: FN<16, 11, STACK_MAXNT>(__VA_ARGS__); break; \
-        case 12: FN<16, 12, STACK_MAXNT>(__VA_ARGS__); break; case 13: FN<16, 13, STACK_MAXNT>(__VA_ARGS__); break; \
-        case 14: FN<16, 14, STACK_MAXNT>(__VA_ARGS__); break; default: FN<16, 15, STACK_MAXNT>(__VA_ARGS__); break; \
+}
+template <int NW, int MAXNT, int W = 0>
+__device__ __forceinline__ void store_dispatch(int w, double* __restrict__ partial, int lane, const double (&acc)[MAXNT][2]) {
+    if constexpr (W < NW) {
+        if (w == W) store_tiles<NW, W, MAXNT>(partial, lane, acc);
+        else store_dispatch<NW, MAXNT, W + 1>(w, partial, lane, acc);
     }
-constexpr int CONS_MAXNT = WarpTiles<12, -1>::MAX_NT;
-constexpr int STACK_MAXNT = WarpTiles<16, -1>::MAX_NT;
+}
+constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
 
 // All F phases of one super-batch, executed by a group of NT threads (index t) separated by SYNC().
 #define SYSID_F_PHASES(SB, NT, SYNC)                                                                                     \
-    for (int it = t; it < SB * M.nfch; it += NT) phase_chains<SB>(M, args.io, base, args.N, ctx, scr, s_bad, it);        \
+    phase_stage<SB, NT>(M, args.io, base, args.N, inp, t);                                                               \
     SYNC();                                                                                                              \
-    for (int it = t; it < SB * MAXEE; it += NT) phase_feet<SB>(M, args.io, base, args.N, ctx, scr, s_bad, it);           \
+    for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, scr, s_bad, it);                   \
+    SYNC();                                                                                                              \
+    F_TICK(0)                                                                                                            \
+    for (int it = t; it < SB * M.nfch; it += NT) phase_chains<SB>(M, base, args.N, inp, ctx, scr, it);                   \
+    SYNC();                                                                                                              \
+    F_TICK(1)                                                                                                            \
+    for (int it = t; it < SB * MAXEE; it += NT) phase_feet<SB>(M, base, args.N, inp, ctx, scr, it);                      \
     SYNC();                                                                                                              \
     for (int it = t; it < SB * (MAXEE * (MAXEE + 1) / 2); it += NT) phase_sblocks<SB>(M, base, args.N, ctx, scr, it);    \
     SYNC();                                                                                                              \
+    F_TICK(2)                                                                                                            \
     for (int it = t; it < SB; it += NT) phase_chol<SB>(base, args.N, ctx, scr, s_bad, it);                               \
     SYNC();                                                                                                              \
+    F_TICK(3)                                                                                                            \
     for (int it = t; it < SB * MAXV; it += NT) phase_wcols<SB>(M, base, args.N, ctx, scr, it);                           \
     SYNC();                                                                                                              \
-    phase_proj<SB, NT>(args.io, base, args.N, ctx, scr, s_bad, t, wsum, nflag0, nflag1);                                 \
+    F_TICK(4)                                                                                                            \
+    phase_proj<SB, NT>(base, args.N, inp, ctx, scr, s_bad, t, s_stat);                                                   \
     SYNC();
 
 struct GramArgs {
@@ -126,94 +140,74 @@ struct GramArgs {
 
 #ifdef SYSID_PHASE_CLOCKS
 #define PHASE_TICK(acc) { const long long now_ = clock64(); acc += now_ - clk0; clk0 = now_; }
+#define F_TICK(k) PHASE_TICK(clkSub[k])
 #else
 #define PHASE_TICK(acc)
+#define F_TICK(k)
 #endif
 
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     extern __shared__ __align__(16) double smem[];
-    double* tiles = smem;
-    double* ctx = smem + NBUF * FTILE;
-    double* scr = ctx + FSB * CX_STRIDE;
-    __shared__ double s_wsum;
-    __shared__ int s_flag0, s_flag1;
+    double* tile = smem;
+    double* scr = smem;                        // aliases the tile: only live during the F phases
+    double* inp = smem + FSB * SC_STRIDE;
+    double* ctx = smem + FUSED_FRONT;
+    __shared__ double s_stat[3];               // sum of weights, rank-loss count, skipped count
     __shared__ int s_bad[FSB];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) { s_wsum = 0.0; s_flag0 = 0; s_flag1 = 0; }
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
+    if (tid < 3) s_stat[tid] = 0.0;
     if (tid < FSB) s_bad[tid] = 0;
+    double acc[GRAM_MAXNT][2];
+#pragma unroll
+    for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
     const long long nsb = (args.N + FSB - 1) / FSB;
-    // tile rounds this CTA runs: every super-batch is full (FSB / FTS rounds) except possibly the globally last one
-    long long total_rounds = 0;
-    if ((long long)blockIdx.x < nsb) {
-        const long long mine = (nsb - 1 - blockIdx.x) / gridDim.x + 1;
-        total_rounds = mine * (FSB / FTS);
-        if ((nsb - 1) % gridDim.x == blockIdx.x) {
-            const long long last = (args.N - (nsb - 1) * FSB + FTS - 1) / FTS;
-            total_rounds -= (FSB / FTS) - last;
-        }
-    }
 #ifdef SYSID_PHASE_CLOCKS
-    long long clkA = 0, clkB = 0, clkC = 0, clk0;
+    long long clkF = 0, clkC = 0, clkM = 0, clk0, clkSub[5] = {0, 0, 0, 0, 0};
 #endif
     __syncthreads();
 #ifdef SYSID_PHASE_CLOCKS
     clk0 = clock64();
 #endif
-    double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
-    if (warp >= CONS_WARPS) {
-        // ------------------------------------------------------------------ producers
-        const int t = tid - NCONS;
-        double wsum = 0.0;
-        int nflag0 = 0, nflag1 = 0;
-        long long rnd = 0;
-        auto psync = [] { named_sync(BAR_PROD, NPROD); };
-        for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
-            const long long base = sb * FSB;
-            SYSID_F_PHASES(FSB, NPROD, psync)
-            if (t < FSB) s_bad[t] = 0;
-            PHASE_TICK(clkA)
-            const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
-            for (int sub = 0; sub < nsub; ++sub, ++rnd) {
-                const int b = (int)(rnd % NBUF);
-                if (rnd >= NBUF) named_sync(BAR_EMPTY + b, GRAM_THREADS);
-                PHASE_TICK(clkC)
-                phase_fill<FTS, TILE_LD, NPROD>(M, ctx, tiles + b * FTILE, sub * FTS, args.friction, t);
-                __threadfence_block();
-                named_arrive(BAR_FULL + b, GRAM_THREADS);
-                PHASE_TICK(clkB)
-            }
-            psync();      // the next super-batch overwrites the context
-        }
-        if (wsum != 0.0) atomicAdd(&s_wsum, wsum);
-        if (nflag0) atomicAdd(&s_flag0, nflag0);
-        if (nflag1) atomicAdd(&s_flag1, nflag1);
-    } else {
-        // ------------------------------------------------------------------ consumers
-        double acc[CONS_MAXNT][2];
-#pragma unroll
-        for (int t = 0; t < CONS_MAXNT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-        for (long long rnd = 0; rnd < total_rounds; ++rnd) {
-            const int b = (int)(rnd % NBUF);
-            named_sync(BAR_FULL + b, GRAM_THREADS);
-            PHASE_TICK(clkA)
-            const double* tile = tiles + b * FTILE;
-            SYSID_WARP_SWITCH12(mma_rows, tile, FROWS / 4, lane, acc)
-            if (rnd + NBUF < total_rounds) named_arrive(BAR_EMPTY + b, GRAM_THREADS);
-            PHASE_TICK(clkB)
-        }
-        SYSID_WARP_SWITCH12(store_tiles, partial, lane, acc)
-    }
-    __syncthreads();
-    if (tid == 0) {
-        partial[GRAM_NTILES * 64 + 0] = s_wsum;
-        partial[GRAM_NTILES * 64 + 1] = (double)s_flag0;
-        partial[GRAM_NTILES * 64 + 2] = (double)s_flag1;
-    }
-#ifdef SYSID_PHASE_CLOCKS
-    if (tid == NCONS) { partial[GRAM_NTILES * 64 + 3] = (double)clkA; partial[GRAM_NTILES * 64 + 4] = (double)clkB; partial[GRAM_NTILES * 64 + 5] = (double)clkC; }
-    if (tid == 0) { partial[GRAM_NTILES * 64 + 6] = (double)clkA; partial[GRAM_NTILES * 64 + 7] = (double)clkB; }
+    for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
+        const long long base = sb * FSB;
+#ifdef SYSID_ONLY_M      // diagnostic: F phases and fill only for the first super-batch, then the M phase on a static tile
+        if (sb == blockIdx.x) {
 #endif
+        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads)
+#ifdef SYSID_ONLY_M
+        }
+#endif
+        if (t < FSB) s_bad[t] = 0;
+        PHASE_TICK(clkF)
+        const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
+        for (int sub = 0; sub < nsub; ++sub) {
+#ifdef SYSID_ONLY_M
+            if (sb == blockIdx.x && sub == 0)
+#endif
+#if SYSID_FILL_CHAINS
+            phase_fill_chains<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
+#else
+            phase_fill<FTS, TILE_LD, GRAM_THREADS, FILL_RPI>(M, ctx, tile, sub * FTS, args.friction, t);
+#endif
+            __syncthreads();
+            PHASE_TICK(clkC)
+            mma_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, tile, FROWS / 4, lane, acc);
+            __syncthreads();
+            PHASE_TICK(clkM)
+        }
+    }
+    double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
+    store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+    if (tid == 0) {
+        partial[GRAM_NTILES * 64 + 0] = s_stat[0];
+        partial[GRAM_NTILES * 64 + 1] = s_stat[1];
+        partial[GRAM_NTILES * 64 + 2] = s_stat[2];
+#ifdef SYSID_PHASE_CLOCKS
+        partial[GRAM_NTILES * 64 + 3] = (double)clkF; partial[GRAM_NTILES * 64 + 4] = (double)clkC; partial[GRAM_NTILES * 64 + 5] = (double)clkM;
+        for (int k = 0; k < 5; ++k) partial[GRAM_NTILES * 64 + 6 + k] = (double)clkSub[k];
+#endif
+    }
 }
 
 // Gram of an already stacked matrix: rows x c (row-major) and b (rows); same M phase, tile filled by plain loads.
@@ -226,9 +220,9 @@ gram_stack_kernel(const StackArgs args) {
     extern __shared__ __align__(16) double smem[];
     double* tile = smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    double acc[STACK_MAXNT][2];
+    double acc[GRAM_MAXNT][2];
 #pragma unroll
-    for (int t = 0; t < STACK_MAXNT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    for (int t = 0; t < GRAM_MAXNT; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
     const int c = args.c;
     const long long nchunks = (args.rows + TILE_ROWS - 1) / TILE_ROWS;
     for (long long ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
@@ -244,11 +238,11 @@ gram_stack_kernel(const StackArgs args) {
             tile[r * TILE_LD + col] = v;
         }
         __syncthreads();
-        SYSID_WARP_SWITCH16(mma_rows, tile, TILE_ROWS / 4, lane, acc)
+        mma_dispatch<16, GRAM_MAXNT>(warp, tile, TILE_ROWS / 4, lane, acc);
         __syncthreads();
     }
     double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
-    SYSID_WARP_SWITCH16(store_tiles, partial, lane, acc)
+    store_dispatch<16, GRAM_MAXNT>(warp, partial, lane, acc);
     if (tid == 0) {
         partial[GRAM_NTILES * 64 + 0] = 0.0; partial[GRAM_NTILES * 64 + 1] = 0.0; partial[GRAM_NTILES * 64 + 2] = 0.0;
     }
@@ -364,7 +358,8 @@ sample_batch_kernel(const __grid_constant__ DevModel M, const BatchArgs args) {
 // partial per CTA: [sum_i ||e_i||^2, per-joint sum of squares (MAXD), count]
 // ------------------------------------------------------------------------------------------------------------
 constexpr int RMSE_PARTIAL = MAXD + 2;
-constexpr size_t RMSE_SMEM_BYTES = sizeof(double) * (TILE_DOUBLES + FSB * CX_STRIDE + FSB * SC_STRIDE);
+constexpr size_t RMSE_SMEM_BYTES = sizeof(double) * (TILE_DOUBLES + RSB * CX_STRIDE);
+static_assert(RSB * (SC_STRIDE + IN_CHANNELS) <= TILE_DOUBLES, "rmse scratch aliases the tile");
 
 struct RmseArgs {
     SampleIO io; long long N; const double* phi; double* partial;
@@ -375,28 +370,31 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
     extern __shared__ __align__(16) double smem[];
     double* tile = smem;
     double* ctx = smem + TILE_DOUBLES;
-    double* scr = ctx + FSB * CX_STRIDE;
+    double* scr = smem;                        // aliases the tile
+    double* inp = smem + RSB * SC_STRIDE;
     __shared__ double s_x[CW];
     __shared__ double s_acc[RMSE_PARTIAL];
-    __shared__ int s_bad[FSB];
+    __shared__ int s_bad[RSB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
     const int np = M.nparams, nd = M.nd;
     if (tid < CW) s_x[tid] = (tid < np) ? args.phi[tid] : ((tid == np + 2 * nd) ? -1.0 : 0.0);
     if (tid < RMSE_PARTIAL) s_acc[tid] = 0.0;
-    if (tid < FSB) s_bad[tid] = 0;
-    double wsum = 0.0;
-    int nflag0 = 0, nflag1 = 0;
-    const long long nsb = (args.N + FSB - 1) / FSB;
+    if (tid < RSB) s_bad[tid] = 0;
+    __shared__ double s_stat[3];
+#ifdef SYSID_PHASE_CLOCKS
+    long long clk0 = 0, clkSub[5] = {0, 0, 0, 0, 0};
+#endif
+    const long long nsb = (args.N + RSB - 1) / RSB;
     __syncthreads();
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
-        const long long base = sb * FSB;
-        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads)
-        if (t < FSB) s_bad[t] = 0;
-        const int nsub = (int)min((long long)(FSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
+        const long long base = sb * RSB;
+        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads)
+        if (t < RSB) s_bad[t] = 0;
+        const int nsub = (int)min((long long)(RSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
         for (int sub = 0; sub < nsub; ++sub) {
-            phase_fill<TILE_SAMPLES, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * TILE_SAMPLES, 1, t);
+            phase_fill<TILE_SAMPLES, TILE_LD, GRAM_THREADS, 1>(M, ctx, tile, sub * TILE_SAMPLES, 1, t);
             __syncthreads();
-            for (int row = warp; row < TILE_ROWS; row += STACK_WARPS) {
+            for (int row = warp; row < TILE_ROWS; row += GRAM_WARPS) {
                 const int rr = row % MAXV;
                 if (rr < 6 || rr >= M.nv) continue;
                 const long long i = base + sub * TILE_SAMPLES + row / MAXV;
@@ -413,7 +411,6 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
             __syncthreads();
         }
     }
-    (void)wsum; (void)nflag0; (void)nflag1;
     if (tid < RMSE_PARTIAL - 1) args.partial[(size_t)blockIdx.x * RMSE_PARTIAL + tid] = s_acc[tid];
 }
 

@@ -19,8 +19,8 @@
 //   sblocks   thread per (sample, pair of stance feet): 3x3 block of S = J_c J_c^T
 //   chol      lane per sample: Cholesky S = L L^T, dependent rows dropped (pinv semantics)
 //   wcols     thread per (sample, dof): column of W = L^-1 J_c by forward substitution
-//   proj      thread per (sample, entry): packed lower triangle of P = I - W^T W
-//   fill      thread per (sample, body, row) + per (sample, row) for the friction / torque columns -> tile rows
+//   proj      thread per (sample, row): packed lower triangle of P = I - W^T W
+//   fill      thread per (sample, body, row group) + per (sample, row group) for the friction / torque columns -> tile rows
 //
 // The contact Jacobian keeps pinocchio's exact semantics for an UN-normalised logged quaternion (float32 logs are
 // off unit norm by ~3e-8; assuming an orthonormal R_b moves P by ~2e-10, above the parity gate):
@@ -44,32 +44,84 @@ constexpr int CX_STRIDE = CX_TAU + MAXD + 1;        // 530
 constexpr int CXT_S = CX_P;                         // [78] packed S, then L
 constexpr int CXT_JL = CX_P + 78;                   // [MAXEE][MAXCH][3] leg columns of J_c
 static_assert(78 + 3 * MAXEE * MAXCH <= NPACK, "temporaries fit the P slot");
-static_assert(CX_STRIDE % 2 == 0, "context stride keeps 16-byte alignment");
+static_assert(CX_STRIDE % 2 == 0 && CX_A % 2 == 0, "context stride keeps 16-byte alignment");
 
 // ---- per-sample scratch (doubles), only live inside the F phases -------------------------------------------
 constexpr int SC_RB = 0;                            // [9] R_b from the raw quaternion
 constexpr int SC_RF = SC_RB + 9;                    // [MAXEE][3] R_b r_k of the stance feet
 constexpr int SC_META = SC_RF + 3 * MAXEE;          // 3m, then the foot index of every stance slot
-constexpr int SC_WM = SC_META + 1 + MAXEE;          // [3*MAXEE][MAXV] W = L^-1 J_c
-constexpr int SC_STRIDE = SC_WM + 3 * MAXEE * MAXV + 1;   // 243 (odd)
+constexpr int SC_WM = SC_META + 1 + MAXEE;          // [3*MAXEE][MAXV] W = L^-1 J_c (16-byte aligned rows)
+constexpr int SC_SC = SC_WM + 3 * MAXEE * MAXV;     // [MAXD][2] sin, cos of the revolute joints
+constexpr int SC_STRIDE = SC_SC + 2 * MAXD + 8;     // 274 == 2 (mod 16): lanes of consecutive samples hit distinct banks
+static_assert(SC_WM % 2 == 0 && SC_STRIDE % 16 == 2 && MAXV % 2 == 0, "W rows are read as double2, conflict-free across samples");
+
+// ---- staged inputs of a super-batch (doubles): channel-major, element (channel, sample) at inp[channel * SB + sample]
+constexpr int IN_Q = 0;                             // quaternion x, y, z, w, then the joint angles
+constexpr int IN_DQ = IN_Q + 4 + MAXD;
+constexpr int IN_DDQ = IN_DQ + MAXV;
+constexpr int IN_TAU = IN_DDQ + MAXV;
+constexpr int IN_CNT = IN_TAU + MAXD;
+constexpr int IN_WGT = IN_CNT + MAXEE;
+constexpr int IN_CHANNELS = IN_WGT + 1;             // 69
 
 __device__ __forceinline__ int pk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
+// ---------------------------------------------------------------------------------------------- stage
+// Coalesced copy of the super-batch's channel values into shared memory (one global-memory latency per super-batch
+// instead of one per joint of the serial chain walk).
+template <int SB, int NT>
+__device__ __forceinline__ void phase_stage(const DevModel& M, const SampleIO& io, long long base, long long N,
+                                            double* __restrict__ inp, int t) {
+    const int nd = M.nd, nv = M.nv, nee = M.n_ee;
+    const long long ld = io.ld;
+    for (int it = t; it < IN_CHANNELS * SB; it += NT) {
+        const int ch = it / SB, s = it - ch * SB;
+        const long long i = base + s;
+        double v = 0.0;
+        if (i < N) {
+            if (ch < IN_DQ) { if (ch < 4 + nd) v = io.q[(3 + ch) * ld + i]; }
+            else if (ch < IN_DDQ) { if (ch - IN_DQ < nv) v = io.dq[(ch - IN_DQ) * ld + i]; }
+            else if (ch < IN_TAU) { if (ch - IN_DDQ < nv) v = io.ddq[(ch - IN_DDQ) * ld + i]; }
+            else if (ch < IN_CNT) { if (ch - IN_TAU < nd && io.tau) v = io.tau[(ch - IN_TAU) * ld + i]; }
+            else if (ch < IN_WGT) { if (ch - IN_CNT < nee) v = io.cnt[(ch - IN_CNT) * ld + i]; }
+            else v = io.weights ? io.weights[i] : 1.0;
+        }
+        inp[it] = v;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- sincos
+// Thread per (sample, joint); also probes every staged value of the sample's column for NaN/Inf (thread of joint 0).
+template <int SB>
+__device__ __forceinline__ void phase_sincos(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
+                                             double* __restrict__ scr, int* s_bad, int t) {
+    if (t >= SB * MAXD) return;
+    const int s = t % SB, k = t / SB;
+    if (base + s >= N || k >= M.nd) return;
+    double sn, cs;
+    sincos(inp[(IN_Q + 4 + k) * SB + s], &sn, &cs);
+    scr[s * SC_STRIDE + SC_SC + 2 * k] = sn;
+    scr[s * SC_STRIDE + SC_SC + 2 * k + 1] = cs;
+    if (k == 0) {
+        double probe = 0.0;
+#pragma unroll 4
+        for (int ch = 0; ch < IN_CNT; ++ch) probe += inp[ch * SB + s];     // contacts and weights are not probed
+        if (!(fabs(probe) < 1e300)) atomicOr(&s_bad[s], 2);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- chains
 template <int SB>
-__device__ __forceinline__ void phase_chains(const DevModel& M, const SampleIO& io, long long base, long long N,
-                                             double* __restrict__ ctx, double* __restrict__ scr, int* s_bad, int t) {
+__device__ __forceinline__ void phase_chains(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
+                                             double* __restrict__ ctx, double* __restrict__ scr, int t) {
     if (t >= SB * M.nfch) return;
-    const int s = t % SB, ch = t / SB;          // sample fastest: coalesced channel loads
-    const long long i = base + s;
-    if (i >= N) return;
+    const int s = t % SB, ch = t / SB;          // sample fastest: conflict-free reads of the staged channels
+    if (base + s >= N) return;
     double* c = ctx + s * CX_STRIDE;
-    const long long ld = io.ld;
-    double probe = 0.0;
+    const double* in = inp + s;
     double Rb[9];
     {   // Eigen::Quaternion::toRotationMatrix on the raw (x, y, z, w): no normalisation, as pinocchio's free-flyer does
-        const double qx = io.q[3 * ld + i], qy = io.q[4 * ld + i], qz = io.q[5 * ld + i], qw = io.q[6 * ld + i];
-        probe += qx + qy + qz + qw;
+        const double qx = in[(IN_Q + 0) * SB], qy = in[(IN_Q + 1) * SB], qz = in[(IN_Q + 2) * SB], qw = in[(IN_Q + 3) * SB];
         const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
         const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
         Rb[0] = 1 - (tyy + tzz); Rb[1] = txy - twz; Rb[2] = txz + twy;
@@ -80,7 +132,7 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, const SampleIO& 
     {   // root (free-flyer): v = dq[0:6]; a = ddq[0:6] + [R_b^T (-g); 0]
         const double g0 = -M.gravity[0], g1 = -M.gravity[1], g2 = -M.gravity[2];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) { v[k] = io.dq[k * ld + i]; a[k] = io.ddq[k * ld + i]; probe += v[k] + a[k]; }
+        for (int k = 0; k < 6; ++k) { v[k] = in[(IN_DQ + k) * SB]; a[k] = in[(IN_DDQ + k) * SB]; }
 #pragma unroll
         for (int k = 0; k < 3; ++k) a[k] += Rb[k] * g0 + Rb[3 + k] * g1 + Rb[6 + k] * g2;
     }
@@ -99,10 +151,8 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, const SampleIO& 
     const int len = M.fch_len[ch], own = M.fch_own[ch];
     for (int e = 0; e < len; ++e) {
         const int j = M.fch[ch][e];
-        const double th = io.q[(5 + j) * ld + i], qd = io.dq[(4 + j) * ld + i], qdd = io.ddq[(4 + j) * ld + i];
-        probe += th + qd + qdd;
-        double sn, cs;
-        sincos(th, &sn, &cs);
+        const double qd = in[(IN_DQ + 4 + j) * SB], qdd = in[(IN_DDQ + 4 + j) * SB];
+        const double sn = scr[s * SC_STRIDE + SC_SC + 2 * (j - 2)], cs = scr[s * SC_STRIDE + SC_SC + 2 * (j - 2) + 1];
         double Rl[9];
         joint_rotation_compose(M, j, sn, cs, Rl);
         const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
@@ -169,26 +219,23 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, const SampleIO& 
             b9[8] = a[2] + (v[3] * v[1] - v[4] * v[0]);
         }
     }
-    if (!(fabs(probe) < 1e300)) atomicOr(&s_bad[s], 2);
 }
 
 // ---------------------------------------------------------------------------------------------- feet
 // Also copies dq / tau of the actuated joints into the context (threads of slot 0).
 template <int SB>
-__device__ __forceinline__ void phase_feet(const DevModel& M, const SampleIO& io, long long base, long long N,
-                                           double* __restrict__ ctx, double* __restrict__ scr, int* s_bad, int t) {
+__device__ __forceinline__ void phase_feet(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
+                                           double* __restrict__ ctx, double* __restrict__ scr, int t) {
     if (t >= SB * MAXEE) return;
     const int s = t % SB, slot = t / SB;
-    const long long i = base + s;
-    if (i >= N) return;
+    if (base + s >= N) return;
     double* c = ctx + s * CX_STRIDE;
     double* sc = scr + s * SC_STRIDE;
-    const long long ld = io.ld;
     int m = 0, kf = -1;
 #pragma unroll
     for (int k = 0; k < MAXEE; ++k) {
         if (k < M.n_ee) {
-            const double cv = io.cnt[k * ld + i];
+            const double cv = inp[(IN_CNT + k) * SB + s];
             if (cv != 0.0) {   // truthiness rule of the reference: state 2 counts as stance; NaN is truthy too
                 if (m == slot) kf = k;
                 ++m;
@@ -197,14 +244,10 @@ __device__ __forceinline__ void phase_feet(const DevModel& M, const SampleIO& io
     }
     if (slot == 0) {
         sc[SC_META] = (double)(3 * m);
-        double probe = 0.0;
         for (int k = 0; k < M.nd; ++k) {
-            const double tk = io.tau ? io.tau[k * ld + i] : 0.0;
-            probe += tk;
-            c[CX_DQ + k] = io.dq[(6 + k) * ld + i];
-            c[CX_TAU + k] = tk;
+            c[CX_DQ + k] = inp[(IN_DQ + 6 + k) * SB + s];
+            c[CX_TAU + k] = inp[(IN_TAU + k) * SB + s];
         }
-        if (!(fabs(probe) < 1e300)) atomicOr(&s_bad[s], 2);
     }
     sc[SC_META + 1 + slot] = (double)kf;
     if (kf < 0) return;
@@ -300,6 +343,8 @@ __device__ __forceinline__ void phase_sblocks(const DevModel& M, long long base,
 }
 
 // ---------------------------------------------------------------------------------------------- Cholesky
+// Lane per sample, textbook left-looking loop.  (A 16-lanes-per-sample shuffle version and a statically unrolled
+// right-looking version were measured slower on B200: the fp64 sqrt / divide sequences dominate, see profiles/.)
 template <int SB>
 __device__ __forceinline__ void phase_chol(long long base, long long N, double* __restrict__ ctx,
                                            const double* __restrict__ scr, int* s_bad, int t) {
@@ -372,119 +417,269 @@ __device__ __forceinline__ void phase_wcols(const DevModel& M, long long base, l
 }
 
 // ---------------------------------------------------------------------------------------------- P = I - W^T W
-// NT = threads in the group; also finalises the per-sample weight and the skip flags (first SB threads).
+// Thread per (sample, row r): entries (r, 0..r) of the packed lower triangle, one independent accumulator per entry.
+// NT = threads in the group; also finalises the per-sample weight and the skip flags (first warp of the group).
 template <int SB, int NT>
-__device__ __forceinline__ void phase_proj(const SampleIO& io, long long base, long long N, double* __restrict__ ctx,
-                                           const double* __restrict__ scr, const int* s_bad, int t,
-                                           double& wsum, int& nflag0, int& nflag1) {
-    for (int it = t; it < SB * NPACK; it += NT) {
-        const int s = it % SB, e = it / SB;
+__device__ __forceinline__ void phase_proj(long long base, long long N, const double* __restrict__ inp, double* __restrict__ ctx,
+                                           const double* __restrict__ scr, const int* s_bad, int t, double* s_stat) {
+    for (int it = t; it < SB * MAXV; it += NT) {
+        const int s = it % SB, r = MAXV - 1 - it / SB;      // long rows first
         if (base + s >= N) continue;
-        int r = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-        while (r * (r + 1) / 2 > e) --r;
-        while ((r + 1) * (r + 2) / 2 <= e) ++r;
-        const int cc = e - r * (r + 1) / 2;
         const double* sc = scr + s * SC_STRIDE;
         const int m3 = (int)sc[SC_META];
-        double pv = (r == cc) ? 1.0 : 0.0;
-        for (int k = 0; k < m3; ++k) pv = fma(-sc[SC_WM + k * MAXV + r], sc[SC_WM + k * MAXV + cc], pv);
-        ctx[s * CX_STRIDE + CX_P + e] = pv;
+        double pv[MAXV];
+#pragma unroll
+        for (int cc = 0; cc < MAXV; ++cc) pv[cc] = (cc == r) ? 1.0 : 0.0;
+        for (int k = 0; k < m3; ++k) {
+            const double2* wrow = reinterpret_cast<const double2*>(sc + SC_WM + k * MAXV);
+            const double wk = -sc[SC_WM + k * MAXV + r];
+#pragma unroll
+            for (int c2 = 0; c2 < MAXV / 2; ++c2) {
+                const double2 w2 = wrow[c2];
+                pv[2 * c2] = fma(wk, w2.x, pv[2 * c2]);
+                pv[2 * c2 + 1] = fma(wk, w2.y, pv[2 * c2 + 1]);
+            }
+        }
+        double* Pr = ctx + s * CX_STRIDE + CX_P + r * (r + 1) / 2;
+#pragma unroll
+        for (int cc = 0; cc < MAXV; ++cc) if (cc <= r) Pr[cc] = pv[cc];
     }
-    if (t < SB) {
+    static_assert(SB <= 32, "the first warp of the group finalises the weights");
+    if (t < 32) {       // warp 0 of the group: deterministic (shuffle-tree) sums of the weights and the flag counts
         const long long i = base + t;
         double w = 0.0;
-        if (i < N) {
+        int f0 = 0, f1 = 0;
+        if (t < SB && i < N) {
             const int bad = s_bad[t];
-            w = io.weights ? io.weights[i] : 1.0;
-            if (!(fabs(w) < 1e300) || (bad & 2)) { w = 0.0; ++nflag1; }
-            if (bad & 1) ++nflag0;
+            w = inp[IN_WGT * SB + t];
+            if (!(fabs(w) < 1e300) || (bad & 2)) { w = 0.0; f1 = 1; }
+            f0 = bad & 1;
             w = fmax(w, 0.0);
         }
-        ctx[t * CX_STRIDE + CX_W] = sqrt(w);
-        wsum += w;
+        if (t < SB) ctx[t * CX_STRIDE + CX_W] = sqrt(w);
+        const unsigned b0 = __ballot_sync(0xffffffffu, f0), b1 = __ballot_sync(0xffffffffu, f1);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (t == 0) { s_stat[0] += w; s_stat[1] += (double)__popc(b0); s_stat[2] += (double)__popc(b1); }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- tile fill
-// One item = one (sample, body, row) -> ten entries of the projected row block, or one (sample, row) -> the friction
-// and torque columns plus the zero padding.  TS samples starting at local sample s0 -> rows [0, TS*MAXV) of `tile`.
-template <int TS, int LD, int NT>
+// Ten entries of one projected row of body i from its body-frame coefficients (el; ea) = bodyRegressor^T (el; ea).
+__device__ __forceinline__ void body_row(const double* __restrict__ b9, double el0, double el1, double el2,
+                                         double ea0, double ea1, double ea2, double* __restrict__ dst) {
+    const double w0 = b9[0], w1 = b9[1], w2 = b9[2], al0 = b9[3], al1 = b9[4], al2 = b9[5], ac0 = b9[6], ac1 = b9[7], ac2 = b9[8];
+    double o[10];
+    // mass column: el . acc
+    o[0] = el0 * ac0 + el1 * ac1 + el2 * ac2;
+    // first-moment columns: -alpha x el + omega x (omega x el) + acc x ea
+    const double u0 = w1 * el2 - w2 * el1, u1 = w2 * el0 - w0 * el2, u2 = w0 * el1 - w1 * el0;
+    o[1] = (w1 * u2 - w2 * u1) - (al1 * el2 - al2 * el1) + (ac1 * ea2 - ac2 * ea1);
+    o[2] = (w2 * u0 - w0 * u2) - (al2 * el0 - al0 * el2) + (ac2 * ea0 - ac0 * ea2);
+    o[3] = (w0 * u1 - w1 * u0) - (al0 * el1 - al1 * el0) + (ac0 * ea1 - ac1 * ea0);
+    // inertia columns (Ixx, Ixy, Iyy, Ixz, Iyz, Izz): ea . Br(alpha)[:,k] + (ea x omega) . Br(omega)[:,k]
+    const double g0 = ea1 * w2 - ea2 * w1, g1 = ea2 * w0 - ea0 * w2, g2 = ea0 * w1 - ea1 * w0;
+    o[4] = ea0 * al0 + g0 * w0;
+    o[5] = ea0 * al1 + ea1 * al0 + g0 * w1 + g1 * w0;
+    o[6] = ea1 * al1 + g1 * w1;
+    o[7] = ea0 * al2 + ea2 * al0 + g0 * w2 + g2 * w0;
+    o[8] = ea1 * al2 + ea2 * al1 + g1 * w2 + g2 * w1;
+    o[9] = ea2 * al2 + g2 * w2;
+    double2* d2 = reinterpret_cast<double2*>(dst);      // 10 * body and the row pitch are even: 16-byte aligned
+#pragma unroll
+    for (int k = 0; k < 5; ++k) d2[k] = make_double2(o[2 * k], o[2 * k + 1]);
+}
+
+// One item = one (sample, body, group of RPI consecutive rows) -> RPI x 10 entries of the projected row block (the rows
+// of a group share the Pluecker axes, pose and body motion loads and give the thread RPI independent dependency
+// chains), or one (sample, row group) -> the friction and torque columns plus the zero padding.
+// TS samples starting at local sample s0 -> rows [0, TS*MAXV) of `tile`.
+template <int TS, int LD, int NT, int RPI>
 __device__ __forceinline__ void phase_fill(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
                                            int s0, int friction, int t) {
+    constexpr int NRG = MAXV / RPI;
+    static_assert(MAXV % RPI == 0, "row groups");
     const int nb = M.nb, np = M.nparams, nd = M.nd;
-    const int per_sample = MAXV * (nb + 1);
+    const int per_sample = NRG * (nb + 1);
     for (int it = t; it < TS * per_sample; it += NT) {
         const int sl = it / per_sample, rem = it - sl * per_sample;
-        const int ib = rem / MAXV, r = rem - ib * MAXV;      // ib in [0, nb]: body ib+1, or nb = friction/torque item
+        const int ib = rem / NRG, r0 = RPI * (rem - ib * NRG);   // ib in [0, nb]: body ib+1, or nb = friction/torque item
         const double* c = ctx + (s0 + sl) * CX_STRIDE;
         const double* P = c + CX_P;
         const double wsq = c[CX_W];
-        double* row = tile + (sl * MAXV + r) * LD;
+        double* row = tile + (sl * MAXV + r0) * LD;
+        // entry (r, cc) of the symmetric P from its packed lower triangle
+        auto Pe = [&](int r, int cc) { return (cc <= r) ? P[r * (r + 1) / 2 + cc] : P[cc * (cc + 1) / 2 + r]; };
         if (ib < nb) {
             double* dst = row + 10 * ib;
             if (wsq == 0.0) {
 #pragma unroll
-                for (int k = 0; k < 10; ++k) dst[k] = 0.0;
+                for (int g = 0; g < RPI; ++g)
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) reinterpret_cast<double2*>(dst + g * LD)[k] = make_double2(0.0, 0.0);
                 continue;
             }
             const int i = ib + 1;
-            double dl0 = P[pk(r, 0)], dl1 = P[pk(r, 1)], dl2 = P[pk(r, 2)], da0 = P[pk(r, 3)], da1 = P[pk(r, 4)], da2 = P[pk(r, 5)];
+            double d[RPI][6];          // (dl; da) of each row
+#pragma unroll
+            for (int g = 0; g < RPI; ++g)
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d[g][k] = Pe(r0 + g, k);
             for (int j = i; j > 1; j = M.parent[j]) {
-                const double pj = P[pk(r, 4 + j)];
-                const double* A = c + CX_A + 6 * (j - 2);
-                dl0 = fma(pj, A[0], dl0); dl1 = fma(pj, A[1], dl1); dl2 = fma(pj, A[2], dl2);
-                da0 = fma(pj, A[3], da0); da1 = fma(pj, A[4], da1); da2 = fma(pj, A[5], da2);
+                const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
+                double pj[RPI];
+#pragma unroll
+                for (int g = 0; g < RPI; ++g) pj[g] = Pe(r0 + g, 4 + j);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double2 ak = A2[k];
+#pragma unroll
+                    for (int g = 0; g < RPI; ++g) { d[g][2 * k] = fma(pj[g], ak.x, d[g][2 * k]); d[g][2 * k + 1] = fma(pj[g], ak.y, d[g][2 * k + 1]); }
+                }
             }
-            double el0, el1, el2, ea0, ea1, ea2;
+            double e[RPI][6];          // (el; ea) of each row
             if (i > 1) {
                 const double* X = c + CX_X + 12 * (i - 2);
                 const double p0 = X[9], p1 = X[10], p2 = X[11];
-                const double t0 = dl0 + (da1 * p2 - da2 * p1), t1 = dl1 + (da2 * p0 - da0 * p2), t2 = dl2 + (da0 * p1 - da1 * p0);
-                el0 = X[0] * t0 + X[3] * t1 + X[6] * t2; el1 = X[1] * t0 + X[4] * t1 + X[7] * t2; el2 = X[2] * t0 + X[5] * t1 + X[8] * t2;
-                ea0 = X[0] * da0 + X[3] * da1 + X[6] * da2; ea1 = X[1] * da0 + X[4] * da1 + X[7] * da2; ea2 = X[2] * da0 + X[5] * da1 + X[8] * da2;
+                double u[RPI][3];
+#pragma unroll
+                for (int g = 0; g < RPI; ++g) {
+                    u[g][0] = d[g][0] + (d[g][4] * p2 - d[g][5] * p1);
+                    u[g][1] = d[g][1] + (d[g][5] * p0 - d[g][3] * p2);
+                    u[g][2] = d[g][2] + (d[g][3] * p1 - d[g][4] * p0);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double x0 = X[k], x1 = X[3 + k], x2 = X[6 + k];
+#pragma unroll
+                    for (int g = 0; g < RPI; ++g) {
+                        e[g][k] = x0 * u[g][0] + x1 * u[g][1] + x2 * u[g][2];
+                        e[g][3 + k] = x0 * d[g][3] + x1 * d[g][4] + x2 * d[g][5];
+                    }
+                }
             } else {
-                el0 = dl0; el1 = dl1; el2 = dl2; ea0 = da0; ea1 = da1; ea2 = da2;
+#pragma unroll
+                for (int g = 0; g < RPI; ++g)
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) e[g][k] = d[g][k];
             }
-            el0 *= wsq; el1 *= wsq; el2 *= wsq; ea0 *= wsq; ea1 *= wsq; ea2 *= wsq;
             const double* b9 = c + CX_B9 + 9 * ib;
-            const double w0 = b9[0], w1 = b9[1], w2 = b9[2], al0 = b9[3], al1 = b9[4], al2 = b9[5], ac0 = b9[6], ac1 = b9[7], ac2 = b9[8];
-            // mass column: el . acc
-            dst[0] = el0 * ac0 + el1 * ac1 + el2 * ac2;
-            // first-moment columns: -alpha x el + omega x (omega x el) + acc x ea
-            const double u0 = w1 * el2 - w2 * el1, u1 = w2 * el0 - w0 * el2, u2 = w0 * el1 - w1 * el0;
-            dst[1] = (w1 * u2 - w2 * u1) - (al1 * el2 - al2 * el1) + (ac1 * ea2 - ac2 * ea1);
-            dst[2] = (w2 * u0 - w0 * u2) - (al2 * el0 - al0 * el2) + (ac2 * ea0 - ac0 * ea2);
-            dst[3] = (w0 * u1 - w1 * u0) - (al0 * el1 - al1 * el0) + (ac0 * ea1 - ac1 * ea0);
-            // inertia columns (Ixx, Ixy, Iyy, Ixz, Iyz, Izz): ea . Br(alpha)[:,k] + (ea x omega) . Br(omega)[:,k]
-            const double g0 = ea1 * w2 - ea2 * w1, g1 = ea2 * w0 - ea0 * w2, g2 = ea0 * w1 - ea1 * w0;
-            dst[4] = ea0 * al0 + g0 * w0;
-            dst[5] = ea0 * al1 + ea1 * al0 + g0 * w1 + g1 * w0;
-            dst[6] = ea1 * al1 + g1 * w1;
-            dst[7] = ea0 * al2 + ea2 * al0 + g0 * w2 + g2 * w0;
-            dst[8] = ea1 * al2 + ea2 * al1 + g1 * w2 + g2 * w1;
-            dst[9] = ea2 * al2 + g2 * w2;
+#pragma unroll
+            for (int g = 0; g < RPI; ++g)
+                body_row(b9, e[g][0] * wsq, e[g][1] * wsq, e[g][2] * wsq, e[g][3] * wsq, e[g][4] * wsq, e[g][5] * wsq, dst + g * LD);
         } else {
-            double tau = 0.0;
-            double* dv = row + np;
-            if (friction) {
+            double tau[RPI];
+#pragma unroll
+            for (int g = 0; g < RPI; ++g) tau[g] = 0.0;
+            const int ntail = friction ? 2 * nd + 1 : 1;
+            if (wsq != 0.0) {
                 for (int jj = 0; jj < nd; ++jj) {
-                    const double pj = (wsq == 0.0) ? 0.0 : P[pk(r, 6 + jj)] * wsq;
-                    const double dqv = (wsq == 0.0) ? 0.0 : c[CX_DQ + jj];
+                    const double tq = c[CX_TAU + jj];
+                    const double dqv = c[CX_DQ + jj];
                     const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
-                    dv[jj] = pj * dqv;
-                    dv[nd + jj] = pj * sg;
-                    tau = fma(pj, (wsq == 0.0) ? 0.0 : c[CX_TAU + jj], tau);
+#pragma unroll
+                    for (int g = 0; g < RPI; ++g) {
+                        const double pj = Pe(r0 + g, 6 + jj) * wsq;
+                        tau[g] = fma(pj, tq, tau[g]);
+                        if (friction) { row[g * LD + np + jj] = pj * dqv; row[g * LD + np + nd + jj] = pj * sg; }
+                    }
                 }
-                dv[2 * nd] = tau;
-                for (int k = np + 2 * nd + 1; k < CW; ++k) row[k] = 0.0;
-            } else {      // without friction columns the torque column follows the body columns directly
-                for (int jj = 0; jj < nd; ++jj) {
-                    const double pj = (wsq == 0.0) ? 0.0 : P[pk(r, 6 + jj)] * wsq;
-                    tau = fma(pj, (wsq == 0.0) ? 0.0 : c[CX_TAU + jj], tau);
-                }
-                dv[0] = tau;
-                for (int k = np + 1; k < CW; ++k) row[k] = 0.0;
+            } else if (friction) {
+                for (int jj = 0; jj < 2 * nd; ++jj)
+#pragma unroll
+                    for (int g = 0; g < RPI; ++g) row[g * LD + np + jj] = 0.0;
             }
+            // without friction columns the torque column follows the body columns directly
+#pragma unroll
+            for (int g = 0; g < RPI; ++g) {
+                row[g * LD + np + ntail - 1] = tau[g];
+                for (int k = np + ntail; k < CW; ++k) row[g * LD + k] = 0.0;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- tile fill, chain walk
+// Lanes are grouped by (leaf chain, split index): a lane owns one (sample, row) of its group, walks the chain from the
+// root accumulating (dl; da) incrementally (6 FMAs per joint instead of re-summing the ancestors per body), and emits
+// the ten entries of every body e of the chain with e % split == its split index.  One more group emits the root body
+// and the friction / torque / padding columns.  Groups are padded to whole warps so that a warp never diverges.
+template <int TS, int LD, int NT>
+__device__ __forceinline__ void phase_fill_chains(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
+                                                  int s0, int friction, int t) {
+    constexpr int GL = ((TS * MAXV + 31) / 32) * 32;     // lanes per group
+    static_assert(NT % 32 == 0 && GL <= NT, "groups are whole warps");
+    const int split = M.fill_split, ngroups = M.nfch * split;
+    const int np = M.nparams, nd = M.nd;
+    const int l = t % GL;
+    if (l >= TS * MAXV) return;
+    const int sl = l / MAXV, r = l - sl * MAXV;
+    const double* c = ctx + (s0 + sl) * CX_STRIDE;
+    const double* P = c + CX_P;
+    const double wsq = c[CX_W];
+    double* row = tile + (sl * MAXV + r) * LD;
+    auto Pe = [&](int cc) { return (cc <= r) ? P[r * (r + 1) / 2 + cc] : P[cc * (cc + 1) / 2 + r]; };
+    for (int g = t / GL; g <= ngroups; g += NT / GL) {
+        if (g < ngroups) {
+            const int ch = g / split, q = g - ch * split;
+            const int len = M.fch_len[ch], own = M.fch_own[ch];
+            if (wsq == 0.0) {
+                for (int e = own; e < len; ++e)
+                    if (e % split == q) {
+                        double2* d2 = reinterpret_cast<double2*>(row + 10 * (M.fch[ch][e] - 1));
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) d2[k] = make_double2(0.0, 0.0);
+                    }
+                continue;
+            }
+            double d[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) d[k] = Pe(k);
+            for (int e = 0; e < len; ++e) {
+                const int j = M.fch[ch][e];
+                const double pj = Pe(4 + j);
+                const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const double2 ak = A2[k]; d[2 * k] = fma(pj, ak.x, d[2 * k]); d[2 * k + 1] = fma(pj, ak.y, d[2 * k + 1]); }
+                if (e >= own && e % split == q) {
+                    const double2* X2 = reinterpret_cast<const double2*>(c + CX_X + 12 * (j - 2));
+                    const double2 x01 = X2[0], x23 = X2[1], x45 = X2[2], x67 = X2[3], x8p = X2[4], p12 = X2[5];
+                    const double p0 = x8p.y, p1 = p12.x, p2 = p12.y;
+                    const double u0 = d[0] + (d[4] * p2 - d[5] * p1), u1 = d[1] + (d[5] * p0 - d[3] * p2), u2 = d[2] + (d[3] * p1 - d[4] * p0);
+                    // (el; ea) = (R^T u; R^T da), R row-major in x01..x8p
+                    const double el0 = x01.x * u0 + x23.y * u1 + x67.x * u2, el1 = x01.y * u0 + x45.x * u1 + x67.y * u2, el2 = x23.x * u0 + x45.y * u1 + x8p.x * u2;
+                    const double ea0 = x01.x * d[3] + x23.y * d[4] + x67.x * d[5], ea1 = x01.y * d[3] + x45.x * d[4] + x67.y * d[5], ea2 = x23.x * d[3] + x45.y * d[4] + x8p.x * d[5];
+                    body_row(c + CX_B9 + 9 * (j - 1), el0 * wsq, el1 * wsq, el2 * wsq, ea0 * wsq, ea1 * wsq, ea2 * wsq, row + 10 * (j - 1));
+                }
+            }
+        } else {
+            // root body (its Pluecker rows are the identity, pose = identity) ...
+            if (wsq == 0.0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) reinterpret_cast<double2*>(row)[k] = make_double2(0.0, 0.0);
+            } else {
+                body_row(c + CX_B9, Pe(0) * wsq, Pe(1) * wsq, Pe(2) * wsq, Pe(3) * wsq, Pe(4) * wsq, Pe(5) * wsq, row);
+            }
+            // ... and the friction / torque columns plus the zero padding
+            double tau = 0.0;
+            const int ntail = friction ? 2 * nd + 1 : 1;
+            if (wsq != 0.0) {
+                for (int jj = 0; jj < nd; ++jj) {
+                    const double pj = Pe(6 + jj) * wsq;
+                    tau = fma(pj, c[CX_TAU + jj], tau);
+                    if (friction) {
+                        const double dqv = c[CX_DQ + jj];
+                        const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
+                        row[np + jj] = pj * dqv;
+                        row[np + nd + jj] = pj * sg;
+                    }
+                }
+            } else if (friction) {
+                for (int jj = 0; jj < 2 * nd; ++jj) row[np + jj] = 0.0;
+            }
+            // without friction columns the torque column follows the body columns directly
+            row[np + ntail - 1] = tau;
+            for (int k = np + ntail; k < CW; ++k) row[k] = 0.0;
         }
     }
 }

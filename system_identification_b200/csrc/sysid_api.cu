@@ -155,6 +155,8 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
             for (int k = own; k < len; ++k) owned[M.fch[c][k]] = true;
         }
     }
+    // tile fill: (chains x split + 1) lane groups of 96 lanes; use up to two groups per chain while all fit one pass
+    M.fill_split = ((M.nfch * 2 + 1) * 96 <= GRAM_THREADS) ? 2 : 1;
     int rc = device_sm_count(&m->sm_count);
     if (rc != SYSID_OK) { delete m; return rc; }
     *out = m;
@@ -297,7 +299,7 @@ int sysid_predict_rmse(const sysid_model* model, const double* q, const double* 
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N <= 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
     cudaStream_t st = (cudaStream_t)stream;
-    const long long nsb = (N + FSB - 1) / FSB;
+    const long long nsb = (N + RSB - 1) / RSB;
     const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
     if (workspace_bytes < sizeof(double) * (size_t)grid * RMSE_PARTIAL) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
     int rc = opt_in_smem(rmse_kernel, RMSE_SMEM_BYTES);
