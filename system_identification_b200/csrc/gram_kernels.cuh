@@ -111,10 +111,10 @@ constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
 #define SYSID_F_PHASES(SB, NT, SYNC)                                                                                     \
     phase_stage<SB, NT>(M, args.io, base, args.N, inp, t);                                                               \
     SYNC();                                                                                                              \
-    for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, scr, s_bad, it);                   \
+    for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, ctx, scr, s_bad, it);              \
     SYNC();                                                                                                              \
     F_TICK(0)                                                                                                            \
-    for (int it = t; it < SB * M.nfch; it += NT) phase_chains<SB>(M, base, args.N, inp, ctx, scr, it);                   \
+    for (int it = t; it < 2 * ((SB * M.nfch + 31) & ~31); it += NT) phase_chains<SB>(M, base, args.N, inp, ctx, scr, it); \
     SYNC();                                                                                                              \
     F_TICK(1)                                                                                                            \
     for (int it = t; it < SB * MAXEE; it += NT) phase_feet<SB>(M, base, args.N, inp, ctx, scr, it);                      \
@@ -180,6 +180,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #endif
         if (t < FSB) s_bad[t] = 0;
         PHASE_TICK(clkF)
+        prefetch_inputs<FSB, GRAM_THREADS>(M, args.io, (sb + gridDim.x) * FSB, args.N, t);     // lands in L2 during the rounds below
         const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
         for (int sub = 0; sub < nsub; ++sub) {
 #ifdef SYSID_ONLY_M

@@ -66,38 +66,58 @@ constexpr int IN_CHANNELS = IN_WGT + 1;             // 69
 
 __device__ __forceinline__ int pk(int r, int c) { return r >= c ? r * (r + 1) / 2 + c : c * (c + 1) / 2 + r; }
 
+// Global address of element (staged channel ch, sample i), or nullptr for a channel this model / call does not have.
+__device__ __forceinline__ const double* channel_ptr(const DevModel& M, const SampleIO& io, int ch, long long i) {
+    const long long ld = io.ld;
+    if (ch < IN_DQ) return (ch < 4 + M.nd) ? io.q + (3 + ch) * ld + i : nullptr;
+    if (ch < IN_DDQ) return (ch - IN_DQ < M.nv) ? io.dq + (ch - IN_DQ) * ld + i : nullptr;
+    if (ch < IN_TAU) return (ch - IN_DDQ < M.nv) ? io.ddq + (ch - IN_DDQ) * ld + i : nullptr;
+    if (ch < IN_CNT) return (ch - IN_TAU < M.nd && io.tau) ? io.tau + (ch - IN_TAU) * ld + i : nullptr;
+    if (ch < IN_WGT) return (ch - IN_CNT < M.n_ee) ? io.cnt + (ch - IN_CNT) * ld + i : nullptr;
+    return io.weights ? io.weights + i : nullptr;
+}
+
+// L2 prefetch of the channel segments of a later super-batch (each segment is SB * 8 bytes: at most 3 lines of 128 B).
+template <int SB, int NT>
+__device__ __forceinline__ void prefetch_inputs(const DevModel& M, const SampleIO& io, long long base, long long N, int t) {
+    constexpr int LINES = (SB * 8 + 127) / 128 + 1;
+    for (int it = t; it < IN_CHANNELS * LINES; it += NT) {
+        const int ch = it / LINES, ln = it - ch * LINES;
+        const long long i = base + ln * 16;
+        if (i >= N || ln * 16 >= SB + 15) continue;
+        const double* p = channel_ptr(M, io, ch, i);
+        if (p) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- stage
 // Coalesced copy of the super-batch's channel values into shared memory (one global-memory latency per super-batch
 // instead of one per joint of the serial chain walk).
 template <int SB, int NT>
 __device__ __forceinline__ void phase_stage(const DevModel& M, const SampleIO& io, long long base, long long N,
                                             double* __restrict__ inp, int t) {
-    const int nd = M.nd, nv = M.nv, nee = M.n_ee;
-    const long long ld = io.ld;
     for (int it = t; it < IN_CHANNELS * SB; it += NT) {
         const int ch = it / SB, s = it - ch * SB;
         const long long i = base + s;
-        double v = 0.0;
+        double v = (ch == IN_WGT) ? 1.0 : 0.0;
         if (i < N) {
-            if (ch < IN_DQ) { if (ch < 4 + nd) v = io.q[(3 + ch) * ld + i]; }
-            else if (ch < IN_DDQ) { if (ch - IN_DQ < nv) v = io.dq[(ch - IN_DQ) * ld + i]; }
-            else if (ch < IN_TAU) { if (ch - IN_DDQ < nv) v = io.ddq[(ch - IN_DDQ) * ld + i]; }
-            else if (ch < IN_CNT) { if (ch - IN_TAU < nd && io.tau) v = io.tau[(ch - IN_TAU) * ld + i]; }
-            else if (ch < IN_WGT) { if (ch - IN_CNT < nee) v = io.cnt[(ch - IN_CNT) * ld + i]; }
-            else v = io.weights ? io.weights[i] : 1.0;
+            const double* p = channel_ptr(M, io, ch, i);
+            if (p) v = *p;
         }
         inp[it] = v;
     }
 }
 
 // ---------------------------------------------------------------------------------------------- sincos
-// Thread per (sample, joint); also probes every staged value of the sample's column for NaN/Inf (thread of joint 0).
+// Thread per (sample, joint); copies the joint's dq / tau into the context; also probes every staged value of the sample's column for NaN/Inf (thread of joint 0).
 template <int SB>
 __device__ __forceinline__ void phase_sincos(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
-                                             double* __restrict__ scr, int* s_bad, int t) {
+                                             double* __restrict__ ctx, double* __restrict__ scr, int* s_bad, int t) {
     if (t >= SB * MAXD) return;
     const int s = t % SB, k = t / SB;
     if (base + s >= N || k >= M.nd) return;
+    ctx[s * CX_STRIDE + CX_DQ + k] = inp[(IN_DQ + 6 + k) * SB + s];
+    ctx[s * CX_STRIDE + CX_TAU + k] = inp[(IN_TAU + k) * SB + s];
     double sn, cs;
     sincos(inp[(IN_Q + 4 + k) * SB + s], &sn, &cs);
     scr[s * SC_STRIDE + SC_SC + 2 * k] = sn;
@@ -111,106 +131,122 @@ __device__ __forceinline__ void phase_sincos(const DevModel& M, long long base, 
 }
 
 // ---------------------------------------------------------------------------------------------- chains
+// Two lanes per (sample, leaf chain), so that each keeps a small register state next to the Gram accumulators:
+//   role 0 (pose)    R_j, p_j relative to the base down the chain -> X_j and the Pluecker axis a_j = (p_j x z_j; z_j)
+//   role 1 (motion)  spatial velocity / gravity-biased acceleration in local frames -> b9_j = (omega, alpha, acc)
 template <int SB>
 __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
                                              double* __restrict__ ctx, double* __restrict__ scr, int t) {
-    if (t >= SB * M.nfch) return;
-    const int s = t % SB, ch = t / SB;          // sample fastest: conflict-free reads of the staged channels
+    const int nlanes = SB * M.nfch, nl32 = (nlanes + 31) & ~31;      // roles start on warp boundaries: no divergence
+    const int role = t / nl32, u = t - role * nl32;
+    if (role > 1 || u >= nlanes) return;
+    const int s = u % SB, ch = u / SB;          // sample fastest: conflict-free reads of the staged channels
     if (base + s >= N) return;
     double* c = ctx + s * CX_STRIDE;
     const double* in = inp + s;
-    double Rb[9];
-    {   // Eigen::Quaternion::toRotationMatrix on the raw (x, y, z, w): no normalisation, as pinocchio's free-flyer does
-        const double qx = in[(IN_Q + 0) * SB], qy = in[(IN_Q + 1) * SB], qz = in[(IN_Q + 2) * SB], qw = in[(IN_Q + 3) * SB];
-        const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
-        const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
-        Rb[0] = 1 - (tyy + tzz); Rb[1] = txy - twz; Rb[2] = txz + twy;
-        Rb[3] = txy + twz; Rb[4] = 1 - (txx + tzz); Rb[5] = tyz - twx;
-        Rb[6] = txz - twy; Rb[7] = tyz + twx; Rb[8] = 1 - (txx + tyy);
+    const double* scs = scr + s * SC_STRIDE + SC_SC;
+    const int len = M.fch_len[ch], own = M.fch_own[ch];
+    if (role == 0) {
+        double R[9], p[3];
+        for (int e = 0; e < len; ++e) {
+            const int j = M.fch[ch][e];
+            double Rl[9];
+            joint_rotation_compose(M, j, scs[2 * (j - 2)], scs[2 * (j - 2) + 1], Rl);
+            const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
+            if (e == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = Rl[k];
+                p[0] = px; p[1] = py; p[2] = pz;
+            } else {
+                double Rn[9];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) Rn[3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) p[r] += R[3 * r] * px + R[3 * r + 1] * py + R[3 * r + 2] * pz;
+#pragma unroll
+                for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+            }
+            if (e >= own) {
+                double* X = c + CX_X + 12 * (j - 2);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) X[k] = R[k];
+                X[9] = p[0]; X[10] = p[1]; X[11] = p[2];
+                double z0, z1, z2;
+                const int jt = M.jtype[j];
+                if (jt == JT_RU) {
+                    const double u0 = M.axis[j][0], u1 = M.axis[j][1], u2 = M.axis[j][2];
+                    z0 = R[0] * u0 + R[1] * u1 + R[2] * u2; z1 = R[3] * u0 + R[4] * u1 + R[5] * u2; z2 = R[6] * u0 + R[7] * u1 + R[8] * u2;
+                } else if (jt == JT_RX) { z0 = R[0]; z1 = R[3]; z2 = R[6]; }
+                else if (jt == JT_RY) { z0 = R[1]; z1 = R[4]; z2 = R[7]; }
+                else { z0 = R[2]; z1 = R[5]; z2 = R[8]; }
+                double* A = c + CX_A + 6 * (j - 2);
+                A[0] = p[1] * z2 - p[2] * z1; A[1] = p[2] * z0 - p[0] * z2; A[2] = p[0] * z1 - p[1] * z0;
+                A[3] = z0; A[4] = z1; A[5] = z2;
+            }
+        }
+        return;
     }
     double v[6], a[6];
-    {   // root (free-flyer): v = dq[0:6]; a = ddq[0:6] + [R_b^T (-g); 0]
+    {
+        double Rb[9];
+        {   // Eigen::Quaternion::toRotationMatrix on the raw (x, y, z, w): no normalisation, as pinocchio's free-flyer does
+            const double qx = in[(IN_Q + 0) * SB], qy = in[(IN_Q + 1) * SB], qz = in[(IN_Q + 2) * SB], qw = in[(IN_Q + 3) * SB];
+            const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+            const double twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx, tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+            Rb[0] = 1 - (tyy + tzz); Rb[1] = txy - twz; Rb[2] = txz + twy;
+            Rb[3] = txy + twz; Rb[4] = 1 - (txx + tzz); Rb[5] = tyz - twx;
+            Rb[6] = txz - twy; Rb[7] = tyz + twx; Rb[8] = 1 - (txx + tyy);
+        }
+        // root (free-flyer): v = dq[0:6]; a = ddq[0:6] + [R_b^T (-g); 0]
         const double g0 = -M.gravity[0], g1 = -M.gravity[1], g2 = -M.gravity[2];
 #pragma unroll
         for (int k = 0; k < 6; ++k) { v[k] = in[(IN_DQ + k) * SB]; a[k] = in[(IN_DDQ + k) * SB]; }
 #pragma unroll
         for (int k = 0; k < 3; ++k) a[k] += Rb[k] * g0 + Rb[3 + k] * g1 + Rb[6 + k] * g2;
-    }
-    if (ch == 0) {
-        double* sc = scr + s * SC_STRIDE;
+        if (ch == 0) {
+            double* sc = scr + s * SC_STRIDE;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) sc[SC_RB + k] = Rb[k];
-        double* b9 = c + CX_B9;
-        b9[0] = v[3]; b9[1] = v[4]; b9[2] = v[5];
-        b9[3] = a[3]; b9[4] = a[4]; b9[5] = a[5];
-        b9[6] = a[0] + (v[4] * v[2] - v[5] * v[1]);
-        b9[7] = a[1] + (v[5] * v[0] - v[3] * v[2]);
-        b9[8] = a[2] + (v[3] * v[1] - v[4] * v[0]);
+            for (int k = 0; k < 9; ++k) sc[SC_RB + k] = Rb[k];
+            double* b9 = c + CX_B9;
+            b9[0] = v[3]; b9[1] = v[4]; b9[2] = v[5];
+            b9[3] = a[3]; b9[4] = a[4]; b9[5] = a[5];
+            b9[6] = a[0] + (v[4] * v[2] - v[5] * v[1]);
+            b9[7] = a[1] + (v[5] * v[0] - v[3] * v[2]);
+            b9[8] = a[2] + (v[3] * v[1] - v[4] * v[0]);
+        }
     }
-    double R[9], p[3];
-    const int len = M.fch_len[ch], own = M.fch_own[ch];
     for (int e = 0; e < len; ++e) {
         const int j = M.fch[ch][e];
         const double qd = in[(IN_DQ + 4 + j) * SB], qdd = in[(IN_DDQ + 4 + j) * SB];
-        const double sn = scr[s * SC_STRIDE + SC_SC + 2 * (j - 2)], cs = scr[s * SC_STRIDE + SC_SC + 2 * (j - 2) + 1];
         double Rl[9];
-        joint_rotation_compose(M, j, sn, cs, Rl);
+        joint_rotation_compose(M, j, scs[2 * (j - 2)], scs[2 * (j - 2) + 1], Rl);
         const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
-        {   // motion: actInv of the parent's (v, a), then the joint's own contribution
-            const double tvx = v[0] - (py * v[5] - pz * v[4]), tvy = v[1] - (pz * v[3] - px * v[5]), tvz = v[2] - (px * v[4] - py * v[3]);
-            const double tax = a[0] - (py * a[5] - pz * a[4]), tay = a[1] - (pz * a[3] - px * a[5]), taz = a[2] - (px * a[4] - py * a[3]);
-            double nv_[6], na[6];
+        // actInv of the parent's (v, a), then the joint's own contribution
+        const double tvx = v[0] - (py * v[5] - pz * v[4]), tvy = v[1] - (pz * v[3] - px * v[5]), tvz = v[2] - (px * v[4] - py * v[3]);
+        const double tax = a[0] - (py * a[5] - pz * a[4]), tay = a[1] - (pz * a[3] - px * a[5]), taz = a[2] - (px * a[4] - py * a[3]);
+        double nv_[6], na[6];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                nv_[k] = Rl[k] * tvx + Rl[3 + k] * tvy + Rl[6 + k] * tvz;
-                nv_[3 + k] = Rl[k] * v[3] + Rl[3 + k] * v[4] + Rl[6 + k] * v[5];
-                na[k] = Rl[k] * tax + Rl[3 + k] * tay + Rl[6 + k] * taz;
-                na[3 + k] = Rl[k] * a[3] + Rl[3 + k] * a[4] + Rl[6 + k] * a[5];
-            }
-            double wj[3];
-            const int jt = M.jtype[j];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) wj[k] = (jt == JT_RU) ? M.axis[j][k] : ((jt - JT_RX) == k ? 1.0 : 0.0);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) nv_[3 + k] += wj[k] * qd;
-            const double w0 = wj[0] * qd, w1 = wj[1] * qd, w2 = wj[2] * qd;
-            na[0] += nv_[1] * w2 - nv_[2] * w1; na[1] += nv_[2] * w0 - nv_[0] * w2; na[2] += nv_[0] * w1 - nv_[1] * w0;
-            na[3] += nv_[4] * w2 - nv_[5] * w1 + wj[0] * qdd; na[4] += nv_[5] * w0 - nv_[3] * w2 + wj[1] * qdd; na[5] += nv_[3] * w1 - nv_[4] * w0 + wj[2] * qdd;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) { v[k] = nv_[k]; a[k] = na[k]; }
+        for (int k = 0; k < 3; ++k) {
+            nv_[k] = Rl[k] * tvx + Rl[3 + k] * tvy + Rl[6 + k] * tvz;
+            nv_[3 + k] = Rl[k] * v[3] + Rl[3 + k] * v[4] + Rl[6 + k] * v[5];
+            na[k] = Rl[k] * tax + Rl[3 + k] * tay + Rl[6 + k] * taz;
+            na[3 + k] = Rl[k] * a[3] + Rl[3 + k] * a[4] + Rl[6 + k] * a[5];
         }
-        if (e == 0) {
+        double wj[3];
+        const int jt = M.jtype[j];
 #pragma unroll
-            for (int k = 0; k < 9; ++k) R[k] = Rl[k];
-            p[0] = px; p[1] = py; p[2] = pz;
-        } else {
-            double Rn[9];
+        for (int k = 0; k < 3; ++k) wj[k] = (jt == JT_RU) ? M.axis[j][k] : ((jt - JT_RX) == k ? 1.0 : 0.0);
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
+        for (int k = 0; k < 3; ++k) nv_[3 + k] += wj[k] * qd;
+        const double w0 = wj[0] * qd, w1 = wj[1] * qd, w2 = wj[2] * qd;
+        na[0] += nv_[1] * w2 - nv_[2] * w1; na[1] += nv_[2] * w0 - nv_[0] * w2; na[2] += nv_[0] * w1 - nv_[1] * w0;
+        na[3] += nv_[4] * w2 - nv_[5] * w1 + wj[0] * qdd; na[4] += nv_[5] * w0 - nv_[3] * w2 + wj[1] * qdd; na[5] += nv_[3] * w1 - nv_[4] * w0 + wj[2] * qdd;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) Rn[3 * r + k] = R[3 * r] * Rl[k] + R[3 * r + 1] * Rl[3 + k] + R[3 * r + 2] * Rl[6 + k];
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) p[r] += R[3 * r] * px + R[3 * r + 1] * py + R[3 * r + 2] * pz;
-#pragma unroll
-            for (int k = 0; k < 9; ++k) R[k] = Rn[k];
-        }
+        for (int k = 0; k < 6; ++k) { v[k] = nv_[k]; a[k] = na[k]; }
         if (e >= own) {
-            double* X = c + CX_X + 12 * (j - 2);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) X[k] = R[k];
-            X[9] = p[0]; X[10] = p[1]; X[11] = p[2];
-            double z0, z1, z2;
-            const int jt = M.jtype[j];
-            if (jt == JT_RU) {
-                const double u0 = M.axis[j][0], u1 = M.axis[j][1], u2 = M.axis[j][2];
-                z0 = R[0] * u0 + R[1] * u1 + R[2] * u2; z1 = R[3] * u0 + R[4] * u1 + R[5] * u2; z2 = R[6] * u0 + R[7] * u1 + R[8] * u2;
-            } else if (jt == JT_RX) { z0 = R[0]; z1 = R[3]; z2 = R[6]; }
-            else if (jt == JT_RY) { z0 = R[1]; z1 = R[4]; z2 = R[7]; }
-            else { z0 = R[2]; z1 = R[5]; z2 = R[8]; }
-            double* A = c + CX_A + 6 * (j - 2);
-            A[0] = p[1] * z2 - p[2] * z1; A[1] = p[2] * z0 - p[0] * z2; A[2] = p[0] * z1 - p[1] * z0;
-            A[3] = z0; A[4] = z1; A[5] = z2;
             double* b9 = c + CX_B9 + 9 * (j - 1);
             b9[0] = v[3]; b9[1] = v[4]; b9[2] = v[5];
             b9[3] = a[3]; b9[4] = a[4]; b9[5] = a[5];
@@ -222,7 +258,6 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
 }
 
 // ---------------------------------------------------------------------------------------------- feet
-// Also copies dq / tau of the actuated joints into the context (threads of slot 0).
 template <int SB>
 __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
                                            double* __restrict__ ctx, double* __restrict__ scr, int t) {
@@ -244,10 +279,6 @@ __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, lo
     }
     if (slot == 0) {
         sc[SC_META] = (double)(3 * m);
-        for (int k = 0; k < M.nd; ++k) {
-            c[CX_DQ + k] = inp[(IN_DQ + 6 + k) * SB + s];
-            c[CX_TAU + k] = inp[(IN_TAU + k) * SB + s];
-        }
     }
     sc[SC_META + 1 + slot] = (double)kf;
     if (kf < 0) return;
@@ -621,11 +652,12 @@ __device__ __forceinline__ void phase_fill_chains(const DevModel& M, const doubl
     auto Pe = [&](int cc) { return (cc <= r) ? P[r * (r + 1) / 2 + cc] : P[cc * (cc + 1) / 2 + r]; };
     for (int g = t / GL; g <= ngroups; g += NT / GL) {
         if (g < ngroups) {
-            const int ch = g / split, q = g - ch * split;
+            const int ch = (split == 1) ? g : (g >> 1), q = (split == 1) ? 0 : (g & 1);      // split is 1 or 2
             const int len = M.fch_len[ch], own = M.fch_own[ch];
+            // body e of the chain is emitted by split index e mod split, tracked by a counter (no integer division)
             if (wsq == 0.0) {
-                for (int e = own; e < len; ++e)
-                    if (e % split == q) {
+                for (int e = 0, turn = 0; e < len; ++e, turn = (turn + 1 == split) ? 0 : turn + 1)
+                    if (e >= own && turn == q) {
                         double2* d2 = reinterpret_cast<double2*>(row + 10 * (M.fch[ch][e] - 1));
 #pragma unroll
                         for (int k = 0; k < 5; ++k) d2[k] = make_double2(0.0, 0.0);
@@ -635,13 +667,13 @@ __device__ __forceinline__ void phase_fill_chains(const DevModel& M, const doubl
             double d[6];
 #pragma unroll
             for (int k = 0; k < 6; ++k) d[k] = Pe(k);
-            for (int e = 0; e < len; ++e) {
+            for (int e = 0, turn = 0; e < len; ++e, turn = (turn + 1 == split) ? 0 : turn + 1) {
                 const int j = M.fch[ch][e];
                 const double pj = Pe(4 + j);
                 const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { const double2 ak = A2[k]; d[2 * k] = fma(pj, ak.x, d[2 * k]); d[2 * k + 1] = fma(pj, ak.y, d[2 * k + 1]); }
-                if (e >= own && e % split == q) {
+                if (e >= own && turn == q) {
                     const double2* X2 = reinterpret_cast<const double2*>(c + CX_X + 12 * (j - 2));
                     const double2 x01 = X2[0], x23 = X2[1], x45 = X2[2], x67 = X2[3], x8p = X2[4], p12 = X2[5];
                     const double p0 = x8p.y, p1 = p12.x, p2 = p12.y;
