@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/sysid_b200.h"
+#include "gram_kernels.cuh"     // DMMA helper and the 8x8 tile tables, shared with the Gram kernels
 
 namespace sysid {
 
@@ -231,24 +232,164 @@ __device__ inline void eig_sym4(const double* in, double ev[4], double V[16]) {
     }
 }
 
-// In-place inverse of the SPD matrix A (n x n, leading dimension ld, in shared memory) by Gauss-Jordan.
-__device__ inline void spd_inverse_inplace(double* A, int n, int ld, double* colbuf, int tid) {
-    for (int k = 0; k < n; ++k) {
-        for (int i = tid; i < n; i += SDP_THREADS) colbuf[i] = A[i * ld + k];
+// In-place Cholesky factorisation A = L L^T of the SPD matrix A (n x n <= 160 x 160, leading dimension ld odd, lower
+// triangle, in shared memory), blocked by panels of 8 columns.  The trailing matrix lives, NEGATED, in DMMA accumulator
+// fragments (the 210 lower-triangular 8x8 tiles of the Gram kernels, same warp ownership), so the rank-8 update
+// -A += P P^T of every panel is mma.sync m8n8k4 f64 straight from the panel buffer; per panel:
+//   1. owners of the panel's tiles write them (un-negated) to pan[k][row]   (k-major, pitch TILE_LD: the fragment layout)
+//   2. every warp that has rows to solve factors the 8 x 8 diagonal block redundantly in lanes 0..7 (shuffles), then
+//      one thread per row forward-substitutes its panel row; results go to A (final L) and back to pan
+//   3. all warps: two DMMAs per owned tile right of the panel
+// invd[k] = 1 / L[k][k] (rsqrt: a Newton direction does not need the last ulp).
+constexpr int SDP_PAN_DOUBLES = 8 * TILE_LD;
+
+template <int W>
+__device__ __forceinline__ void chol_load_tiles(const double* A, int n, int ld, int lane, double (&acc)[GRAM_MAXNT][2]) {
+    using T = WarpTiles<16, W>;
+#pragma unroll
+    for (int t = 0; t < T::NT; ++t) {
+        const int r = 8 * T::G(T::IA(t)) + (lane >> 2), c0 = 8 * T::G(T::IB(t)) + 2 * (lane & 3);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int cc = c0 + e;
+            double v;
+            if (r < n && cc < n) v = (cc <= r) ? A[r * ld + cc] : A[cc * ld + r];
+            else v = (r == cc) ? 1.0 : 0.0;                    // identity padding up to 160
+            acc[t][e] = -v;
+        }
+    }
+}
+template <int W>
+__device__ __forceinline__ void chol_publish_panel(double* pan, int tp, int lane, const double (&acc)[GRAM_MAXNT][2]) {
+    using T = WarpTiles<16, W>;
+#pragma unroll
+    for (int t = 0; t < T::NT; ++t)
+        if (T::G(T::IB(t)) == tp) {
+            const int r = 8 * T::G(T::IA(t)) + (lane >> 2), k0 = 2 * (lane & 3);
+            pan[k0 * TILE_LD + r] = -acc[t][0];
+            pan[(k0 + 1) * TILE_LD + r] = -acc[t][1];
+        }
+}
+template <int W>
+__device__ __forceinline__ void chol_update_tiles(const double* pan, int tp, int lane, double (&acc)[GRAM_MAXNT][2]) {
+    using T = WarpTiles<16, W>;
+    const double* base = pan + (lane & 3) * TILE_LD + (lane >> 2);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+        double frag[T::NG];
+#pragma unroll
+        for (int g = 0; g < T::NG; ++g) frag[g] = (T::G(g) > tp) ? base[ks * 4 * TILE_LD + 8 * T::G(g)] : 0.0;
+#pragma unroll
+        for (int t = 0; t < T::NT; ++t)
+            if (T::G(T::IB(t)) > tp) dmma884(acc[t][0], acc[t][1], frag[T::IA(t)], frag[T::IB(t)]);
+    }
+}
+#define SDP_WARP_CALL(FN, ...)                                                                             \
+    switch (warp) {                                                                                        \
+        case 0: FN<0>(__VA_ARGS__); break;   case 1: FN<1>(__VA_ARGS__); break;   case 2: FN<2>(__VA_ARGS__); break;    \
+        case 3: FN<3>(__VA_ARGS__); break;   case 4: FN<4>(__VA_ARGS__); break;   case 5: FN<5>(__VA_ARGS__); break;    \
+        case 6: FN<6>(__VA_ARGS__); break;   case 7: FN<7>(__VA_ARGS__); break;   case 8: FN<8>(__VA_ARGS__); break;    \
+        case 9: FN<9>(__VA_ARGS__); break;   case 10: FN<10>(__VA_ARGS__); break; case 11: FN<11>(__VA_ARGS__); break;  \
+        case 12: FN<12>(__VA_ARGS__); break; case 13: FN<13>(__VA_ARGS__); break; case 14: FN<14>(__VA_ARGS__); break;  \
+        default: FN<15>(__VA_ARGS__); break;                                                               \
+    }
+
+__device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, double* pan, int tid) {
+    static_assert(SDP_THREADS == 512, "tile ownership tables are for 16 warps");
+    const int warp = tid >> 5, lane = tid & 31;
+    const unsigned full = 0xffffffffu;
+    double acc[GRAM_MAXNT][2];
+    SDP_WARP_CALL(chol_load_tiles, A, n, ld, lane, acc)
+    for (int tp = 0; tp < 20; ++tp) {
+        if (8 * tp >= n) break;
+        SDP_WARP_CALL(chol_publish_panel, pan, tp, lane, acc)
         __syncthreads();
-        const double p = 1.0 / colbuf[k];
-        for (int e = tid; e < n * n; e += SDP_THREADS) {
-            const int i = e / n, j = e - i * n;
-            if (i == k) continue;
-            const double f = colbuf[i] * p;
-            const double akj = (j == k) ? 1.0 : A[k * ld + j];
-            const double aij = (j == k) ? 0.0 : A[i * ld + j];
-            A[i * ld + j] = aij - f * akj;
+        const int row = 8 * tp + tid;                     // one thread per row at or below the panel's diagonal block
+        if (8 * tp + 32 * warp < 160) {                   // warp-uniform: this warp has rows to solve
+            // 8 x 8 diagonal block, lane b (< 8) owns row b
+            const int b = lane & 7;
+            double s[8], rs[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) s[cc] = pan[cc * TILE_LD + 8 * tp + b];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const double d = fmax(__shfl_sync(full, s[a], a), 1e-300);
+                rs[a] = rsqrt(d);
+                s[a] = (b == a) ? d * rs[a] : s[a] * rs[a];           // L[b][a] (meaningful for b >= a)
+#pragma unroll
+                for (int c2 = a + 1; c2 < 8; ++c2) {
+                    const double lc = __shfl_sync(full, s[a], c2);    // L[c2][a]
+                    s[c2] = fma(-s[a], lc, s[c2]);                    // row b, entry c2 (meaningful for c2 <= b)
+                }
+            }
+            // forward substitution of this thread's panel row against the block: x_c = (v_c - sum_{p<c} x_p L[c][p]) / L[c][c]
+            double x[8];
+            const bool live = row < 160;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) x[cc] = live ? pan[cc * TILE_LD + row] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+#pragma unroll
+                for (int p = 0; p < cc; ++p) x[cc] = fma(-x[p], __shfl_sync(full, s[p], cc), x[cc]);    // L[cc][p] from lane cc
+                x[cc] *= rs[cc];
+            }
+            if (live) {
+                const int rb = row - 8 * tp;              // rows of the diagonal block keep only their lower part
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) {
+                    // rows of the diagonal block (threads 0..7: lane == rb) take the factor itself; they are not written
+                    // back to pan (other warps may still be reading the block, and the update never uses these rows)
+                    const double v = (rb < 8) ? s[cc] : x[cc];
+                    if (rb >= 8) pan[cc * TILE_LD + row] = v;
+                    if (row < n && 8 * tp + cc < n && (rb >= 8 || cc <= rb)) A[row * ld + 8 * tp + cc] = v;
+                    if (rb == cc && 8 * tp + cc < n) invd[8 * tp + cc] = rs[cc];
+                }
+            }
         }
         __syncthreads();
-        for (int j = tid; j < n; j += SDP_THREADS) A[k * ld + j] = ((j == k) ? 1.0 : A[k * ld + j]) * p;
+        SDP_WARP_CALL(chol_update_tiles, pan, tp, lane, acc)
         __syncthreads();
     }
+}
+
+// x = (L L^T)^-1 b by one warp: lane l keeps elements l, l + 32, ... in registers; the pivot element travels by shuffle.
+constexpr int SDP_SOLVE_T = (SDP_MAXC + 31) / 32;      // 5 register slots per lane
+__device__ inline void chol_solve_warp(const double* A, int n, int ld, const double* invd, const double* b, double* x, int lane) {
+    double z[SDP_SOLVE_T];
+#pragma unroll
+    for (int t = 0; t < SDP_SOLVE_T; ++t) { const int i = lane + 32 * t; z[t] = (i < n) ? b[i] : 0.0; }
+    // forward: L z = b
+#pragma unroll
+    for (int tk = 0; tk < SDP_SOLVE_T; ++tk) {
+        for (int kk = 0; kk < 32; ++kk) {
+            const int k = 32 * tk + kk;
+            if (k >= n) break;
+            const double zk = __shfl_sync(0xffffffffu, z[tk] * invd[k], kk);
+            if (lane == kk) z[tk] = zk;
+#pragma unroll
+            for (int t = tk; t < SDP_SOLVE_T; ++t) {
+                const int i = lane + 32 * t;
+                if (i > k && i < n) z[t] = fma(-A[i * ld + k], zk, z[t]);
+            }
+        }
+    }
+    // backward: L^T x = z
+#pragma unroll
+    for (int tk = SDP_SOLVE_T - 1; tk >= 0; --tk) {
+        for (int kk = 31; kk >= 0; --kk) {
+            const int k = 32 * tk + kk;
+            if (k >= n) continue;
+            const double xk = __shfl_sync(0xffffffffu, z[tk] * invd[k], kk);
+            if (lane == kk) z[tk] = xk;
+#pragma unroll
+            for (int t = 0; t <= tk; ++t) {
+                const int i = lane + 32 * t;
+                if (i < k) z[t] = fma(-A[k * ld + i], xk, z[t]);
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < SDP_SOLVE_T; ++t) { const int i = lane + 32 * t; if (i < n) x[i] = z[t]; }
 }
 
 // ------------------------------------------------------------------------------------------------ the solver
@@ -266,14 +407,15 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* Tm = Am + (size_t)L * SDP_ROWS_PER_LINK * 10;   // L*100, T_i row-major (upper triangular)
     double* tf = Tm + (size_t)L * 100;                 // 2nd friction scales
     // shared memory carve-up
-    double* W = sm;                                    // c*c  Newton matrix, inverted in place
-    double* gt = W + c * c;                            // c   scaled linear term
+    const int ldw = c + 1;                             // odd: conflict-free column access
+    double* W = sm;                                    // c*(c+1)  Newton matrix (lower triangle), Cholesky-factored in place
+    double* gt = W + c * ldw;                          // c   scaled linear term
     double* at = gt + c;                               // c   scaled equality vector
     double* y = at + c;                                // c
     double* yt = y + c;                                // c   trial point / K^-1 grad
     double* hy = yt + c;                               // c   Hs y
     double* grad = hy + c;                             // c
-    double* dy = grad + c;                             // c   Newton direction (also the pivot-column buffer of the inverse)
+    double* dy = grad + c;                             // c   Newton direction
     double* Ka = dy + c;                               // c   K^-1 at, then Hs dy
     double* rhs = Ka + c;                              // c   x = T y at the end
     double* lam = rhs + c;                             // m   multiplier
@@ -284,7 +426,11 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* tv = pw + m;                               // m   scratch
     double* evals = tv + m;                            // 2L*4
     double* evecs = evals + 8 * L;                     // 2L*16 (row-major V, columns = eigenvectors)
-    double* red = evecs + 32 * L;                      // 32
+    double* invd = evecs + 32 * L;                     // c   reciprocal pivots of the Cholesky factor
+    double* red = invd + c;                            // 32
+    // 8 x TILE_LD panel buffer of the factorisation: aliases gy|wv|pw|tv|evals (all dead between the Newton-matrix set-up
+    // and the next evaluate()) when they are large enough, else its own buffer behind `red` (small problems)
+    double* pan = (4 * m + 8 * L >= SDP_PAN_DOUBLES) ? gy : red + 32;
     __shared__ double s_scalar[8];
 
     const double n_rows = stats[(size_t)c * c + c + 1];
@@ -435,6 +581,12 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     //   L_sigma(y) = f(y) + (|Proj_K(lam - sigma g(y))|^2 - |lam|^2) / (2 sigma),   f(y) = 1/2 y^T Hs y - gt^T y
     //   inner: Newton on L_sigma restricted to at^T y = total_mass, generalized Hessian Hs + sigma A^T D A with
     //          D in the Clarke Jacobian of Proj_K (from the 4x4 eigen-decompositions);  outer: lam <- Proj_K(lam - sigma g(y)).
+#ifdef SYSID_PHASE_CLOCKS
+    long long ck[6] = {0, 0, 0, 0, 0, 0}, ck0 = clock64();
+#define SDP_TICK(k) { const long long now_ = clock64(); ck[k] += now_ - ck0; ck0 = now_; }
+#else
+#define SDP_TICK(k)
+#endif
     double sigma = 1.0;
     const double eps = fmax(10.0 * prm.tol, 1e-11);
 
@@ -474,9 +626,10 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         return block_sum(part, red, tid);
     };
 
-    // W <- (Hs + sigma A^T D A)^-1 at the current evaluation point (uses wv / evals / evecs)
-    auto newton_matrix_inverse = [&]() {
-        for (int e = tid; e < c * c; e += SDP_THREADS) W[e] = Hs[e];
+    // W <- Cholesky factor of Hs + sigma A^T D A at the current evaluation point (uses wv / evals / evecs)
+    auto newton_matrix_factor = [&]() {
+        for (int a = warp; a < c; a += SDP_THREADS / 32)
+            for (int b = lane; b <= a; b += 32) W[a * ldw + b] = Hs[(size_t)a * c + b];
         __syncthreads();
         // one warp per link: lane a (< 10) owns column a of the link's 10 x 10 diagonal block
         for (int i = warp; i < L; i += SDP_THREADS / 32) {
@@ -531,27 +684,18 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
                     for (int b = 0; b < 10; ++b) colacc[b] += va * Ai[10 * rr + b];
                 }
             }
-            if (lane < 10) {
+            if (lane < 10) {       // the block is symmetric: only its lower triangle is kept
 #pragma unroll
-                for (int b = 0; b < 10; ++b) W[(size_t)(10 * i + b) * c + 10 * i + a] += sigma * colacc[b];
+                for (int b = 0; b < 10; ++b) if (b >= a) W[(10 * i + b) * ldw + 10 * i + a] += sigma * colacc[b];
             }
         }
         for (int k = tid; k < 2 * nd; k += SDP_THREADS)
-            if (wv[L * SDP_ROWS_PER_LINK + k] > 0.0) W[(size_t)(np + k) * c + np + k] += sigma;
+            if (wv[L * SDP_ROWS_PER_LINK + k] > 0.0) W[(np + k) * ldw + np + k] += sigma;
         __syncthreads();
-        spd_inverse_inplace(W, c, c, dy, tid);
+        SDP_TICK(5)
+        chol_factor_smem(W, c, ldw, invd, pan, tid);
     };
 
-    auto matvec_smem = [&](const double* Mx, const double* v, double* out) {      // out = Mx v, Mx c x c in shared memory
-        for (int a = warp; a < c; a += SDP_THREADS / 32) {
-            double s = 0.0;
-            for (int b = lane; b < c; b += 32) s += Mx[a * c + b] * v[b];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            if (lane == 0) out[a] = s;
-        }
-        __syncthreads();
-    };
     auto dot_c = [&](const double* u, const double* v) -> double {
         double part = 0.0;
         for (int a = tid; a < c; a += SDP_THREADS) part += u[a] * v[a];
@@ -587,9 +731,13 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             for (int a = tid; a < c; a += SDP_THREADS) { const double d = grad[a] - nu * at[a]; part += d * d; }
             rd = sqrt(block_sum(part, red, tid));
             if (rd <= tol_in) break;
-            newton_matrix_inverse();
-            matvec_smem(W, grad, yt);                      // yt = K^-1 grad
-            matvec_smem(W, at, Ka);                        // Ka = K^-1 at
+            SDP_TICK(0)
+            newton_matrix_factor();
+            SDP_TICK(1)
+            if (warp == 0) chol_solve_warp(W, c, ldw, invd, grad, yt, lane);        // yt = K^-1 grad
+            else if (warp == 1) chol_solve_warp(W, c, ldw, invd, at, Ka, lane);     // Ka = K^-1 at
+            __syncthreads();
+            SDP_TICK(2)
             const double a_v1 = dot_c(at, yt), a_Ka = dot_c(at, Ka);
             for (int a = tid; a < c; a += SDP_THREADS) dy[a] = -(yt[a] - Ka[a] * (a_v1 / a_Ka));
             __syncthreads();
@@ -608,6 +756,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
                 for (int a = tid; a < c; a += SDP_THREADS) part2 += (hy[a] - gt[a]) * dy[a];
                 lin = block_sum(part2, red, tid);
             }
+            SDP_TICK(3)
             const double val0 = pw2 / (2.0 * sigma);          // f(y) cancels on both sides of the Armijo test
             double t = 1.0;
             bool accepted = false;
@@ -620,6 +769,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
                 t *= 0.5;
             }
             ++iters;
+            SDP_TICK(4)
             if (!accepted) { pw2 = evaluate(y); break; }      // no descent at fp64 resolution: hand over to the multiplier update
             for (int a = tid; a < c; a += SDP_THREADS) { y[a] = yt[a]; hy[a] += t * Ka[a]; }
             __syncthreads();
@@ -638,6 +788,9 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         kkt_prev = rp;
         pw2 = evaluate(y);
     }
+#ifdef SYSID_PHASE_CLOCKS
+    if (tid == 0 && prob == 0) printf("sdp clocks: grad %lld  chol %lld  solve %lld  Hs.dy %lld  linesearch %lld  K-setup %lld  (newton %d)\n", ck[0], ck[1], ck[2], ck[3], ck[4], ck[5], iters);
+#endif
     if (status != SYSID_OK && rp <= 1e3 * eps * (1.0 + gnorm) && rd <= 1e3 * eps * (1.0 + gnorm)) status = SDP_STATUS_INACCURATE;
     __syncthreads();
     // ---- output: x = T y, diagnostics ----------------------------------------------------------------------------------
@@ -725,7 +878,8 @@ inline int sdp_solve_launch(const sysid_sdp_desc& d, const double* stats, int64_
     prm.total_mass = d.total_mass; prm.eps = d.epsilon; prm.const_reg = const_reg; prm.tol = d.tol > 0 ? d.tol : 1e-10;
     prm.max_iters = d.max_iters > 0 ? d.max_iters : SDP_DEFAULT_MAX_ITERS;
     prm.stats_stride = stats_stride; prm.ws_stride = ws_n;
-    const size_t smem = sizeof(double) * ((size_t)prm.c * prm.c + 9 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + 32);
+    const size_t smem = sizeof(double) * ((size_t)prm.c * (prm.c + 1) + 10 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + 32 +
+                                         ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES));
     e = cudaFuncSetAttribute(sdp_alm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { snprintf(msg, msglen, "smem opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
     sdp_alm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, dplan + plan_n, x_out, info_out);
