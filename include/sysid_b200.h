@@ -13,6 +13,8 @@
  *                             P@S^T@diag(dq), P@S^T@diag(sign dq))   reference src/sys_identification.py:113-135,401-418
  *   sysid_gram_accumulate     the demo stacking loops + the normal equations MOSEK forms internally:
  *                             reference demo/solo_identification.py:36-55,79-84 and src/solver.py:186-190
+ *   sysid_gram_accumulate_host  the same call for arrays still in host memory, exactly as read_data leaves them
+ *                             (reference demo/solo_identification.py:9-33): upload and kernel overlap chunk by chunk
  *   sysid_gram_from_stack     same statistics from an already stacked (rows x c) matrix, for callers that built
  *                             Y_proj/B_v/B_c through the per-sample API and hand them to Solver(...)  src/solver.py:6-29
  *   sysid_sdp_solve           Solver.solve_fully_consistent: cvxpy problem + problem.solve(solver=cp.MOSEK)
@@ -115,6 +117,16 @@ int sysid_gram_accumulate(const sysid_model* model, const double* q, const doubl
                           const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
                           int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
                           void* stream);
+
+/* Same statistics from HOST arrays (the layout read_data returns; pinned memory for full PCIe speed): the log is
+ * streamed through two device staging buffers in chunks of `chunk` samples; the copy of chunk k+1 (internal copy
+ * stream, cudaMemcpy2DAsync) overlaps the kernels of chunk k on `stream`.  stats / info / workspace are DEVICE pointers;
+ * weights_host is nullable.  The host arrays must stay valid until `stream` has drained.  ADDS into stats. */
+size_t sysid_gram_host_workspace_bytes(const sysid_model* model, int64_t chunk);
+int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, const double* dq_host, const double* ddq_host,
+                               const double* tau_host, const double* contact_host, int64_t N, int64_t ld_host,
+                               const double* weights_host, int32_t friction, double* stats, int64_t* info,
+                               void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
 
 /* Same statistics from a stacked matrix A (rows x c, row-major, device) and vector b (rows). */
 int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,

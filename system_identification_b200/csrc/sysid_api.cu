@@ -262,6 +262,74 @@ int sysid_gram_accumulate(const sysid_model* model, const double* q, const doubl
     return SYSID_OK;
 }
 
+size_t sysid_gram_host_workspace_bytes(const sysid_model* model, int64_t chunk) {
+    if (!model || chunk <= 0) return 0;
+    const DevModel& M = model->dev;
+    const size_t per_sample = (size_t)M.nq + 2 * (size_t)M.nv + (size_t)M.nd + (size_t)M.n_ee + 1;
+    return sysid_gram_workspace_bytes(model) + 2 * sizeof(double) * per_sample * (size_t)chunk + 256;
+}
+
+int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, const double* dq_host, const double* ddq_host,
+                               const double* tau_host, const double* contact_host, int64_t N, int64_t ld_host,
+                               const double* weights_host, int32_t friction, double* stats, int64_t* info,
+                               void* workspace, size_t workspace_bytes, int64_t chunk, void* stream) {
+    if (!model || !q_host || !dq_host || !ddq_host || !tau_host || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (model->dev.n_ee > 0 && !contact_host) return fail(SYSID_ERR_INVALID, "null contact array");
+    if (N < 0 || ld_host < N || chunk <= 0) return fail(SYSID_ERR_INVALID, "bad N/ld/chunk");
+    if (N == 0) return SYSID_OK;
+    if (workspace_bytes < sysid_gram_host_workspace_bytes(model, chunk)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+    const DevModel& M = model->dev;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t gram_ws = (sysid_gram_workspace_bytes(model) + 255) & ~(size_t)255;
+    const size_t per_sample = (size_t)M.nq + 2 * (size_t)M.nv + (size_t)M.nd + (size_t)M.n_ee + 1;
+    double* stage[2] = {(double*)((char*)workspace + gram_ws), (double*)((char*)workspace + gram_ws) + per_sample * (size_t)chunk};
+    cudaStream_t cp = nullptr;
+    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, start = nullptr;
+    int rc = SYSID_OK;
+    auto cleanup = [&]() {
+        for (int b = 0; b < 2; ++b) { if (copied[b]) cudaEventDestroy(copied[b]); if (consumed[b]) cudaEventDestroy(consumed[b]); }
+        if (start) cudaEventDestroy(start);
+        if (cp) cudaStreamDestroy(cp);       // pending copies complete first; the runtime releases the stream afterwards
+    };
+#define HOST_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(SYSID_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+    HOST_TRY(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+    HOST_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    for (int b = 0; b < 2; ++b) {
+        HOST_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+        HOST_TRY(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+    }
+    // the staging buffers may still be read by earlier work on `stream`
+    HOST_TRY(cudaEventRecord(start, st));
+    HOST_TRY(cudaStreamWaitEvent(cp, start, 0));
+    const size_t W = sizeof(double);
+    long long k = 0;
+    for (int64_t lo = 0; lo < N; lo += chunk, ++k) {
+        const int b = (int)(k & 1);
+        const int64_t n = (N - lo < chunk) ? (N - lo) : chunk;
+        if (k >= 2) HOST_TRY(cudaStreamWaitEvent(cp, consumed[b], 0));
+        double* dq_ = stage[b] + (size_t)M.nq * chunk;
+        double* ddq_ = dq_ + (size_t)M.nv * chunk;
+        double* tau_ = ddq_ + (size_t)M.nv * chunk;
+        double* cnt_ = tau_ + (size_t)M.nd * chunk;
+        double* w_ = cnt_ + (size_t)M.n_ee * chunk;
+        HOST_TRY(cudaMemcpy2DAsync(stage[b], chunk * W, q_host + lo, ld_host * W, n * W, M.nq, cudaMemcpyHostToDevice, cp));
+        HOST_TRY(cudaMemcpy2DAsync(dq_, chunk * W, dq_host + lo, ld_host * W, n * W, M.nv, cudaMemcpyHostToDevice, cp));
+        HOST_TRY(cudaMemcpy2DAsync(ddq_, chunk * W, ddq_host + lo, ld_host * W, n * W, M.nv, cudaMemcpyHostToDevice, cp));
+        HOST_TRY(cudaMemcpy2DAsync(tau_, chunk * W, tau_host + lo, ld_host * W, n * W, M.nd, cudaMemcpyHostToDevice, cp));
+        if (M.n_ee > 0) HOST_TRY(cudaMemcpy2DAsync(cnt_, chunk * W, contact_host + lo, ld_host * W, n * W, M.n_ee, cudaMemcpyHostToDevice, cp));
+        if (weights_host) HOST_TRY(cudaMemcpyAsync(w_, weights_host + lo, n * W, cudaMemcpyHostToDevice, cp));
+        HOST_TRY(cudaEventRecord(copied[b], cp));
+        HOST_TRY(cudaStreamWaitEvent(st, copied[b], 0));
+        rc = sysid_gram_accumulate(model, stage[b], dq_, ddq_, tau_, M.n_ee > 0 ? cnt_ : nullptr, n, chunk, weights_host ? w_ : nullptr,
+                                   friction, stats, info, workspace, gram_ws, st);
+        if (rc != SYSID_OK) { cleanup(); return rc; }
+        HOST_TRY(cudaEventRecord(consumed[b], st));
+    }
+#undef HOST_TRY
+    cleanup();
+    return SYSID_OK;
+}
+
 int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,
                           void* workspace, size_t workspace_bytes, void* stream) {
     if (!A || !b || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");

@@ -14,6 +14,30 @@ from . import distributed as D
 from .ops import to_device, sdp_solve
 
 
+def _host_streamable(arrays, weights):
+    """True when all five arrays are host float64, 2-D, unit inner stride, one common leading dimension."""
+    ts = []
+    for a in arrays:
+        if isinstance(a, np.ndarray):
+            if a.dtype != np.float64 or a.ndim != 2 or a.strides[1] != 8:
+                return False
+            ts.append(a.strides[0])
+        elif isinstance(a, torch.Tensor):
+            if a.is_cuda or a.dtype != torch.float64 or a.dim() != 2 or a.stride(1) != 1:
+                return False
+            ts.append(a.stride(0) * 8)
+        else:
+            return False
+    if len(set(ts)) != 1:
+        return False
+    if weights is not None:
+        w = weights
+        if isinstance(w, np.ndarray):
+            return w.dtype == np.float64 and w.ndim == 1 and w.flags.c_contiguous
+        return isinstance(w, torch.Tensor) and (not w.is_cuda) and w.dtype == torch.float64 and w.is_contiguous()
+    return True
+
+
 def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=1000, reg_type="constant_pullback",
              friction=True, return_info=False, sharded=False, weights=None):
     """sysid: SystemIdentification.  Arrays: (channels x N) numpy or torch (host or device).
@@ -28,13 +52,18 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         q, dq, ddq, tau, cnt = (a[:, lo:hi] for a in (q, dq, ddq, tau, cnt))
         if weights is not None:
             weights = weights[lo:hi]
-    dev = [a if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64) else to_device(a) for a in (q, dq, ddq, tau, cnt)]
-    dev = [a if a.stride(1) == 1 else a.contiguous() for a in dev]
-    if len({a.stride(0) for a in dev}) != 1:
-        dev = [a.contiguous() for a in dev]
-    if weights is not None and not (isinstance(weights, torch.Tensor) and weights.is_cuda):
-        weights = torch.as_tensor(np.asarray(weights, dtype=np.float64)).cuda()
-    stats = dm.gram_accumulate(*dev, friction=friction, weights=weights)
+    arrays = (q, dq, ddq, tau, cnt)
+    if _host_streamable(arrays, weights):
+        # host float64 arrays: chunked upload overlapped with the kernel inside the library
+        stats = dm.gram_accumulate_host(*arrays, friction=friction, weights=weights)
+    else:
+        dev = [a if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64) else to_device(a) for a in arrays]
+        dev = [a if a.stride(1) == 1 else a.contiguous() for a in dev]
+        if len({a.stride(0) for a in dev}) != 1:
+            dev = [a.contiguous() for a in dev]
+        if weights is not None and not (isinstance(weights, torch.Tensor) and weights.is_cuda):
+            weights = torch.as_tensor(np.asarray(weights, dtype=np.float64)).cuda()
+        stats = dm.gram_accumulate(*dev, friction=friction, weights=weights)
     D.allreduce_stats(stats)
     L, nd = sysid.get_num_links(), (sysid.joints_dof if friction else 0)
     c = 10 * L + 2 * nd

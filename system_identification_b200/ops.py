@@ -121,6 +121,38 @@ class DeviceModel:
                                                   ws.numel(), _stream()))
         return stats
 
+    def gram_accumulate_host(self, q, dq, ddq, tau, cnt, friction=True, weights=None, stats=None, info=None, chunk=131072,
+                             device=None):
+        """gram_accumulate for arrays still in HOST memory (float64 torch CPU tensors or numpy arrays, channel-major with
+        unit inner stride and one common leading dimension; pinned memory for full PCIe speed): the upload is chunked and
+        overlapped with the kernel inside the library (sysid_gram_accumulate_host).  Returns the device statistics."""
+        hs = []
+        for a, ch, name in ((q, self.nq, "q"), (dq, self.nv, "dq"), (ddq, self.nv, "ddq"), (tau, self.nd, "tau"), (cnt, self.n_ee, "contact")):
+            t = torch.from_numpy(a) if isinstance(a, np.ndarray) else a
+            if t.is_cuda or t.dtype != torch.float64 or t.dim() != 2 or t.shape[0] != ch or t.stride(1) != 1:
+                raise ValueError(f"{name}: expected a host float64 array of shape ({ch}, N) with unit inner stride")
+            hs.append(t)
+        N = hs[0].shape[1]
+        ld = self._common_ld(*hs)
+        device = torch.device(device or "cuda")
+        if stats is None:
+            stats = torch.zeros(self.stats_len(friction), dtype=torch.float64, device=device)
+        wh = None
+        if weights is not None:
+            wh = torch.from_numpy(weights) if isinstance(weights, np.ndarray) else weights
+            if wh.is_cuda or wh.dtype != torch.float64 or wh.numel() != N or not wh.is_contiguous():
+                raise ValueError("weights: expected contiguous host float64 of length N")
+        chunk = int(max(1, min(chunk, N)))
+        nbytes = self.lib.sysid_gram_host_workspace_bytes(self.handle, chunk)
+        ws = self._workspace("gram_host", nbytes, device)
+        self._keepalive = (hs, wh)        # the host arrays must outlive the asynchronous copies
+        _lib.check(self.lib.sysid_gram_accumulate_host(self.handle, C.c_void_p(hs[0].data_ptr()), C.c_void_p(hs[1].data_ptr()),
+                                                       C.c_void_p(hs[2].data_ptr()), C.c_void_p(hs[3].data_ptr()),
+                                                       C.c_void_p(hs[4].data_ptr()) if self.n_ee > 0 else None, N, ld,
+                                                       C.c_void_p(wh.data_ptr()) if wh is not None else None,
+                                                       1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), chunk, _stream()))
+        return stats
+
     def predict_rmse(self, q, dq, ddq, tau, cnt, phi):
         """(total mean-square, per-joint RMSE) of reference print_tau_prediction_rmse (src/sys_identification.py:421-437)."""
         q = _chan(q, self.nq, "q"); dq = _chan(dq, self.nv, "dq"); ddq = _chan(ddq, self.nv, "ddq")

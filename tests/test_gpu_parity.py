@@ -121,6 +121,33 @@ def test_gram_edge_cases_ragged_empty_accumulate_weights_nan():
         assert np.abs(P.cpu().numpy() - Po).max() <= 1e-12
 
 
+def test_host_streaming_entry_equals_device_entry():
+    """sysid_gram_accumulate_host (chunked upload overlapped with the kernel) == the device-resident call; ragged last
+    chunk, pinned and pageable sources, weights, and identify() taking host arrays directly."""
+    flat, data = H.small_log("g1_12dof", 1000, seed=5)
+    dm = _dev(flat)
+    full = dm.gram_accumulate(*_up(data)).cpu().numpy()
+    host = [np.ascontiguousarray(a, dtype=np.float64) for a in data]
+    for chunk in (1000, 384, 37):
+        st = dm.gram_accumulate_host(*host, chunk=chunk)
+        torch.cuda.synchronize()
+        assert H.rel(st.cpu().numpy(), full) <= 1e-13
+    pinned = [torch.from_numpy(a).pin_memory() for a in host]
+    st = dm.gram_accumulate_host(*pinned, chunk=256)
+    torch.cuda.synchronize()
+    assert H.rel(st.cpu().numpy(), full) <= 1e-13
+    w = np.zeros(1000); w[::3] = 2.0
+    sw = dm.gram_accumulate_host(*host, weights=w, chunk=300)
+    swd = dm.gram_accumulate(*_up(data), weights=torch.from_numpy(w).cuda())
+    torch.cuda.synchronize()
+    assert H.rel(sw.cpu().numpy(), swd.cpu().numpy()) <= 1e-13
+    # a column slice of a wider host array (leading dimension > N)
+    wide = [np.ascontiguousarray(np.concatenate([a, a], axis=1)) for a in host]
+    st = dm.gram_accumulate_host(*(a[:, :1000] for a in wide), chunk=512)
+    torch.cuda.synchronize()
+    assert H.rel(st.cpu().numpy(), full) <= 1e-13
+
+
 def test_api_errors_are_reported_not_thrown_across_the_abi():
     from system_identification_b200 import _lib
     from system_identification_b200.ops import DeviceModel
