@@ -587,7 +587,10 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
 #else
 #define SDP_TICK(k)
 #endif
-    double sigma = 1.0;
+#ifndef SYSID_SDP_SIGMA0
+#define SYSID_SDP_SIGMA0 1000.0     // initial penalty: 1e3 needs ~15 % fewer Newton steps than 1 on the Solo / Spot / G1 problems (same optima)
+#endif
+    double sigma = SYSID_SDP_SIGMA0;
     const double eps = fmax(10.0 * prm.tol, 1e-11);
 
     // evaluate at the point yy: gy = A yy + c0, w = lam - sigma gy, eigen-decompose the LMI blocks of w, pw = Proj_K(w).
