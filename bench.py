@@ -44,6 +44,17 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic(n_loc):
+    """DRAM bytes of one fused-kernel launch from the committed ncu capture (scaled linearly when a rank's launch covers
+    fewer samples than the captured one); None when the capture is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "gram_fused_traffic.json")) as f:
+            t = json.load(f)
+        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n_loc / t["samples_per_launch"]
+    except Exception:
+        return None
+
+
 def load_flat():
     from system_identification_b200.model import FlatModel
     return FlatModel.load(os.path.join(ROOT, "system_identification_b200", "robots", ROBOT + ".json"))
@@ -261,7 +272,8 @@ def run_ours(args):
                        "samples_per_rank": n_loc, "sharding": f"contiguous time shards over {world} rank(s), one NCCL all-reduce of {c * c + c + 2} fp64",
                        "l2": "256 MiB buffer rewritten between timed iterations (inputs per rank: %.0f MB)" % (BYTES_PER_SAMPLE * n_loc / 1e6)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": None, "peak_source": peak_how,
+                         "traffic": ncu_traffic(n_loc), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/gram_fused_traffic.json)",
+                         "algorithmic_bytes": BYTES_PER_SAMPLE * n_loc, "peak_source": peak_how,
                          "note": "fp64 DMMA contraction; achieved = 435204 algorithmic FLOP/sample x samples per launch / CUDA-event time of the fused kernel (+ its 10-us reduction kernel)",
                          "hbm_stream_gbs": BYTES_PER_SAMPLE * n_loc / kernel_s * 1e-9},
             "e2e": {"value": N_SAMPLES * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": BYTES_PER_SAMPLE * N_SAMPLES,
