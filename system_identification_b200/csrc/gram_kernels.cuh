@@ -117,7 +117,7 @@ constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
     for (int it = t; it < 2 * ((SB * M.nfch + 31) & ~31); it += NT) phase_chains<SB>(M, base, args.N, inp, ctx, scr, it); \
     SYNC();                                                                                                              \
     F_TICK(1)                                                                                                            \
-    for (int it = t; it < SB * MAXEE; it += NT) phase_feet<SB>(M, base, args.N, inp, ctx, scr, it);                      \
+    for (int it = t; it < SB * MAXEE * (MAXCH + 1); it += NT) phase_feet<SB>(M, base, args.N, inp, ctx, scr, it);        \
     SYNC();                                                                                                              \
     for (int it = t; it < SB * (MAXEE * (MAXEE + 1) / 2); it += NT) phase_sblocks<SB>(M, base, args.N, ctx, scr, it);    \
     SYNC();                                                                                                              \

@@ -36,15 +36,16 @@ constexpr int CX_P = 0;                             // [171] packed lower triang
 constexpr int CX_W = CX_P + NPACK;                  // sqrt(weight); 0 => sample contributes nothing
 constexpr int CX_A = CX_W + 1;                      // [MAXD][6] Pluecker axis (m; z) of every revolute joint
 constexpr int CX_X = CX_A + 6 * MAXD;               // [MAXD][12] R (9, row-major), p (3) relative to the base
-constexpr int CX_B9 = CX_X + 12 * MAXD;             // [MAXB][9] omega, alpha, acc (local frame)
-constexpr int CX_DQ = CX_B9 + 9 * MAXB;             // [MAXD]
+constexpr int B9S = 10;                             // body-motion record: omega, alpha, acc + 1 pad (16-byte loads)
+constexpr int CX_B9 = CX_X + 12 * MAXD;             // [MAXB][B9S] omega, alpha, acc (local frame)
+constexpr int CX_DQ = CX_B9 + B9S * MAXB;           // [MAXD]
 constexpr int CX_TAU = CX_DQ + MAXD;                // [MAXD]
-constexpr int CX_STRIDE = CX_TAU + MAXD + 1;        // 530
+constexpr int CX_STRIDE = CX_TAU + MAXD + 4;        // 546 == 2 (mod 16): lanes of consecutive samples hit distinct banks
 // temporaries living in the P slot until `proj` overwrites it
 constexpr int CXT_S = CX_P;                         // [78] packed S, then L
 constexpr int CXT_JL = CX_P + 78;                   // [MAXEE][MAXCH][3] leg columns of J_c
 static_assert(78 + 3 * MAXEE * MAXCH <= NPACK, "temporaries fit the P slot");
-static_assert(CX_STRIDE % 2 == 0 && CX_A % 2 == 0, "context stride keeps 16-byte alignment");
+static_assert(CX_STRIDE % 16 == 2 && CX_A % 2 == 0 && CX_X % 2 == 0 && CX_B9 % 2 == 0, "context layout keeps 16-byte alignment");
 
 // ---- per-sample scratch (doubles), only live inside the F phases -------------------------------------------
 constexpr int SC_RB = 0;                            // [9] R_b from the raw quaternion
@@ -247,7 +248,7 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
 #pragma unroll
         for (int k = 0; k < 6; ++k) { v[k] = nv_[k]; a[k] = na[k]; }
         if (e >= own) {
-            double* b9 = c + CX_B9 + 9 * (j - 1);
+            double* b9 = c + CX_B9 + B9S * (j - 1);
             b9[0] = v[3]; b9[1] = v[4]; b9[2] = v[5];
             b9[3] = a[3]; b9[4] = a[4]; b9[5] = a[5];
             b9[6] = a[0] + (v[4] * v[2] - v[5] * v[1]);
@@ -258,11 +259,13 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
 }
 
 // ---------------------------------------------------------------------------------------------- feet
+// Thread per (sample, stance slot, e): e < MAXCH -> leg column e of the slot's contact Jacobian rows,
+// e == MAXCH -> the slot's world-aligned lever arm and the stance bookkeeping.
 template <int SB>
 __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
                                            double* __restrict__ ctx, double* __restrict__ scr, int t) {
-    if (t >= SB * MAXEE) return;
-    const int s = t % SB, slot = t / SB;
+    if (t >= SB * MAXEE * (MAXCH + 1)) return;
+    const int s = t % SB, u = t / SB, slot = u % MAXEE, e = u / MAXEE;
     if (base + s >= N) return;
     double* c = ctx + s * CX_STRIDE;
     double* sc = scr + s * SC_STRIDE;
@@ -277,11 +280,12 @@ __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, lo
             }
         }
     }
-    if (slot == 0) {
-        sc[SC_META] = (double)(3 * m);
+    if (e == MAXCH) {
+        if (slot == 0) sc[SC_META] = (double)(3 * m);
+        sc[SC_META + 1 + slot] = (double)kf;
     }
-    sc[SC_META + 1 + slot] = (double)kf;
     if (kf < 0) return;
+    if (e < MAXCH && e >= M.chain_len[kf]) return;
     double Rb[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) Rb[k] = sc[SC_RB + k];
@@ -289,28 +293,28 @@ __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, lo
     double rf[3];   // foot point in the base frame
     if (jf == 1) {
 #pragma unroll
-        for (int e = 0; e < 3; ++e) rf[e] = M.ee_off[kf][e];
+        for (int k = 0; k < 3; ++k) rf[k] = M.ee_off[kf][k];
     } else {
         const double* X = c + CX_X + 12 * (jf - 2);
 #pragma unroll
-        for (int e = 0; e < 3; ++e) rf[e] = X[9 + e] + X[3 * e] * M.ee_off[kf][0] + X[3 * e + 1] * M.ee_off[kf][1] + X[3 * e + 2] * M.ee_off[kf][2];
+        for (int k = 0; k < 3; ++k) rf[k] = X[9 + k] + X[3 * k] * M.ee_off[kf][0] + X[3 * k + 1] * M.ee_off[kf][1] + X[3 * k + 2] * M.ee_off[kf][2];
     }
+    if (e == MAXCH) {
 #pragma unroll
-    for (int e = 0; e < 3; ++e) sc[SC_RF + 3 * slot + e] = Rb[3 * e] * rf[0] + Rb[3 * e + 1] * rf[1] + Rb[3 * e + 2] * rf[2];
-    const int len = M.chain_len[kf];
-    for (int e = 0; e < len; ++e) {
-        const int cj = M.chain[kf][e];
-        const double* A = c + CX_A + 6 * (cj - 2);
-        const double* X = c + CX_X + 12 * (cj - 2);
-        const double ax0 = A[3], ax1 = A[4], ax2 = A[5];
-        const double bx = rf[0] - X[9], by = rf[1] - X[10], bz = rf[2] - X[11];
-        const double a0 = Rb[0] * ax0 + Rb[1] * ax1 + Rb[2] * ax2, a1 = Rb[3] * ax0 + Rb[4] * ax1 + Rb[5] * ax2, a2 = Rb[6] * ax0 + Rb[7] * ax1 + Rb[8] * ax2;
-        const double dx = Rb[0] * bx + Rb[1] * by + Rb[2] * bz, dy = Rb[3] * bx + Rb[4] * by + Rb[5] * bz, dz = Rb[6] * bx + Rb[7] * by + Rb[8] * bz;
-        double* jl = c + CXT_JL + 3 * (slot * MAXCH + e);
-        jl[0] = a1 * dz - a2 * dy;
-        jl[1] = a2 * dx - a0 * dz;
-        jl[2] = a0 * dy - a1 * dx;
+        for (int k = 0; k < 3; ++k) sc[SC_RF + 3 * slot + k] = Rb[3 * k] * rf[0] + Rb[3 * k + 1] * rf[1] + Rb[3 * k + 2] * rf[2];
+        return;
     }
+    const int cj = M.chain[kf][e];
+    const double* A = c + CX_A + 6 * (cj - 2);
+    const double* X = c + CX_X + 12 * (cj - 2);
+    const double ax0 = A[3], ax1 = A[4], ax2 = A[5];
+    const double bx = rf[0] - X[9], by = rf[1] - X[10], bz = rf[2] - X[11];
+    const double a0 = Rb[0] * ax0 + Rb[1] * ax1 + Rb[2] * ax2, a1 = Rb[3] * ax0 + Rb[4] * ax1 + Rb[5] * ax2, a2 = Rb[6] * ax0 + Rb[7] * ax1 + Rb[8] * ax2;
+    const double dx = Rb[0] * bx + Rb[1] * by + Rb[2] * bz, dy = Rb[3] * bx + Rb[4] * by + Rb[5] * bz, dz = Rb[6] * bx + Rb[7] * by + Rb[8] * bz;
+    double* jl = c + CXT_JL + 3 * (slot * MAXCH + e);
+    jl[0] = a1 * dz - a2 * dy;
+    jl[1] = a2 * dx - a0 * dz;
+    jl[2] = a0 * dy - a1 * dx;
 }
 
 // ---------------------------------------------------------------------------------------------- S blocks
@@ -390,8 +394,10 @@ __device__ __forceinline__ void phase_chol(long long base, long long N, double* 
         double d = S[tri(a, a)];
         for (int k = 0; k < a; ++k) { const double l = S[tri(a, k)]; d -= l * l; }
         double inv;
-        if (d > piv_tol) { const double sd = sqrt(d); S[tri(a, a)] = sd; inv = 1.0 / sd; }
-        else { S[tri(a, a)] = 0.0; inv = 0.0; flags |= 1; }    // row a is (numerically) dependent: drop it
+        // the diagonal keeps 1 / L[a][a] (rsqrt, 1-2 ulp): that is all the W columns need; 0 marks a dropped row
+        if (d > piv_tol) inv = rsqrt(d);
+        else { inv = 0.0; flags |= 1; }                        // row a is (numerically) dependent: drop it (pinv semantics)
+        S[tri(a, a)] = inv;
         for (int b = a + 1; b < m3; ++b) {
             double vv = S[tri(b, a)];
             for (int k = 0; k < a; ++k) vv -= S[tri(b, k)] * S[tri(a, k)];
@@ -438,9 +444,7 @@ __device__ __forceinline__ void phase_wcols(const DevModel& M, long long base, l
                 double val = (x == 0) ? j0 : ((x == 1) ? j1 : j2);
 #pragma unroll
                 for (int l = 0; l < 3 * MAXEE; ++l) if (l < k) val = fma(-L[tri(k, l)], w[l], val);
-                const double lkk = L[tri(k, k)];
-                const double inv = (lkk != 0.0) ? 1.0 / lkk : 0.0;     // dropped (dependent) row: W row = 0
-                w[k] = val * inv;
+                w[k] = val * L[tri(k, k)];                 // the diagonal holds 1 / L[k][k] (0 for a dropped row: W row = 0)
                 sc[SC_WM + k * MAXV + col] = w[k];
             }
         }
@@ -454,7 +458,7 @@ template <int SB, int NT>
 __device__ __forceinline__ void phase_proj(long long base, long long N, const double* __restrict__ inp, double* __restrict__ ctx,
                                            const double* __restrict__ scr, const int* s_bad, int t, double* s_stat) {
     for (int it = t; it < SB * MAXV; it += NT) {
-        const int s = it % SB, r = MAXV - 1 - it / SB;      // long rows first
+        const int s = it / MAXV, r = it - s * MAXV;         // row fastest: the lanes of a sample read the same W row (broadcast)
         if (base + s >= N) continue;
         const double* sc = scr + s * SC_STRIDE;
         const int m3 = (int)sc[SC_META];
@@ -499,7 +503,9 @@ __device__ __forceinline__ void phase_proj(long long base, long long N, const do
 // Ten entries of one projected row of body i from its body-frame coefficients (el; ea) = bodyRegressor^T (el; ea).
 __device__ __forceinline__ void body_row(const double* __restrict__ b9, double el0, double el1, double el2,
                                          double ea0, double ea1, double ea2, double* __restrict__ dst) {
-    const double w0 = b9[0], w1 = b9[1], w2 = b9[2], al0 = b9[3], al1 = b9[4], al2 = b9[5], ac0 = b9[6], ac1 = b9[7], ac2 = b9[8];
+    const double2* b2 = reinterpret_cast<const double2*>(b9);
+    const double2 q0 = b2[0], q1 = b2[1], q2 = b2[2], q3 = b2[3];
+    const double w0 = q0.x, w1 = q0.y, w2 = q1.x, al0 = q1.y, al1 = q2.x, al2 = q2.y, ac0 = q3.x, ac1 = q3.y, ac2 = b9[8];
     double o[10];
     // mass column: el . acc
     o[0] = el0 * ac0 + el1 * ac1 + el2 * ac2;
@@ -594,7 +600,7 @@ __device__ __forceinline__ void phase_fill(const DevModel& M, const double* __re
 #pragma unroll
                     for (int k = 0; k < 6; ++k) e[g][k] = d[g][k];
             }
-            const double* b9 = c + CX_B9 + 9 * ib;
+            const double* b9 = c + CX_B9 + B9S * ib;
 #pragma unroll
             for (int g = 0; g < RPI; ++g)
                 body_row(b9, e[g][0] * wsq, e[g][1] * wsq, e[g][2] * wsq, e[g][3] * wsq, e[g][4] * wsq, e[g][5] * wsq, dst + g * LD);
@@ -681,7 +687,7 @@ __device__ __forceinline__ void phase_fill_chains(const DevModel& M, const doubl
                     // (el; ea) = (R^T u; R^T da), R row-major in x01..x8p
                     const double el0 = x01.x * u0 + x23.y * u1 + x67.x * u2, el1 = x01.y * u0 + x45.x * u1 + x67.y * u2, el2 = x23.x * u0 + x45.y * u1 + x8p.x * u2;
                     const double ea0 = x01.x * d[3] + x23.y * d[4] + x67.x * d[5], ea1 = x01.y * d[3] + x45.x * d[4] + x67.y * d[5], ea2 = x23.x * d[3] + x45.y * d[4] + x8p.x * d[5];
-                    body_row(c + CX_B9 + 9 * (j - 1), el0 * wsq, el1 * wsq, el2 * wsq, ea0 * wsq, ea1 * wsq, ea2 * wsq, row + 10 * (j - 1));
+                    body_row(c + CX_B9 + B9S * (j - 1), el0 * wsq, el1 * wsq, el2 * wsq, ea0 * wsq, ea1 * wsq, ea2 * wsq, row + 10 * (j - 1));
                 }
             }
         } else {
