@@ -189,16 +189,37 @@ __device__ __forceinline__ double block_sum(double v, double* red, int tid) {
 
 // Eigen-decomposition of a symmetric 4x4 given in svec form (off-diagonals carry sqrt(2)) by cyclic Jacobi.
 // ev[e] = eigenvalue e, V[4 * row + e] = component `row` of eigenvector e.
-__device__ inline void eig_sym4(const double* in, double ev[4], double V[16]) {
+// V0 (nullable): an orthogonal basis to start from -- the eigenvectors of the previous evaluation of the same cone --
+// so that only the change since then has to be rotated away (1-2 sweeps instead of 5-6).
+__device__ inline void eig_sym4(const double* in, double ev[4], double V[16], const double* V0 = nullptr) {
     const double IS2 = 0.70710678118654752440;
     double a[4][4], v[4][4];
     a[0][0] = in[0]; a[1][0] = a[0][1] = in[1] * IS2; a[1][1] = in[2];
     a[2][0] = a[0][2] = in[3] * IS2; a[2][1] = a[1][2] = in[4] * IS2; a[2][2] = in[5];
     a[3][0] = a[0][3] = in[6] * IS2; a[3][1] = a[1][3] = in[7] * IS2; a[3][2] = a[2][3] = in[8] * IS2; a[3][3] = in[9];
+    if (V0) {
+        double av[4][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+            for (int j = 0; j < 4; ++j) v[i][j] = V0[4 * i + j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) av[i][j] = a[i][0] * v[0][j] + a[i][1] * v[1][j] + a[i][2] * v[2][j] + a[i][3] * v[3][j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = i; j < 4; ++j) {
+                const double t = v[0][i] * av[0][j] + v[1][i] * av[1][j] + v[2][i] * av[2][j] + v[3][i] * av[3][j];
+                a[i][j] = t; a[j][i] = t;
+            }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[i][j] = (i == j) ? 1.0 : 0.0;
+    }
     for (int sweep = 0; sweep < 12; ++sweep) {
         double off = 0.0, tot = 0.0;
 #pragma unroll
@@ -294,16 +315,24 @@ __device__ __forceinline__ void chol_update_tiles(const double* pan, int tp, int
         default: FN<15>(__VA_ARGS__); break;                                                               \
     }
 
-__device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, double* pan, int tid) {
+__device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, double* pan, int tid, long long* dbg = nullptr) {
     static_assert(SDP_THREADS == 512, "tile ownership tables are for 16 warps");
     const int warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
     double acc[GRAM_MAXNT][2];
+#ifdef SYSID_PHASE_CLOCKS
+    long long c0_ = clock64();
+#define CH_TICK(k) if (dbg) { const long long now_ = clock64(); dbg[k] += now_ - c0_; c0_ = now_; }
+#else
+#define CH_TICK(k)
+#endif
     SDP_WARP_CALL(chol_load_tiles, A, n, ld, lane, acc)
+    CH_TICK(0)
     for (int tp = 0; tp < 20; ++tp) {
         if (8 * tp >= n) break;
         SDP_WARP_CALL(chol_publish_panel, pan, tp, lane, acc)
         __syncthreads();
+        CH_TICK(1)
         const int row = 8 * tp + tid;                     // one thread per row at or below the panel's diagonal block
         if (8 * tp + 32 * warp < 160) {                   // warp-uniform: this warp has rows to solve
             // 8 x 8 diagonal block, lane b (< 8) owns row b
@@ -333,58 +362,127 @@ __device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, 
                 for (int p = 0; p < cc; ++p) x[cc] = fma(-x[p], __shfl_sync(full, s[p], cc), x[cc]);    // L[cc][p] from lane cc
                 x[cc] *= rs[cc];
             }
-            if (live) {
-                const int rb = row - 8 * tp;              // rows of the diagonal block keep only their lower part
+            if (live && row >= 8 * tp + 8) {              // rows below the diagonal block: final L entries, and back to pan
 #pragma unroll
                 for (int cc = 0; cc < 8; ++cc) {
-                    // rows of the diagonal block (threads 0..7: lane == rb) take the factor itself; they are not written
-                    // back to pan (other warps may still be reading the block, and the update never uses these rows)
-                    const double v = (rb < 8) ? s[cc] : x[cc];
-                    if (rb >= 8) pan[cc * TILE_LD + row] = v;
-                    if (row < n && 8 * tp + cc < n && (rb >= 8 || cc <= rb)) A[row * ld + 8 * tp + cc] = v;
-                    if (rb == cc && 8 * tp + cc < n) invd[8 * tp + cc] = rs[cc];
+                    pan[cc * TILE_LD + row] = x[cc];
+                    if (row < n && 8 * tp + cc < n) A[row * ld + 8 * tp + cc] = x[cc];
                 }
+            }
+        } else if (warp == 5) {
+            // an otherwise idle warp: the INVERSE of the diagonal block goes into A's diagonal block (that is what the
+            // blocked triangular solves use).  Lane c < 8 forward-substitutes e_c: x[cc] = (L_dd^-1)[cc][c].
+            const int b = lane & 7;
+            double s[8], rs[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) s[cc] = pan[cc * TILE_LD + 8 * tp + b];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const double d = fmax(__shfl_sync(full, s[a], a), 1e-300);
+                rs[a] = rsqrt(d);
+                s[a] = (b == a) ? d * rs[a] : s[a] * rs[a];
+#pragma unroll
+                for (int c2 = a + 1; c2 < 8; ++c2) {
+                    const double lc = __shfl_sync(full, s[a], c2);
+                    s[c2] = fma(-s[a], lc, s[c2]);
+                }
+            }
+            double x[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) x[cc] = (cc == b) ? 1.0 : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+#pragma unroll
+                for (int p = 0; p < cc; ++p) x[cc] = fma(-x[p], __shfl_sync(full, s[p], cc), x[cc]);
+                x[cc] *= rs[cc];
+            }
+            if (lane < 8) {
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc)
+                    if (cc >= lane && 8 * tp + cc < n) A[(8 * tp + cc) * ld + 8 * tp + lane] = x[cc];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) if (cc == lane && 8 * tp + cc < n) invd[8 * tp + cc] = rs[cc];
             }
         }
         __syncthreads();
+        CH_TICK(2)
         SDP_WARP_CALL(chol_update_tiles, pan, tp, lane, acc)
         __syncthreads();
+        CH_TICK(3)
     }
 }
 
-// x = (L L^T)^-1 b by one warp: lane l keeps elements l, l + 32, ... in registers; the pivot element travels by shuffle.
+// x = (L L^T)^-1 b by one warp, blocked by 8: lane l keeps elements l, l + 32, ... in registers.  A holds L below the
+// 8 x 8 diagonal blocks and the INVERSE of each diagonal block in its place (chol_factor_smem), so a block step is a
+// small dense product (every lane forms the 8 block unknowns redundantly from shuffled values and broadcast loads)
+// followed by an independent 8-term update of each remaining element -- no per-column dependency chain.
 constexpr int SDP_SOLVE_T = (SDP_MAXC + 31) / 32;      // 5 register slots per lane
-__device__ inline void chol_solve_warp(const double* A, int n, int ld, const double* invd, const double* b, double* x, int lane) {
+constexpr int SDP_SOLVE_NB = (SDP_MAXC + 7) / 8;       // 20 blocks
+__device__ inline void chol_solve_warp(const double* A, int n, int ld, const double* b, double* x, int lane) {
+    const unsigned full = 0xffffffffu;
     double z[SDP_SOLVE_T];
 #pragma unroll
     for (int t = 0; t < SDP_SOLVE_T; ++t) { const int i = lane + 32 * t; z[t] = (i < n) ? b[i] : 0.0; }
     // forward: L z = b
 #pragma unroll
-    for (int tk = 0; tk < SDP_SOLVE_T; ++tk) {
-        for (int kk = 0; kk < 32; ++kk) {
-            const int k = 32 * tk + kk;
-            if (k >= n) break;
-            const double zk = __shfl_sync(0xffffffffu, z[tk] * invd[k], kk);
-            if (lane == kk) z[tk] = zk;
+    for (int t0 = 0; t0 < SDP_SOLVE_T; ++t0)
+#pragma unroll 1
+    for (int q4 = 0; q4 < 4; ++q4) {
+        const int base = 32 * t0 + 8 * q4, lane0 = 8 * q4;
+        if (base < n) {
+            double bv[8], xv[8];
 #pragma unroll
-            for (int t = tk; t < SDP_SOLVE_T; ++t) {
+            for (int c = 0; c < 8; ++c) bv[c] = __shfl_sync(full, z[t0], lane0 + c);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = 0; c <= r; ++c) if (base + r < n) acc = fma(A[(base + r) * ld + base + c], bv[c], acc);
+                xv[r] = acc;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (lane == lane0 + r) z[t0] = xv[r];
+#pragma unroll
+            for (int t = t0; t < SDP_SOLVE_T; ++t) {
                 const int i = lane + 32 * t;
-                if (i > k && i < n) z[t] = fma(-A[i * ld + k], zk, z[t]);
+                if (i >= base + 8 && i < n) {
+                    const double* Ai = A + i * ld + base;
+                    double acc = z[t];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) acc = fma(-Ai[c], xv[c], acc);
+                    z[t] = acc;
+                }
             }
         }
     }
     // backward: L^T x = z
 #pragma unroll
-    for (int tk = SDP_SOLVE_T - 1; tk >= 0; --tk) {
-        for (int kk = 31; kk >= 0; --kk) {
-            const int k = 32 * tk + kk;
-            if (k >= n) continue;
-            const double xk = __shfl_sync(0xffffffffu, z[tk] * invd[k], kk);
-            if (lane == kk) z[tk] = xk;
+    for (int t0 = SDP_SOLVE_T - 1; t0 >= 0; --t0)
+#pragma unroll 1
+    for (int q4 = 3; q4 >= 0; --q4) {
+        const int base = 32 * t0 + 8 * q4, lane0 = 8 * q4;
+        if (base < n) {
+            double bv[8], xv[8];
 #pragma unroll
-            for (int t = 0; t <= tk; ++t) {
+            for (int c = 0; c < 8; ++c) bv[c] = __shfl_sync(full, z[t0], lane0 + c);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                double acc = 0.0;
+#pragma unroll
+                for (int c = r; c < 8; ++c) if (base + c < n) acc = fma(A[(base + c) * ld + base + r], bv[c], acc);   // (L_dd^-1)^T
+                xv[r] = acc;
+            }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) if (lane == lane0 + r) z[t0] = xv[r];
+#pragma unroll
+            for (int t = 0; t <= t0; ++t) {
                 const int i = lane + 32 * t;
-                if (i < k) z[t] = fma(-A[k * ld + i], xk, z[t]);
+                if (i < base) {
+                    double acc = z[t];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) if (base + c < n) acc = fma(-A[(base + c) * ld + i], xv[c], acc);
+                    z[t] = acc;
+                }
             }
         }
     }
@@ -582,7 +680,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     //   inner: Newton on L_sigma restricted to at^T y = total_mass, generalized Hessian Hs + sigma A^T D A with
     //          D in the Clarke Jacobian of Proj_K (from the 4x4 eigen-decompositions);  outer: lam <- Proj_K(lam - sigma g(y)).
 #ifdef SYSID_PHASE_CLOCKS
-    long long ck[6] = {0, 0, 0, 0, 0, 0}, ck0 = clock64();
+    long long ck[6] = {0, 0, 0, 0, 0, 0}, ck0 = clock64(), chk[4] = {0, 0, 0, 0};
 #define SDP_TICK(k) { const long long now_ = clock64(); ck[k] += now_ - ck0; ck0 = now_; }
 #else
 #define SDP_TICK(k)
@@ -595,6 +693,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
 
     // evaluate at the point yy: gy = A yy + c0, w = lam - sigma gy, eigen-decompose the LMI blocks of w, pw = Proj_K(w).
     // Returns |pw|^2 (block-uniform).
+    bool warm = false;            // eigenvector warm start: off for the first evaluation of every outer iteration (bounds drift)
     auto evaluate = [&](const double* yy) -> double {
         for (int r = tid; r < m; r += SDP_THREADS) { const double gv = apply_A(yy, r); gy[r] = gv; wv[r] = lam[r] - sigma * gv; }
         __syncthreads();
@@ -603,7 +702,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             if (lane < 2 && k < 2 * L) {
                 const int off = (k >> 1) * SDP_ROWS_PER_LINK + 10 * (k & 1);
                 double ev[4], V[16];
-                eig_sym4(wv + off, ev, V);
+                eig_sym4(wv + off, ev, V, warm ? evecs + 16 * k : nullptr);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) evals[4 * k + e] = ev[e];
 #pragma unroll
@@ -696,7 +795,11 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             if (wv[L * SDP_ROWS_PER_LINK + k] > 0.0) W[(np + k) * ldw + np + k] += sigma;
         __syncthreads();
         SDP_TICK(5)
+#ifdef SYSID_PHASE_CLOCKS
+        chol_factor_smem(W, c, ldw, invd, pan, tid, chk);
+#else
         chol_factor_smem(W, c, ldw, invd, pan, tid);
+#endif
     };
 
     auto dot_c = [&](const double* u, const double* v) -> double {
@@ -723,6 +826,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     int iters = 0, refacts = 0, status = SYSID_ERR_NOT_OPTIMAL;
     double rp = 1.0, rd = 1.0, kkt_prev = 1.0;
     double pw2 = evaluate(y);
+    warm = true;
     for (int outer = 0; outer < 200 && iters < prm.max_iters; ++outer) {
         const double tol_in = fmax(0.5 * eps * (1.0 + gnorm), 1e-2 * fmin(1.0, kkt_prev));
         for (int inner = 0; inner < 40 && iters < prm.max_iters; ++inner) {
@@ -737,8 +841,8 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             SDP_TICK(0)
             newton_matrix_factor();
             SDP_TICK(1)
-            if (warp == 0) chol_solve_warp(W, c, ldw, invd, grad, yt, lane);        // yt = K^-1 grad
-            else if (warp == 1) chol_solve_warp(W, c, ldw, invd, at, Ka, lane);     // Ka = K^-1 at
+            if (warp == 0) chol_solve_warp(W, c, ldw, grad, yt, lane);        // yt = K^-1 grad
+            else if (warp == 1) chol_solve_warp(W, c, ldw, at, Ka, lane);     // Ka = K^-1 at
             __syncthreads();
             SDP_TICK(2)
             const double a_v1 = dot_c(at, yt), a_Ka = dot_c(at, Ka);
@@ -789,9 +893,12 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         if (rp <= eps * (1.0 + gyn) && rd <= eps * (1.0 + gnorm)) { status = SYSID_OK; break; }
         if (rp > 0.25 * kkt_prev) sigma = fmin(sigma * 10.0, 1e6);
         kkt_prev = rp;
+        warm = false;                 // cold start once per outer iteration: rounding drift of the accumulated rotations stays bounded
         pw2 = evaluate(y);
+        warm = true;
     }
 #ifdef SYSID_PHASE_CLOCKS
+    if (tid == 0 && prob == 0) printf("chol clocks: load %lld  publish %lld  panel %lld  update %lld\n", chk[0], chk[1], chk[2], chk[3]);
     if (tid == 0 && prob == 0) printf("sdp clocks: grad %lld  chol %lld  solve %lld  Hs.dy %lld  linesearch %lld  K-setup %lld  (newton %d)\n", ck[0], ck[1], ck[2], ck[3], ck[4], ck[5], iters);
 #endif
     if (status != SYSID_OK && rp <= 1e3 * eps * (1.0 + gnorm) && rd <= 1e3 * eps * (1.0 + gnorm)) status = SDP_STATUS_INACCURATE;
