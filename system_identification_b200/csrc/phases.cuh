@@ -670,12 +670,13 @@ __device__ __forceinline__ void phase_fill_chains(const DevModel& M, const doubl
                     }
                 continue;
             }
-            double d[6];
+            double d[6];           // (dl; da), pre-multiplied by sqrt(weight)
 #pragma unroll
-            for (int k = 0; k < 6; ++k) d[k] = Pe(k);
+            for (int k = 0; k < 6; ++k) d[k] = Pe(k) * wsq;
+            const int rowbase = r * (r + 1) / 2;
             for (int e = 0, turn = 0; e < len; ++e, turn = (turn + 1 == split) ? 0 : turn + 1) {
-                const int j = M.fch[ch][e];
-                const double pj = Pe(4 + j);
+                const int jp = M.fchp[ch][e], j = jp & 0xff, cc = 4 + j;
+                const double pj = P[(cc <= r) ? rowbase + cc : (jp >> 8) + r] * wsq;
                 const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { const double2 ak = A2[k]; d[2 * k] = fma(pj, ak.x, d[2 * k]); d[2 * k + 1] = fma(pj, ak.y, d[2 * k + 1]); }
@@ -687,7 +688,7 @@ __device__ __forceinline__ void phase_fill_chains(const DevModel& M, const doubl
                     // (el; ea) = (R^T u; R^T da), R row-major in x01..x8p
                     const double el0 = x01.x * u0 + x23.y * u1 + x67.x * u2, el1 = x01.y * u0 + x45.x * u1 + x67.y * u2, el2 = x23.x * u0 + x45.y * u1 + x8p.x * u2;
                     const double ea0 = x01.x * d[3] + x23.y * d[4] + x67.x * d[5], ea1 = x01.y * d[3] + x45.x * d[4] + x67.y * d[5], ea2 = x23.x * d[3] + x45.y * d[4] + x8p.x * d[5];
-                    body_row(c + CX_B9 + B9S * (j - 1), el0 * wsq, el1 * wsq, el2 * wsq, ea0 * wsq, ea1 * wsq, ea2 * wsq, row + 10 * (j - 1));
+                    body_row(c + CX_B9 + B9S * (j - 1), el0, el1, el2, ea0, ea1, ea2, row + 10 * (j - 1));
                 }
             }
         } else {
