@@ -19,6 +19,8 @@
  *                             Y_proj/B_v/B_c through the per-sample API and hand them to Solver(...)  src/solver.py:6-29
  *   sysid_sdp_solve           Solver.solve_fully_consistent: cvxpy problem + problem.solve(solver=cp.MOSEK)
  *                             reference src/solver.py:123-210
+ *   sysid_filtfilt / sysid_savgol  the scipy.signal.filtfilt / savgol_filter calls of read_data
+ *                             reference demo/solo_identification.py:15-32 (the step immediately before the path)
  *   sysid_predict_rmse        SystemIdentification.print_tau_prediction_rmse   reference src/sys_identification.py:421-437
  *
  * Conventions
@@ -132,6 +134,21 @@ int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, c
 int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,
                           void* workspace, size_t workspace_bytes, void* stream);
 size_t sysid_gram_from_stack_workspace_bytes(int32_t c);
+
+/* Pre-processing of read_data (reference demo/solo_identification.py:15-32), channel-major device arrays (channels x N, ld).
+ * sysid_filtfilt = scipy.signal.filtfilt(b, a, x, axis=1) with its defaults (padtype 'odd', padlen 3 max(nb, na),
+ * method 'pad'); b_host / a_host are HOST coefficient arrays (at most 9 each).  y may alias x.  pad_float32 != 0: the
+ * values came from a float32 log (np.loadtxt(dtype=np.float32), demo/solo_identification.py:10-14): scipy then forms
+ * the odd extension in float32, and so does this call (the pad samples are rounded to float32); bit-identical pads.
+ * sysid_savgol = scipy.signal.savgol_filter(x, window_length, polyorder) with its defaults (deriv 0, mode 'interp');
+ * y must not alias x. */
+size_t sysid_filtfilt_workspace_bytes(int32_t channels, int64_t N, int32_t ncoef /* max(nb, na) */);
+int sysid_filtfilt(const double* b_host, int32_t nb, const double* a_host, int32_t na, const double* x, double* y,
+                   int32_t channels, int64_t N, int64_t ld, int32_t pad_float32, void* workspace, size_t workspace_bytes,
+                   void* stream);
+size_t sysid_savgol_workspace_bytes(int32_t window_length);
+int sysid_savgol(int32_t window_length, int32_t polyorder, const double* x, double* y, int32_t channels, int64_t N,
+                 int64_t ld, void* workspace, size_t workspace_bytes, void* stream);
 
 /* LMI-constrained fit (reference src/solver.py:123-210).  All pointers in the desc are HOST pointers. */
 enum { SYSID_REG_CONSTANT_PULLBACK = 0, SYSID_REG_EUCLIDEAN = 1 };

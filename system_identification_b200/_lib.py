@@ -70,6 +70,10 @@ _SIGNATURES = {
     "sysid_gram_accumulate_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
     "sysid_gram_from_stack": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P]),
     "sysid_gram_from_stack_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "sysid_filtfilt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),
+    "sysid_filtfilt": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_size_t, _P]),
+    "sysid_savgol_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "sysid_savgol": (C.c_int, [C.c_int32, C.c_int32, _P, _P, C.c_int32, C.c_int64, C.c_int64, _P, C.c_size_t, _P]),
     "sysid_sdp_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sysid_sdp_solve": (C.c_int, [C.POINTER(SdpDesc), _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "sysid_predict_rmse": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),

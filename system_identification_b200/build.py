@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsysid_b200.so")
 SOURCES = ["sysid_api.cu"]
-DEPS = ["sysid_api.cu", "gram_kernels.cuh", "kinematics.cuh", "phases.cuh", "model.cuh", "sdp_kernels.cuh", "gram_tiles.inc",
+DEPS = ["sysid_api.cu", "gram_kernels.cuh", "kinematics.cuh", "phases.cuh", "model.cuh", "sdp_kernels.cuh", "filter_kernels.cuh", "gram_tiles.inc",
         os.path.join("..", "..", "include", "sysid_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "550"]

@@ -1,0 +1,141 @@
+// Pre-processing step immediately before the hot path: the reference's read_data filters the
+// logged joint velocities / accelerations / torques along the time axis with scipy
+// (reference demo/solo_identification.py:15-32):
+//     signal.filtfilt(b, a, x, axis=1)           zero-phase IIR, padtype 'odd', padlen 3 max(len a, len b), method 'pad'
+//     savgol_filter(x, window_length, polyorder)  deriv 0, mode 'interp'
+// Both are restated here for channel-major device arrays (channels x N, leading dimension ld), fp64.
+//
+// filtfilt: scipy's lfilter is the direct-form-II-transposed recursion, sequential in time.  It is parallelised over
+// (channel, chunk of FILT_CHUNK samples) in three kernels per direction:
+//   A  every chunk runs the recursion from a ZERO state and keeps only its final state f_k
+//   S  one thread per channel chains the chunks:  s_{k+1} = Phi^FILT_CHUNK s_k + f_k,  s_0 = zi * x_ext[0]
+//      (Phi = the recursion's zero-input state transition; its power is formed on the host)
+//   B  every chunk re-runs the recursion from its true initial state s_k and writes the outputs
+// Inside a chunk the arithmetic is exactly lfilter's; only the chunk-initial states carry ~1e-16 relative rounding of
+// their own.  The odd extension is generated on the fly; the backward direction reads the forward result reversed and
+// writes its output reversed and cropped.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace sysid {
+
+constexpr int FILT_MAXS = 8;          // state dimension = max(len a, len b) - 1 (coefficients zero-padded: same arithmetic)
+constexpr int FILT_CHUNK = 256;
+
+struct FiltCoef {
+    double b[FILT_MAXS + 1];
+    double a[FILT_MAXS + 1];          // a[0] == 1 (normalised on the host)
+    double zi[FILT_MAXS];
+    double phiL[FILT_MAXS][FILT_MAXS];   // Phi^FILT_CHUNK
+};
+
+struct FiltArgs {
+    const double* x;        // forward: the signal (channels x N, ld);  backward: the forward result (channels x Next, ld = Next)
+    double* y;              // forward: channels x Next (ld = Next);     backward: the final output (channels x N, ld)
+    double* fstate;         // [channels][nchunks][FILT_MAXS] chunk-final states from zero state
+    double* sstate;         // [channels][nchunks][FILT_MAXS] true chunk-initial states
+    long long N, ld, Next;
+    int channels, padlen, nchunks, backward;
+    int pad_float32;        // the log was float32 (np.loadtxt(dtype=float32), reference quirk Q8): scipy then forms the odd
+                            // extension in float32 before lfilter widens it -- reproduce that rounding of the pad samples
+};
+
+// sample i (0 <= i < Next) of the stream this direction filters
+__device__ __forceinline__ double filt_input(const FiltArgs& g, int ch, long long i) {
+    if (g.backward) return g.x[(size_t)ch * g.Next + (g.Next - 1 - i)];
+    const double* x = g.x + (size_t)ch * g.ld;
+    const long long j = i - g.padlen;
+    if (j >= 0 && j < g.N) return x[j];
+    const double e = (j < 0) ? 2.0 * x[0] - x[-j]                   // odd extension, left:  2 x[0] - x[padlen - i]
+                             : 2.0 * x[g.N - 1] - x[2 * (g.N - 1) - j];   // right: 2 x[N-1] - x[N-2-(j-N)]
+    return g.pad_float32 ? (double)__double2float_rn(e) : e;
+}
+
+__device__ __forceinline__ double df2t_step(const FiltCoef& c, double z[FILT_MAXS], double xv) {
+    const double yv = c.b[0] * xv + z[0];
+#pragma unroll
+    for (int k = 0; k < FILT_MAXS - 1; ++k) z[k] = c.b[k + 1] * xv + z[k + 1] - c.a[k + 1] * yv;
+    z[FILT_MAXS - 1] = c.b[FILT_MAXS] * xv - c.a[FILT_MAXS] * yv;
+    return yv;
+}
+
+// MODE 0 = kernel A (zero state -> final state), MODE 1 = kernel B (true state -> outputs)
+template <int MODE>
+__global__ void __launch_bounds__(128) filt_chunk_kernel(const __grid_constant__ FiltCoef c, const FiltArgs g) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)g.channels * g.nchunks) return;
+    const int ch = (int)(t / g.nchunks), k = (int)(t - (long long)ch * g.nchunks);
+    double z[FILT_MAXS];
+    double* st = ((MODE == 0) ? g.fstate : g.sstate) + ((size_t)ch * g.nchunks + k) * FILT_MAXS;
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) z[e] = (MODE == 0) ? 0.0 : st[e];
+    const long long i0 = (long long)k * FILT_CHUNK;
+    const long long i1 = (i0 + FILT_CHUNK < g.Next) ? i0 + FILT_CHUNK : g.Next;
+    for (long long i = i0; i < i1; ++i) {
+        const double yv = df2t_step(c, z, filt_input(g, ch, i));
+        if (MODE == 1) {
+            if (!g.backward) g.y[(size_t)ch * g.Next + i] = yv;
+            else {
+                const long long j = g.Next - 1 - i - g.padlen;        // un-reverse and crop the extension
+                if (j >= 0 && j < g.N) g.y[(size_t)ch * g.ld + j] = yv;
+            }
+        }
+    }
+    if (MODE == 0) {
+#pragma unroll
+        for (int e = 0; e < FILT_MAXS; ++e) st[e] = z[e];
+    }
+}
+
+__global__ void filt_scan_kernel(const __grid_constant__ FiltCoef c, const FiltArgs g) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= g.channels) return;
+    double s[FILT_MAXS];
+    const double x0 = filt_input(g, ch, 0);
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) s[e] = c.zi[e] * x0;
+    for (int k = 0; k < g.nchunks; ++k) {
+        double* ss = g.sstate + ((size_t)ch * g.nchunks + k) * FILT_MAXS;
+        const double* fs = g.fstate + ((size_t)ch * g.nchunks + k) * FILT_MAXS;
+        double nx[FILT_MAXS];
+#pragma unroll
+        for (int e = 0; e < FILT_MAXS; ++e) { ss[e] = s[e]; nx[e] = fs[e]; }
+#pragma unroll
+        for (int e = 0; e < FILT_MAXS; ++e)
+#pragma unroll
+            for (int f = 0; f < FILT_MAXS; ++f) nx[e] = fma(c.phiL[e][f], s[f], nx[e]);
+#pragma unroll
+        for (int e = 0; e < FILT_MAXS; ++e) s[e] = nx[e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- Savitzky-Golay
+constexpr int SG_MAXW = 63;            // window_length limit (odd)
+struct SavgolArgs {
+    const double* x; double* y;
+    const double* coef;                // [W] interior FIR taps, then [half][W] left-edge rows, then [half][W] right-edge rows
+    long long N, ld;
+    int channels, W;
+};
+
+__global__ void __launch_bounds__(256) savgol_kernel(const SavgolArgs g) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)g.channels * g.N) return;
+    const int ch = (int)(t / g.N);
+    const long long i = t - (long long)ch * g.N;
+    const double* x = g.x + (size_t)ch * g.ld;
+    const int W = g.W, half = W / 2;
+    double s = 0.0;
+    if (i < half) {                                   // polynomial fitted to the first W samples, evaluated at i
+        const double* row = g.coef + W + (size_t)i * W;
+        for (int k = 0; k < W; ++k) s = fma(row[k], x[k], s);
+    } else if (i >= g.N - half) {                     // ... to the last W samples
+        const double* row = g.coef + W + (size_t)half * W + (size_t)(i - (g.N - half)) * W;
+        for (int k = 0; k < W; ++k) s = fma(row[k], x[g.N - W + k], s);
+    } else {
+        for (int k = 0; k < W; ++k) s = fma(g.coef[k], x[i - half + k], s);
+    }
+    g.y[(size_t)ch * g.ld + i] = s;
+}
+
+}  // namespace sysid

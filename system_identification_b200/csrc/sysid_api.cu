@@ -5,12 +5,14 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include <cuda_runtime.h>
 
 #include "../../include/sysid_b200.h"
 #include "gram_kernels.cuh"
 #include "sdp_kernels.cuh"
+#include "filter_kernels.cuh"
 
 using namespace sysid;
 
@@ -378,6 +380,138 @@ int sysid_predict_rmse(const sysid_model* model, const double* q, const double* 
     rmse_kernel<<<grid, GRAM_THREADS, RMSE_SMEM_BYTES, st>>>(model->dev, a);
     CUDA_TRY(cudaGetLastError());
     rmse_finalize_kernel<<<1, 32, 0, st>>>((const double*)workspace, grid, model->dev.nd, N, out);
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ pre-processing filters
+size_t sysid_filtfilt_workspace_bytes(int32_t channels, int64_t N, int32_t ncoef) {
+    if (channels <= 0 || N <= 0 || ncoef < 1) return 0;
+    const int64_t next = N + 2 * 3 * (int64_t)ncoef;
+    const int64_t nchunks = (next + FILT_CHUNK - 1) / FILT_CHUNK;
+    return sizeof(double) * ((size_t)channels * (size_t)next + 2 * (size_t)channels * (size_t)nchunks * FILT_MAXS) + 256;
+}
+
+int sysid_filtfilt(const double* b_host, int32_t nb, const double* a_host, int32_t na, const double* x, double* y,
+                   int32_t channels, int64_t N, int64_t ld, int32_t pad_float32, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+    if (!b_host || !a_host || !x || !y || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (nb < 1 || na < 1 || nb > FILT_MAXS + 1 || na > FILT_MAXS + 1) return fail(SYSID_ERR_UNSUPPORTED, "filter longer than %d coefficients", FILT_MAXS + 1);
+    if (a_host[0] == 0.0) return fail(SYSID_ERR_INVALID, "a[0] must be non-zero");
+    if (channels < 0 || N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad channels/N/ld");
+    const int ntaps = nb > na ? nb : na, padlen = 3 * ntaps;
+    if (N <= padlen) return fail(SYSID_ERR_INVALID, "The length of the input vector x must be greater than padlen, which is %d.", padlen);
+    if (channels == 0) return SYSID_OK;
+    if (workspace_bytes < sysid_filtfilt_workspace_bytes(channels, N, ntaps)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+    FiltCoef c;
+    std::memset(&c, 0, sizeof(c));
+    for (int k = 0; k < nb; ++k) c.b[k] = b_host[k] / a_host[0];
+    for (int k = 0; k < na; ++k) c.a[k] = a_host[k] / a_host[0];
+    const int n = ntaps - 1;
+    // steady state of the step response (scipy.signal.lfilter_zi): (I - companion(a)^T) zi = b[1:] - a[1:] b[0], solved in closed form
+    if (n > 0) {
+        double bsum = 0.0, colsum = 1.0;
+        for (int k = 1; k <= n; ++k) { bsum += c.b[k] - c.a[k] * c.b[0]; colsum += c.a[k]; }
+        c.zi[0] = bsum / colsum;
+        double asum = 1.0, csum = 0.0;
+        for (int k = 1; k < n; ++k) {
+            asum += c.a[k];
+            csum += c.b[k] - c.a[k] * c.b[0];
+            c.zi[k] = asum * c.zi[0] - csum;
+        }
+    }
+    {   // Phi^FILT_CHUNK by repeated squaring in extended precision (FILT_CHUNK is a power of two)
+        static_assert((FILT_CHUNK & (FILT_CHUNK - 1)) == 0, "power of two");
+        long double P[FILT_MAXS][FILT_MAXS] = {}, Q[FILT_MAXS][FILT_MAXS];
+        for (int k = 0; k < FILT_MAXS; ++k) { P[k][0] = -(long double)c.a[k + 1]; if (k + 1 < FILT_MAXS) P[k][k + 1] = 1.0L; }
+        for (int sq = 1; sq < FILT_CHUNK; sq <<= 1) {
+            for (int i = 0; i < FILT_MAXS; ++i) for (int j = 0; j < FILT_MAXS; ++j) { long double t = 0; for (int k = 0; k < FILT_MAXS; ++k) t += P[i][k] * P[k][j]; Q[i][j] = t; }
+            std::memcpy(P, Q, sizeof(P));
+        }
+        for (int i = 0; i < FILT_MAXS; ++i) for (int j = 0; j < FILT_MAXS; ++j) c.phiL[i][j] = (double)P[i][j];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    FiltArgs g{};
+    g.N = N; g.ld = ld; g.Next = N + 2 * (long long)padlen; g.channels = channels; g.padlen = padlen;
+    g.pad_float32 = pad_float32 ? 1 : 0;
+    g.nchunks = (int)((g.Next + FILT_CHUNK - 1) / FILT_CHUNK);
+    double* Y1 = (double*)workspace;
+    g.fstate = Y1 + (size_t)channels * g.Next;
+    g.sstate = g.fstate + (size_t)channels * g.nchunks * FILT_MAXS;
+    const long long items = (long long)channels * g.nchunks;
+    const unsigned grid = (unsigned)((items + 127) / 128);
+    for (int dir = 0; dir < 2; ++dir) {
+        g.backward = dir;
+        g.x = dir ? Y1 : x;
+        g.y = dir ? y : Y1;
+        filt_chunk_kernel<0><<<grid, 128, 0, st>>>(c, g);
+        filt_scan_kernel<<<(channels + 63) / 64, 64, 0, st>>>(c, g);
+        filt_chunk_kernel<1><<<grid, 128, 0, st>>>(c, g);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SYSID_OK;
+}
+
+namespace {
+// rows of E = V_eval pinv(V_fit) for a degree-p polynomial fitted to W equally spaced samples: row t gives the fitted
+// value at window position pos[t] as a linear combination of the W samples.  Abscissae are centred and scaled to
+// [-1, 1] (the fitted polynomial does not depend on the parametrisation); QR by modified Gram-Schmidt, twice, in
+// extended precision.
+void polyfit_rows(int W, int p, const int* pos, int npos, double* rows /* npos x W */) {
+    const int m = p + 1, half = W / 2;
+    std::vector<long double> Q((size_t)W * m), R((size_t)m * m, 0.0L);
+    for (int j = 0; j < W; ++j) { long double u = (long double)(j - half) / (long double)(half > 0 ? half : 1), pw = 1.0L; for (int k = 0; k < m; ++k) { Q[(size_t)j * m + k] = pw; pw *= u; } }
+    for (int k = 0; k < m; ++k) {
+        for (int pass = 0; pass < 2; ++pass)
+            for (int i = 0; i < k; ++i) {
+                long double d = 0; for (int j = 0; j < W; ++j) d += Q[(size_t)j * m + i] * Q[(size_t)j * m + k];
+                for (int j = 0; j < W; ++j) Q[(size_t)j * m + k] -= d * Q[(size_t)j * m + i];
+                R[(size_t)i * m + k] += d;
+            }
+        long double nr = 0; for (int j = 0; j < W; ++j) nr += Q[(size_t)j * m + k] * Q[(size_t)j * m + k];
+        nr = sqrtl(nr);
+        R[(size_t)k * m + k] = nr;
+        for (int j = 0; j < W; ++j) Q[(size_t)j * m + k] /= nr;
+    }
+    for (int t = 0; t < npos; ++t) {
+        // w solves R^T w = v(pos[t]);  row = Q w
+        long double v[32], w[32];
+        long double u = (long double)(pos[t] - half) / (long double)(half > 0 ? half : 1), pw = 1.0L;
+        for (int k = 0; k < m; ++k) { v[k] = pw; pw *= u; }
+        for (int k = 0; k < m; ++k) { long double sres = v[k]; for (int i = 0; i < k; ++i) sres -= R[(size_t)i * m + k] * w[i]; w[k] = sres / R[(size_t)k * m + k]; }
+        for (int j = 0; j < W; ++j) { long double sres = 0; for (int k = 0; k < m; ++k) sres += Q[(size_t)j * m + k] * w[k]; rows[(size_t)t * W + j] = (double)sres; }
+    }
+}
+}  // namespace
+
+size_t sysid_savgol_workspace_bytes(int32_t window_length) {
+    if (window_length < 1) return 0;
+    return sizeof(double) * (size_t)window_length * (size_t)(window_length + 1) + 256;
+}
+
+int sysid_savgol(int32_t window_length, int32_t polyorder, const double* x, double* y, int32_t channels, int64_t N,
+                 int64_t ld, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!x || !y || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (x == y) return fail(SYSID_ERR_INVALID, "savgol cannot run in place");
+    if (window_length < 1 || window_length % 2 == 0 || window_length > SG_MAXW) return fail(SYSID_ERR_UNSUPPORTED, "window_length must be odd and <= %d", SG_MAXW);
+    if (polyorder < 0 || polyorder >= window_length || polyorder > 15) return fail(SYSID_ERR_INVALID, "polyorder must be less than window_length.");
+    if (channels < 0 || N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad channels/N/ld");
+    if (N < window_length) return fail(SYSID_ERR_INVALID, "If mode is 'interp', window_length must be less than or equal to the size of x.");
+    if (channels == 0 || N == 0) return SYSID_OK;
+    if (workspace_bytes < sysid_savgol_workspace_bytes(window_length)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+    const int W = window_length, half = W / 2;
+    std::vector<double> coef((size_t)W * (W + 1), 0.0);
+    std::vector<int> pos;
+    pos.push_back(half);                                          // interior taps: the fit evaluated at the window centre
+    for (int i = 0; i < half; ++i) pos.push_back(i);              // left edge rows
+    for (int i = 0; i < half; ++i) pos.push_back(W - half + i);   // right edge rows
+    polyfit_rows(W, polyorder, pos.data(), (int)pos.size(), coef.data());
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaMemcpyAsync(workspace, coef.data(), sizeof(double) * (size_t)W * (2 * half + 1), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));     // coef dies with this frame
+    SavgolArgs g{x, y, (const double*)workspace, N, ld, channels, W};
+    const long long items = (long long)channels * N;
+    savgol_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>(g);
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
 }

@@ -161,3 +161,19 @@ def test_print_inertial_params_matches_reference_table_format(capsys):
     assert "|Parameter    |A priori     |Identified   |Change       |error %      |" in out        # RUN_DEMO.md:12
     assert "|mass (kg)    |     1.680000|     1.696800|     0.016800|          1.0|" in out
     assert "|c_x (m)      |    -0.005374|" in out and "Robot total mass:" in out
+
+
+def test_butterworth_design_matches_scipy_and_fixture():
+    """butter_lowpass restates scipy.signal.butter(order, wn, 'low'): checked live against scipy (the reference's own
+    dependency, importable here) and against the coefficients stored in the scipy-generated fixture."""
+    from system_identification_b200.filters import butter_lowpass
+    g = np.load(os.path.join(H.GOLDEN_DIR, "filters_scipy.npz"))
+    b, a = butter_lowpass(5, 0.15)
+    assert np.abs(b - g["b"]).max() <= 1e-15 and np.abs(a - g["a"]).max() <= 1e-14
+    signal = pytest.importorskip("scipy.signal")
+    for order, wn in ((1, 0.9), (2, 0.3), (5, 0.15), (8, 0.05)):
+        b, a = butter_lowpass(order, wn)
+        bs, as_ = signal.butter(order, wn, btype="low", analog=False)
+        assert np.abs(b - bs).max() <= 1e-14 * np.abs(bs).max() and np.abs(a - as_).max() <= 1e-13 * np.abs(as_).max()
+    with pytest.raises(ValueError):
+        butter_lowpass(5, 1.5)

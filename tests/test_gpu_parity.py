@@ -291,3 +291,67 @@ def test_full_size_properties_20k():
     out = dm.predict_rmse(*dev, phi).cpu().numpy()
     # the rmse pass only sees joint rows; the Gram sees all 18: compare through a second Gram restricted check instead
     assert ssr > 0 and out[0] > 0 and out[0] * 20000 <= ssr * (1 + 1e-9)
+
+
+TOL_FILT = 1e-10       # relative to the max-abs of the scipy result (fp64 recursions / fits in a different summation order)
+
+
+def test_filters_vs_scipy_fixture_and_live():
+    """sysid_filtfilt / sysid_savgol == scipy.signal.filtfilt / savgol_filter as read_data calls them
+    (reference demo/solo_identification.py:15-32).  Checked against the scipy-generated fixture (always) and against scipy
+    itself on longer, multi-chunk signals (scipy is importable in this image); plus properties at full size."""
+    from system_identification_b200 import filters as F
+    g = np.load(os.path.join(H.GOLDEN_DIR, "filters_scipy.npz"))
+    b, a = F.butter_lowpass(5, 0.15)
+    up = lambda v: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64)).cuda()
+    for xk, yk in (("x", "filtfilt"), ("x_short", "filtfilt_short")):
+        y = F.filtfilt(b, a, up(g[xk]), float32_input=True).cpu().numpy()      # the fixture filters a float32 log, as the reference does
+        assert np.abs(y - g[yk]).max() <= TOL_FILT * np.abs(g[yk]).max()
+        y64 = F.filtfilt(b, a, up(g[xk])).cpu().numpy()                       # fp64 pads: differs only by the float32 rounding of the pads
+        assert 0 < np.abs(y64 - g[yk]).max() <= 1e-6 * np.abs(g[yk]).max()
+    for xk, yk in (("x", "savgol_f64"), ("x_w21", "savgol_w21")):
+        y = F.savgol_filter(up(g[xk]), 21, 5).cpu().numpy()
+        assert np.abs(y - g[yk]).max() <= TOL_FILT * np.abs(g[yk]).max()
+    # on a float32 log scipy runs savgol_filter IN float32 (and returns float32): the reference's own result carries that
+    # rounding; the fp64 device result agrees with it to float32 precision
+    assert g["savgol"].dtype == np.float32
+    y = F.savgol_filter(up(g["x"]), 21, 5).cpu().numpy()
+    assert np.abs(y - g["savgol"]).max() <= 3e-5 * np.abs(g["savgol"]).max()
+    assert _loaded_native()
+    # reference error behaviour
+    with pytest.raises(ValueError):
+        F.filtfilt(b, a, up(g["x"][:, :18]))                       # N <= padlen
+    with pytest.raises(ValueError):
+        F.savgol_filter(up(g["x"][:, :20]), 21, 5)                 # window longer than the signal
+    # in place, and a column slice of a wider array (leading dimension > N)
+    xd = up(g["x"])
+    wide = torch.cat([xd, xd], dim=1)
+    y = F.filtfilt(b, a, wide[:, :700], out=torch.empty_like(wide)[:, :700], float32_input=True).cpu().numpy()
+    assert np.abs(y - g["filtfilt"]).max() <= TOL_FILT * np.abs(g["filtfilt"]).max()
+    xi = xd.clone(); F.filtfilt(b, a, xi, out=xi, float32_input=True)
+    assert np.abs(xi.cpu().numpy() - g["filtfilt"]).max() <= TOL_FILT * np.abs(g["filtfilt"]).max()
+    # multi-chunk signals against scipy itself, other filter orders / windows
+    signal = pytest.importorskip("scipy.signal")
+    rng = np.random.default_rng(7)
+    x = (np.cumsum(rng.standard_normal((3, 20000)), axis=1) * 0.01 + rng.standard_normal((3, 20000))).astype(np.float32).astype(np.float64)
+    for order, wn in ((5, 0.15), (2, 0.3), (8, 0.1)):
+        bb, aa = F.butter_lowpass(order, wn)
+        ref = signal.filtfilt(bb, aa, x, axis=1)
+        y = F.filtfilt(bb, aa, up(x)).cpu().numpy()
+        assert np.abs(y - ref).max() <= TOL_FILT * np.abs(ref).max()
+    for W, p in ((21, 5), (5, 2), (51, 3)):
+        ref = signal.savgol_filter(x, W, p)
+        y = F.savgol_filter(up(x), W, p).cpu().numpy()
+        assert np.abs(y - ref).max() <= TOL_FILT * np.abs(ref).max()
+    # size-independent properties at 1 M samples: unit DC gain, linearity, time-reversal symmetry of the zero-phase filter
+    N = 1_000_000
+    xl = torch.randn((4, N), dtype=torch.float64, device="cuda")
+    const = torch.full((1, N), 3.25, dtype=torch.float64, device="cuda")
+    assert (F.filtfilt(b, a, const) - 3.25).abs().max().item() <= 1e-11
+    assert (F.savgol_filter(const, 21, 5) - 3.25).abs().max().item() <= 1e-12
+    y1, y2 = F.filtfilt(b, a, xl[:2]), F.filtfilt(b, a, xl[2:])
+    y12 = F.filtfilt(b, a, (2.0 * xl[:2] - 0.5 * xl[2:]).contiguous())
+    assert (y12 - (2.0 * y1 - 0.5 * y2)).abs().max().item() <= 1e-11
+    yr = F.filtfilt(b, a, torch.flip(xl[:2], dims=[1]).contiguous())
+    # forward-backward == backward-forward away from the edge transients (the two passes commute; only the padding differs)
+    assert (torch.flip(yr, dims=[1]) - y1)[:, 5000:-5000].abs().max().item() <= 1e-9
