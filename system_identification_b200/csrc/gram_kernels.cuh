@@ -33,7 +33,7 @@ constexpr int GRAM_WARPS = GRAM_THREADS / 32;
 #define SYSID_FTS 4
 #endif
 #ifndef SYSID_FSB
-#define SYSID_FSB 28
+#define SYSID_FSB 24
 #endif
 #ifndef SYSID_FILL_CHAINS
 #define SYSID_FILL_CHAINS 1
@@ -108,7 +108,7 @@ __device__ __forceinline__ void store_dispatch(int w, double* __restrict__ parti
 constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
 
 // All F phases of one super-batch, executed by a group of NT threads (index t) separated by SYNC().
-#define SYSID_F_PHASES(SB, NT, SYNC)                                                                                     \
+#define SYSID_F_PHASES(SB, NT, SYNC, LASTPHASE)                                                                                   \
     phase_stage<SB, NT>(M, args.io, base, args.N, inp, t);                                                               \
     SYNC();                                                                                                              \
     for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, ctx, scr, s_bad, it);              \
@@ -128,7 +128,18 @@ constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
     for (int it = t; it < SB * MAXV; it += NT) phase_wcols<SB>(M, base, args.N, ctx, scr, it);                           \
     SYNC();                                                                                                              \
     F_TICK(4)                                                                                                            \
+    LASTPHASE(SB, NT, SYNC)
+
+// last F phase: the packed projector (rmse kernel) or the orthonormal null-space basis (Gram kernel)
+#define SYSID_LAST_PROJ(SB, NT, SYNC)                                                                                    \
     phase_proj<SB, NT>(base, args.N, inp, ctx, scr, s_bad, t, s_stat);                                                   \
+    SYNC();
+#define SYSID_LAST_QBASIS(SB, NT, SYNC)                                                                                  \
+    for (int it = t; it < ((16 * SB + 31) & ~31); it += NT) phase_qbuild<SB>(base, args.N, ctx, scr, it);                \
+    phase_finish<SB>(base, args.N, inp, ctx, s_bad, t, s_stat);                                                          \
+    SYNC();                                                                                                              \
+    F_TICK(5)                                                                                                            \
+    for (int it = t; it < SB * NQMAX; it += NT) phase_qcols<SB>(base, args.N, ctx, scr, it);                             \
     SYNC();
 
 struct GramArgs {
@@ -163,7 +174,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
     const long long nsb = (args.N + FSB - 1) / FSB;
 #ifdef SYSID_PHASE_CLOCKS
-    long long clkF = 0, clkC = 0, clkM = 0, clk0, clkSub[5] = {0, 0, 0, 0, 0};
+    long long clkF = 0, clkC = 0, clkM = 0, clk0, clkSub[6] = {0, 0, 0, 0, 0, 0};
 #endif
     __syncthreads();
 #ifdef SYSID_PHASE_CLOCKS
@@ -174,7 +185,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #ifdef SYSID_ONLY_M      // diagnostic: F phases and fill only for the first super-batch, then the M phase on a static tile
         if (sb == blockIdx.x) {
 #endif
-        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads)
+        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_LAST_QBASIS)
 #ifdef SYSID_ONLY_M
         }
 #endif
@@ -186,14 +197,10 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #ifdef SYSID_ONLY_M
             if (sb == blockIdx.x && sub == 0)
 #endif
-#if SYSID_FILL_CHAINS
-            phase_fill_chains<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
-#else
-            phase_fill<FTS, TILE_LD, GRAM_THREADS, FILL_RPI>(M, ctx, tile, sub * FTS, args.friction, t);
-#endif
+            const int ksteps = phase_fill_q<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
             __syncthreads();
             PHASE_TICK(clkC)
-            mma_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, tile, FROWS / 4, lane, acc);
+            mma_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, tile, ksteps, lane, acc);
             __syncthreads();
             PHASE_TICK(clkM)
         }
@@ -206,7 +213,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         partial[GRAM_NTILES * 64 + 2] = s_stat[2];
 #ifdef SYSID_PHASE_CLOCKS
         partial[GRAM_NTILES * 64 + 3] = (double)clkF; partial[GRAM_NTILES * 64 + 4] = (double)clkC; partial[GRAM_NTILES * 64 + 5] = (double)clkM;
-        for (int k = 0; k < 5; ++k) partial[GRAM_NTILES * 64 + 6 + k] = (double)clkSub[k];
+        for (int k = 0; k < 6; ++k) partial[GRAM_NTILES * 64 + 6 + k] = (double)clkSub[k];
 #endif
     }
 }
@@ -383,13 +390,13 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
     if (tid < RSB) s_bad[tid] = 0;
     __shared__ double s_stat[3];
 #ifdef SYSID_PHASE_CLOCKS
-    long long clk0 = 0, clkSub[5] = {0, 0, 0, 0, 0};
+    long long clk0 = 0, clkSub[6] = {0, 0, 0, 0, 0, 0};
 #endif
     const long long nsb = (args.N + RSB - 1) / RSB;
     __syncthreads();
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * RSB;
-        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads)
+        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_LAST_PROJ)
         if (t < RSB) s_bad[t] = 0;
         const int nsub = (int)min((long long)(RSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
         for (int sub = 0; sub < nsub; ++sub) {

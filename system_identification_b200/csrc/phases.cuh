@@ -32,19 +32,22 @@ namespace sysid {
 
 // ---- per-sample context (doubles) ------------------------------------------------------------------------
 constexpr int NPACK = MAXV * (MAXV + 1) / 2;        // 171
-constexpr int CX_P = 0;                             // [171] packed lower triangle of P
-constexpr int CX_W = CX_P + NPACK;                  // sqrt(weight); 0 => sample contributes nothing
-constexpr int CX_A = CX_W + 1;                      // [MAXD][6] Pluecker axis (m; z) of every revolute joint
+constexpr int NQMAX = MAXV - 3;                     // a sample with a stance foot has at most 15 null-space directions
+constexpr int CX_Q = 0;                             // [NQMAX][MAXV] orthonormal basis of null(J_c), one vector per row (Gram kernel)
+constexpr int CX_P = CX_Q;                          // [171] packed lower triangle of P, same slot (rmse kernel)
+constexpr int CX_W = CX_Q + NQMAX * MAXV;           // sqrt(weight); 0 => sample contributes nothing
+constexpr int CX_NQ = CX_W + 1;                     // number of basis vectors (= rows of the sample's block); MAXV with no stance foot: Q = I, not stored
+constexpr int CX_A = CX_NQ + 1;                     // [MAXD][6] Pluecker axis (m; z) of every revolute joint
 constexpr int CX_X = CX_A + 6 * MAXD;               // [MAXD][12] R (9, row-major), p (3) relative to the base
 constexpr int B9S = 10;                             // body-motion record: omega, alpha, acc + 1 pad (16-byte loads)
 constexpr int CX_B9 = CX_X + 12 * MAXD;             // [MAXB][B9S] omega, alpha, acc (local frame)
 constexpr int CX_DQ = CX_B9 + B9S * MAXB;           // [MAXD]
 constexpr int CX_TAU = CX_DQ + MAXD;                // [MAXD]
-constexpr int CX_STRIDE = CX_TAU + MAXD + 4;        // 546 == 2 (mod 16): lanes of consecutive samples hit distinct banks
+constexpr int CX_STRIDE = CX_TAU + MAXD;            // 642 == 2 (mod 16): lanes of consecutive samples hit distinct banks
 // temporaries living in the P slot until `proj` overwrites it
 constexpr int CXT_S = CX_P;                         // [78] packed S, then L
 constexpr int CXT_JL = CX_P + 78;                   // [MAXEE][MAXCH][3] leg columns of J_c
-static_assert(78 + 3 * MAXEE * MAXCH <= NPACK, "temporaries fit the P slot");
+static_assert(78 + 3 * MAXEE * MAXCH <= NPACK && NPACK <= NQMAX * MAXV, "temporaries and the packed P fit the Q slot");
 static_assert(CX_STRIDE % 16 == 2 && CX_A % 2 == 0 && CX_X % 2 == 0 && CX_B9 % 2 == 0, "context layout keeps 16-byte alignment");
 
 // ---- per-sample scratch (doubles), only live inside the F phases -------------------------------------------
@@ -451,6 +454,109 @@ __device__ __forceinline__ void phase_wcols(const DevModel& M, long long base, l
     }
 }
 
+template <int SB>
+__device__ __forceinline__ void phase_finish(long long base, long long N, const double* __restrict__ inp, double* __restrict__ ctx,
+                                             const int* s_bad, int t, double* s_stat);
+
+// ---------------------------------------------------------------------------------------------- null-space basis
+// G = sum A^T A with A = P Ytilde and P = Q Q^T (Q: orthonormal basis of null(J_c), 18 x nq, nq = 18 - rank J_c), so
+// A^T A = (Q^T Ytilde)^T (Q^T Ytilde): the Gram kernel contracts nq rows per sample instead of 18 -- 12..15 with one or
+// two feet down, 6 with four.  W = L^-1 J_c has orthonormal rows (zero rows where a dependent contact row was dropped);
+// Householder reflectors H_0 .. H_{rank-1} map them onto e_0 .. e_{rank-1}, and Q = H_0 ... H_{rank-1} [e_rank .. e_17].
+// qbuild: lane per sample, reflector t overwrites W row t.   qcols: thread per (sample, basis vector).
+// Sixteen lanes per sample (two samples per warp); lane b holds the b-th LIVE row of W in registers (dropped rows are
+// exactly zero and are compacted away, so the pivot of step t sits in component t).  Step t: lane t turns its row into
+// the reflector and publishes it in shared memory (over W row t, which is no longer needed: every lane already holds
+// its row); lanes > t apply it to their rows.  `t` must cover whole warps: [0, 16 SB) rounded up to a multiple of 32.
+template <int SB>
+__device__ __forceinline__ void phase_qbuild(long long base, long long N, double* __restrict__ ctx, double* __restrict__ scr, int t) {
+    constexpr int MR = 3 * MAXEE;
+    static_assert(MR <= 16, "one half-warp per sample");
+    const unsigned full = 0xffffffffu;
+    const int s = t >> 4, b = t & 15, hshift = threadIdx.x & 16;
+    const bool live = (s < SB) && (base + s < N);
+    double* sc = scr + (live ? s : 0) * SC_STRIDE;
+    const int m3 = live ? (int)sc[SC_META] : 0;
+    // live rows of W (a dropped row is exactly zero: its first-foot base block cannot vanish otherwise)
+    bool rowlive = false;
+    if (b < m3) {
+        double n2 = 0.0;
+#pragma unroll
+        for (int r = 0; r < MAXV; ++r) { const double w = sc[SC_WM + b * MAXV + r]; n2 = fma(w, w, n2); }
+        rowlive = n2 != 0.0;
+    }
+    const unsigned mask16 = (__ballot_sync(full, rowlive) >> hshift) & 0xffffu;
+    const int rank = __popc(mask16);
+    // lane b takes the b-th live row
+    int src = -1;
+    {
+        unsigned m = mask16;
+        for (int k = 0; k < b; ++k) m &= m - 1;             // drop the b lowest set bits
+        if (m) src = __ffs(m) - 1;
+    }
+    double x[MAXV];
+#pragma unroll
+    for (int r = 0; r < MAXV; ++r) x[r] = (b < rank && src >= 0) ? sc[SC_WM + src * MAXV + r] : 0.0;
+    __syncwarp();                                            // every lane holds its row: W rows may now be overwritten
+#pragma unroll
+    for (int ts = 0; ts < MR; ++ts) {
+        if (__any_sync(full, ts < rank)) {
+            double* vrow = sc + SC_WM + ts * MAXV;
+            if (b == ts && ts < rank) {
+                double ta = 0.0, tb = 0.0, tc = 0.0;
+#pragma unroll
+                for (int r = ts; r < MAXV; ++r) { if (r % 3 == 0) ta = fma(x[r], x[r], ta); else if (r % 3 == 1) tb = fma(x[r], x[r], tb); else tc = fma(x[r], x[r], tc); }
+                const double tail2 = ta + tb + tc;
+                const double nt = tail2 * rsqrt(fmax(tail2, 1e-300));
+                const double alpha = (x[ts] >= 0.0) ? nt : -nt;
+                const double inv = rsqrt(2.0 * (tail2 + fabs(x[ts]) * nt));      // 1 / |x[ts:] + alpha e_ts|
+#pragma unroll
+                for (int r = 0; r < MAXV; ++r) vrow[r] = (r < ts) ? 0.0 : ((r == ts) ? (x[r] + alpha) * inv : x[r] * inv);
+            }
+            __syncwarp();
+            if (b > ts && b < rank) {
+                // the reflector is streamed from shared memory twice (dot, then update) instead of being held in registers
+                const double2* v2 = reinterpret_cast<const double2*>(vrow);
+                double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+                for (int r2 = ts / 2; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; d0 = fma(q.x, x[2 * r2], d0); d1 = fma(q.y, x[2 * r2 + 1], d1); }
+                const double d = -2.0 * (d0 + d1);
+#pragma unroll
+                for (int r2 = ts / 2; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; x[2 * r2] = fma(d, q.x, x[2 * r2]); x[2 * r2 + 1] = fma(d, q.y, x[2 * r2 + 1]); }
+            }
+        }
+    }
+    if (b == 0 && s < SB) {
+        if (live) sc[SC_META] = (double)rank;               // from here on: the number of reflectors
+        ctx[s * CX_STRIDE + CX_NQ] = live ? (double)(MAXV - rank) : 0.0;
+    }
+}
+
+template <int SB>
+__device__ __forceinline__ void phase_qcols(long long base, long long N, double* __restrict__ ctx, const double* __restrict__ scr, int t) {
+    if (t >= SB * NQMAX) return;
+    const int s = t / NQMAX, k = t - s * NQMAX;              // vector index fastest: a sample's lanes read the same reflector (broadcast)
+    if (base + s >= N) return;
+    const double* sc = scr + s * SC_STRIDE;
+    const int rank = (int)sc[SC_META];
+    if (rank == 0 || k >= MAXV - rank) return;               // no stance foot: Q = I is implicit
+    double x[MAXV];
+#pragma unroll
+    for (int r = 0; r < MAXV; ++r) x[r] = (r == rank + k) ? 1.0 : 0.0;
+    for (int p = rank - 1; p >= 0; --p) {                    // x <- H_p x, last reflector first (streamed twice: no register copy)
+        const double2* v2 = reinterpret_cast<const double2*>(sc + SC_WM + p * MAXV);
+        double d0 = 0.0, d1 = 0.0;
+#pragma unroll
+        for (int r2 = 0; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; d0 = fma(q.x, x[2 * r2], d0); d1 = fma(q.y, x[2 * r2 + 1], d1); }
+        const double d = -2.0 * (d0 + d1);
+#pragma unroll
+        for (int r2 = 0; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; x[2 * r2] = fma(d, q.x, x[2 * r2]); x[2 * r2 + 1] = fma(d, q.y, x[2 * r2 + 1]); }
+    }
+    double2* q2 = reinterpret_cast<double2*>(ctx + s * CX_STRIDE + CX_Q + k * MAXV);
+#pragma unroll
+    for (int r2 = 0; r2 < MAXV / 2; ++r2) q2[r2] = make_double2(x[2 * r2], x[2 * r2 + 1]);
+}
+
 // ---------------------------------------------------------------------------------------------- P = I - W^T W
 // Thread per (sample, row r): entries (r, 0..r) of the packed lower triangle, one independent accumulator per entry.
 // NT = threads in the group; also finalises the per-sample weight and the skip flags (first warp of the group).
@@ -479,8 +585,15 @@ __device__ __forceinline__ void phase_proj(long long base, long long N, const do
 #pragma unroll
         for (int cc = 0; cc < MAXV; ++cc) if (cc <= r) Pr[cc] = pv[cc];
     }
+    phase_finish<SB>(base, N, inp, ctx, s_bad, t, s_stat);
+}
+
+// Per-sample weight and skip flags (first warp of the group): deterministic (shuffle-tree) sums of the weights and counts.
+template <int SB>
+__device__ __forceinline__ void phase_finish(long long base, long long N, const double* __restrict__ inp, double* __restrict__ ctx,
+                                             const int* s_bad, int t, double* s_stat) {
     static_assert(SB <= 32, "the first warp of the group finalises the weights");
-    if (t < 32) {       // warp 0 of the group: deterministic (shuffle-tree) sums of the weights and the flag counts
+    if (t < 32) {
         const long long i = base + t;
         double w = 0.0;
         int f0 = 0, f1 = 0;
@@ -721,6 +834,88 @@ __device__ __forceinline__ void phase_fill_chains(const DevModel& M, const doubl
             for (int k = np + ntail; k < CW; ++k) row[k] = 0.0;
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------- tile fill, null-space rows
+// As phase_fill_chains, but a lane owns one (sample, basis vector q_k) instead of one (sample, dof row): its tile row is
+// q_k^T Ytilde, so a sample contributes nq = 18 - rank(J_c) rows, packed one after the other.  Returns (to every
+// thread) the number of k-steps of 4 rows the round occupies; rows up to that multiple of 4 are zero-filled.
+template <int TS, int LD, int NT>
+__device__ __forceinline__ int phase_fill_q(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
+                                            int s0, int friction, int t) {
+    constexpr int GL = ((TS * MAXV + 31) / 32) * 32;     // lanes per group
+    static_assert(NT % 32 == 0 && GL <= NT, "groups are whole warps");
+    const int split = M.fill_split, ngroups = M.nfch * split;
+    const int np = M.nparams, nd = M.nd;
+    // row offsets of the round's samples
+    int off[TS + 1];
+    off[0] = 0;
+#pragma unroll
+    for (int u = 0; u < TS; ++u) {
+        const double* cu = ctx + (s0 + u) * CX_STRIDE;
+        off[u + 1] = off[u] + ((cu[CX_W] == 0.0) ? 0 : (int)cu[CX_NQ]);
+    }
+    const int rows = off[TS], ksteps = (rows + 3) >> 2;
+    for (int e = t; e < (4 * ksteps - rows) * CW; e += NT) tile[(rows + e / CW) * LD + (e % CW)] = 0.0;   // pad rows of the last k-step
+    const int l = t % GL;
+    if (l >= TS * MAXV) return ksteps;
+    const int sl = l / MAXV, k = l - sl * MAXV;
+    int rowi = 0, nq = 0;
+#pragma unroll
+    for (int u = 0; u < TS; ++u) if (u == sl) { rowi = off[u] + k; nq = off[u + 1] - off[u]; }
+    if (k >= nq) return ksteps;
+    const double* c = ctx + (s0 + sl) * CX_STRIDE;
+    const double wsq = c[CX_W];
+    const bool ident = (nq == MAXV);                      // no stance foot: Q = I
+    const double* Qk = c + CX_Q + k * MAXV;
+    double* row = tile + rowi * LD;
+    auto Qe = [&](int cc) { return ident ? ((cc == k) ? 1.0 : 0.0) : Qk[cc]; };
+    for (int g = t / GL; g <= ngroups; g += NT / GL) {
+        if (g < ngroups) {
+            const int ch = (split == 1) ? g : (g >> 1), q = (split == 1) ? 0 : (g & 1);      // split is 1 or 2
+            const int len = M.fch_len[ch], own = M.fch_own[ch];
+            double d[6];           // (dl; da) = q_k^T [I_6; a_j ...], pre-multiplied by sqrt(weight)
+#pragma unroll
+            for (int cc = 0; cc < 6; ++cc) d[cc] = Qe(cc) * wsq;
+            for (int e = 0, turn = 0; e < len; ++e, turn = (turn + 1 == split) ? 0 : turn + 1) {
+                const int j = M.fch[ch][e];
+                const double pj = Qe(4 + j) * wsq;
+                const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
+#pragma unroll
+                for (int cc = 0; cc < 3; ++cc) { const double2 ak = A2[cc]; d[2 * cc] = fma(pj, ak.x, d[2 * cc]); d[2 * cc + 1] = fma(pj, ak.y, d[2 * cc + 1]); }
+                if (e >= own && turn == q) {
+                    const double2* X2 = reinterpret_cast<const double2*>(c + CX_X + 12 * (j - 2));
+                    const double2 x01 = X2[0], x23 = X2[1], x45 = X2[2], x67 = X2[3], x8p = X2[4], p12 = X2[5];
+                    const double p0 = x8p.y, p1 = p12.x, p2 = p12.y;
+                    const double u0 = d[0] + (d[4] * p2 - d[5] * p1), u1 = d[1] + (d[5] * p0 - d[3] * p2), u2 = d[2] + (d[3] * p1 - d[4] * p0);
+                    // (el; ea) = (R^T u; R^T da), R row-major in x01..x8p
+                    const double el0 = x01.x * u0 + x23.y * u1 + x67.x * u2, el1 = x01.y * u0 + x45.x * u1 + x67.y * u2, el2 = x23.x * u0 + x45.y * u1 + x8p.x * u2;
+                    const double ea0 = x01.x * d[3] + x23.y * d[4] + x67.x * d[5], ea1 = x01.y * d[3] + x45.x * d[4] + x67.y * d[5], ea2 = x23.x * d[3] + x45.y * d[4] + x8p.x * d[5];
+                    body_row(c + CX_B9 + B9S * (j - 1), el0, el1, el2, ea0, ea1, ea2, row + 10 * (j - 1));
+                }
+            }
+        } else {
+            // root body (its Pluecker rows are the identity, pose = identity) ...
+            body_row(c + CX_B9, Qe(0) * wsq, Qe(1) * wsq, Qe(2) * wsq, Qe(3) * wsq, Qe(4) * wsq, Qe(5) * wsq, row);
+            // ... and the friction / torque columns plus the zero padding
+            double tau = 0.0;
+            const int ntail = friction ? 2 * nd + 1 : 1;
+            for (int jj = 0; jj < nd; ++jj) {
+                const double pj = Qe(6 + jj) * wsq;
+                tau = fma(pj, c[CX_TAU + jj], tau);
+                if (friction) {
+                    const double dqv = c[CX_DQ + jj];
+                    const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
+                    row[np + jj] = pj * dqv;
+                    row[np + nd + jj] = pj * sg;
+                }
+            }
+            // without friction columns the torque column follows the body columns directly
+            row[np + ntail - 1] = tau;
+            for (int cc = np + ntail; cc < CW; ++cc) row[cc] = 0.0;
+        }
+    }
+    return ksteps;
 }
 
 }  // namespace sysid
