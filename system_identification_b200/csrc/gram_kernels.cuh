@@ -90,12 +90,29 @@ __device__ __forceinline__ void store_tiles(double* __restrict__ partial, int la
     }
 }
 
+template <int NW, int W, int MAXNT>
+__device__ __forceinline__ void load_tiles(const double* __restrict__ partial, int lane, double (&acc)[MAXNT][2]) {
+    using T = WarpTiles<NW, W>;
+#pragma unroll
+    for (int t = 0; t < T::NT; ++t) {
+        const double2 v = *reinterpret_cast<const double2*>(partial + T::ID(t) * 64 + (lane >> 2) * 8 + 2 * (lane & 3));
+        acc[t][0] = v.x; acc[t][1] = v.y;
+    }
+}
+
 // warp-uniform dispatch to the per-warp tile tables
 template <int NW, int MAXNT, int W = 0>
 __device__ __forceinline__ void mma_dispatch(int w, const double* __restrict__ tile, int ksteps, int lane, double (&acc)[MAXNT][2]) {
     if constexpr (W < NW) {
         if (w == W) mma_rows<NW, W, MAXNT>(tile, ksteps, lane, acc);
         else mma_dispatch<NW, MAXNT, W + 1>(w, tile, ksteps, lane, acc);
+    }
+}
+template <int NW, int MAXNT, int W = 0>
+__device__ __forceinline__ void load_dispatch(int w, const double* __restrict__ partial, int lane, double (&acc)[MAXNT][2]) {
+    if constexpr (W < NW) {
+        if (w == W) load_tiles<NW, W, MAXNT>(partial, lane, acc);
+        else load_dispatch<NW, MAXNT, W + 1>(w, partial, lane, acc);
     }
 }
 template <int NW, int MAXNT, int W = 0>
@@ -108,7 +125,7 @@ __device__ __forceinline__ void store_dispatch(int w, double* __restrict__ parti
 constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
 
 // All F phases of one super-batch, executed by a group of NT threads (index t) separated by SYNC().
-#define SYSID_F_PHASES(SB, NT, SYNC, LASTPHASE)                                                                                   \
+#define SYSID_F_PHASES(SB, NT, SYNC, CONTACT)                                                                            \
     phase_stage<SB, NT>(M, args.io, base, args.N, inp, t);                                                               \
     SYNC();                                                                                                              \
     for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, ctx, scr, s_bad, it);              \
@@ -119,26 +136,27 @@ constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
     F_TICK(1)                                                                                                            \
     for (int it = t; it < SB * MAXEE * (MAXCH + 1); it += NT) phase_feet<SB>(M, base, args.N, inp, ctx, scr, it);        \
     SYNC();                                                                                                              \
+    F_TICK(2)                                                                                                            \
+    CONTACT(SB, NT, SYNC)
+
+// contact part, rmse kernel: S = J J^T -> Cholesky -> W = L^-1 J -> packed projector P = I - W^T W
+#define SYSID_CONTACT_PROJ(SB, NT, SYNC)                                                                                 \
     for (int it = t; it < SB * (MAXEE * (MAXEE + 1) / 2); it += NT) phase_sblocks<SB>(M, base, args.N, ctx, scr, it);    \
     SYNC();                                                                                                              \
-    F_TICK(2)                                                                                                            \
     for (int it = t; it < SB; it += NT) phase_chol<SB>(base, args.N, ctx, scr, s_bad, it);                               \
     SYNC();                                                                                                              \
     F_TICK(3)                                                                                                            \
     for (int it = t; it < SB * MAXV; it += NT) phase_wcols<SB>(M, base, args.N, ctx, scr, it);                           \
     SYNC();                                                                                                              \
     F_TICK(4)                                                                                                            \
-    LASTPHASE(SB, NT, SYNC)
-
-// last F phase: the packed projector (rmse kernel) or the orthonormal null-space basis (Gram kernel)
-#define SYSID_LAST_PROJ(SB, NT, SYNC)                                                                                    \
     phase_proj<SB, NT>(base, args.N, inp, ctx, scr, s_bad, t, s_stat);                                                   \
     SYNC();
-#define SYSID_LAST_QBASIS(SB, NT, SYNC)                                                                                  \
-    for (int it = t; it < ((16 * SB + 31) & ~31); it += NT) phase_qbuild<SB>(base, args.N, ctx, scr, it);                \
-    phase_finish<SB>(base, args.N, inp, ctx, s_bad, t, s_stat);                                                          \
+// contact part, Gram kernel: Householder QR of J_c^T -> orthonormal basis Q of null(J_c)
+#define SYSID_CONTACT_QBASIS(SB, NT, SYNC)                                                                               \
+    for (int it = t; it < ((16 * SB + 31) & ~31); it += NT) phase_qbuild<SB>(M, base, args.N, ctx, scr, s_bad, it);      \
     SYNC();                                                                                                              \
-    F_TICK(5)                                                                                                            \
+    F_TICK(3)                                                                                                            \
+    phase_finish<SB>(base, args.N, inp, ctx, s_bad, t, s_stat);                                                          \
     for (int it = t; it < SB * NQMAX; it += NT) phase_qcols<SB>(base, args.N, ctx, scr, it);                             \
     SYNC();
 
@@ -170,8 +188,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     if (tid < 3) s_stat[tid] = 0.0;
     if (tid < FSB) s_bad[tid] = 0;
     double acc[GRAM_MAXNT][2];
-#pragma unroll
-    for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+    double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
     const long long nsb = (args.N + FSB - 1) / FSB;
 #ifdef SYSID_PHASE_CLOCKS
     long long clkF = 0, clkC = 0, clkM = 0, clk0, clkSub[6] = {0, 0, 0, 0, 0, 0};
@@ -182,21 +199,20 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #endif
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * FSB;
-#ifdef SYSID_ONLY_M      // diagnostic: F phases and fill only for the first super-batch, then the M phase on a static tile
-        if (sb == blockIdx.x) {
-#endif
-        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_LAST_QBASIS)
-#ifdef SYSID_ONLY_M
+        // The Gram accumulators (56 registers per thread) are parked in this CTA's partial-Gram slot (L2-resident, 107 KB)
+        // while the F phases run, so that those phases get the whole register file instead of spilling around them.
+        if (sb != (long long)blockIdx.x) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_QBASIS)
+        if (sb != (long long)blockIdx.x) load_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+        else {
+#pragma unroll
+            for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
         }
-#endif
         if (t < FSB) s_bad[t] = 0;
         PHASE_TICK(clkF)
         prefetch_inputs<FSB, GRAM_THREADS>(M, args.io, (sb + gridDim.x) * FSB, args.N, t);     // lands in L2 during the rounds below
         const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
         for (int sub = 0; sub < nsub; ++sub) {
-#ifdef SYSID_ONLY_M
-            if (sb == blockIdx.x && sub == 0)
-#endif
             const int ksteps = phase_fill_q<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
             __syncthreads();
             PHASE_TICK(clkC)
@@ -205,7 +221,6 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
             PHASE_TICK(clkM)
         }
     }
-    double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
     store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
     if (tid == 0) {
         partial[GRAM_NTILES * 64 + 0] = s_stat[0];
@@ -396,7 +411,7 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
     __syncthreads();
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * RSB;
-        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_LAST_PROJ)
+        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_PROJ)
         if (t < RSB) s_bad[t] = 0;
         const int nsub = (int)min((long long)(RSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
         for (int sub = 0; sub < nsub; ++sub) {

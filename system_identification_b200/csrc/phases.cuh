@@ -464,70 +464,95 @@ __device__ __forceinline__ void phase_finish(long long base, long long N, const 
 // two feet down, 6 with four.  W = L^-1 J_c has orthonormal rows (zero rows where a dependent contact row was dropped);
 // Householder reflectors H_0 .. H_{rank-1} map them onto e_0 .. e_{rank-1}, and Q = H_0 ... H_{rank-1} [e_rank .. e_17].
 // qbuild: lane per sample, reflector t overwrites W row t.   qcols: thread per (sample, basis vector).
-// Sixteen lanes per sample (two samples per warp); lane b holds the b-th LIVE row of W in registers (dropped rows are
-// exactly zero and are compacted away, so the pivot of step t sits in component t).  Step t: lane t turns its row into
-// the reflector and publishes it in shared memory (over W row t, which is no longer needed: every lane already holds
-// its row); lanes > t apply it to their rows.  `t` must cover whole warps: [0, 16 SB) rounded up to a multiple of 32.
+// Householder QR of J_c^T, sixteen lanes per sample (two samples per warp): lane b holds contact row b of J_c (built
+// from R_b, the world-aligned lever arms and the leg columns of the `feet` phase) in registers.  For pivot position p
+// the next row whose remainder below p is not negligible (|.|^2 > 1e-13 max_b |J_b|^2: the pinv rank rule, the same
+// quantity the Cholesky pivot of J_c J_c^T measures) becomes reflector p and is published in shared memory; later rows
+// apply it.  No S = J J^T, no Cholesky, no W: the basis comes straight from J_c (and is better conditioned for it).
+// `t` must cover whole warps: [0, 16 SB) rounded up to a multiple of 32.
 template <int SB>
-__device__ __forceinline__ void phase_qbuild(long long base, long long N, double* __restrict__ ctx, double* __restrict__ scr, int t) {
+__device__ __forceinline__ void phase_qbuild(const DevModel& M, long long base, long long N, double* __restrict__ ctx,
+                                             double* __restrict__ scr, int* s_bad, int t) {
     constexpr int MR = 3 * MAXEE;
     static_assert(MR <= 16, "one half-warp per sample");
     const unsigned full = 0xffffffffu;
-    const int s = t >> 4, b = t & 15, hshift = threadIdx.x & 16;
+    const int s = t >> 4, b = t & 15, hbase = threadIdx.x & 16;
     const bool live = (s < SB) && (base + s < N);
     double* sc = scr + (live ? s : 0) * SC_STRIDE;
+    const double* c = ctx + (live ? s : 0) * CX_STRIDE;
     const int m3 = live ? (int)sc[SC_META] : 0;
-    // live rows of W (a dropped row is exactly zero: its first-foot base block cannot vanish otherwise)
-    bool rowlive = false;
-    if (b < m3) {
-        double n2 = 0.0;
-#pragma unroll
-        for (int r = 0; r < MAXV; ++r) { const double w = sc[SC_WM + b * MAXV + r]; n2 = fma(w, w, n2); }
-        rowlive = n2 != 0.0;
-    }
-    const unsigned mask16 = (__ballot_sync(full, rowlive) >> hshift) & 0xffffu;
-    const int rank = __popc(mask16);
-    // lane b takes the b-th live row
-    int src = -1;
-    {
-        unsigned m = mask16;
-        for (int k = 0; k < b; ++k) m &= m - 1;             // drop the b lowest set bits
-        if (m) src = __ffs(m) - 1;
-    }
     double x[MAXV];
 #pragma unroll
-    for (int r = 0; r < MAXV; ++r) x[r] = (b < rank && src >= 0) ? sc[SC_WM + src * MAXV + r] : 0.0;
-    __syncwarp();                                            // every lane holds its row: W rows may now be overwritten
+    for (int r = 0; r < MAXV; ++r) x[r] = 0.0;
+    double n2 = 0.0;
+    if (b < m3) {
+        // row (slot, xx) of J_c = [ R_b | -[r]x R_b | leg columns ], assembled through this lane's own (dead) W row slot
+        const int slot = b / 3, xx = b - 3 * slot;
+        const int kt = (int)sc[SC_META + 1 + slot];
+        double* mine = sc + SC_WM + b * MAXV;
+        const double r0 = sc[SC_RF + 3 * slot], r1 = sc[SC_RF + 3 * slot + 1], r2 = sc[SC_RF + 3 * slot + 2];
 #pragma unroll
-    for (int ts = 0; ts < MR; ++ts) {
-        if (__any_sync(full, ts < rank)) {
-            double* vrow = sc + SC_WM + ts * MAXV;
-            if (b == ts && ts < rank) {
-                double ta = 0.0, tb = 0.0, tc = 0.0;
+        for (int cc = 0; cc < 3; ++cc) {
+            const double b0 = sc[SC_RB + cc], b1 = sc[SC_RB + 3 + cc], b2 = sc[SC_RB + 6 + cc];
+            mine[cc] = (xx == 0) ? b0 : ((xx == 1) ? b1 : b2);
+            mine[3 + cc] = -((xx == 0) ? (r1 * b2 - r2 * b1) : ((xx == 1) ? (r2 * b0 - r0 * b2) : (r0 * b1 - r1 * b0)));
+        }
 #pragma unroll
-                for (int r = ts; r < MAXV; ++r) { if (r % 3 == 0) ta = fma(x[r], x[r], ta); else if (r % 3 == 1) tb = fma(x[r], x[r], tb); else tc = fma(x[r], x[r], tc); }
-                const double tail2 = ta + tb + tc;
-                const double nt = tail2 * rsqrt(fmax(tail2, 1e-300));
-                const double alpha = (x[ts] >= 0.0) ? nt : -nt;
-                const double inv = rsqrt(2.0 * (tail2 + fabs(x[ts]) * nt));      // 1 / |x[ts:] + alpha e_ts|
+        for (int cc = 6; cc < MAXV; ++cc) mine[cc] = 0.0;
+        const int len = M.chain_len[kt];
+        for (int e = 0; e < len; ++e) mine[4 + M.chain[kt][e]] = c[CXT_JL + 3 * (slot * MAXCH + e) + xx];
 #pragma unroll
-                for (int r = 0; r < MAXV; ++r) vrow[r] = (r < ts) ? 0.0 : ((r == ts) ? (x[r] + alpha) * inv : x[r] * inv);
+        for (int r = 0; r < MAXV; ++r) { x[r] = mine[r]; n2 = fma(x[r], x[r], n2); }
+    }
+    double mx = n2;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(full, mx, o));
+    const double tol = 1e-13 * mx;
+    __syncwarp();                                            // every lane holds its row: the slots may now take reflectors
+    int cur = 0, rank = 0, dropped = 0;                      // uniform per half-warp
+#pragma unroll
+    for (int p = 0; p < MR; ++p) {
+        // next row whose remainder below position p is not negligible
+        bool found = false;
+        while (__any_sync(full, !found && cur < m3)) {
+            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+            for (int r = p; r < MAXV; ++r) { if (r % 3 == 0) t0 = fma(x[r], x[r], t0); else if (r % 3 == 1) t1 = fma(x[r], x[r], t1); else t2 = fma(x[r], x[r], t2); }
+            const double tail2 = __shfl_sync(full, t0 + t1 + t2, hbase + min(cur, 15));
+            if (!found && cur < m3) {
+                if (tail2 > tol) found = true;
+                else { ++cur; dropped = 1; }                // dependent row: dropped (pinv semantics)
+            }
+        }
+        if (__any_sync(full, found)) {
+            double* vrow = sc + SC_WM + p * MAXV;
+            if (found && b == cur) {
+                double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+                for (int r = p; r < MAXV; ++r) { if (r % 3 == 0) t0 = fma(x[r], x[r], t0); else if (r % 3 == 1) t1 = fma(x[r], x[r], t1); else t2 = fma(x[r], x[r], t2); }
+                const double tail2 = t0 + t1 + t2;
+                const double nt = tail2 * rsqrt(tail2);
+                const double alpha = (x[p] >= 0.0) ? nt : -nt;
+                const double inv = rsqrt(2.0 * (tail2 + fabs(x[p]) * nt));       // 1 / |x[p:] + alpha e_p|
+#pragma unroll
+                for (int r = 0; r < MAXV; ++r) vrow[r] = (r < p) ? 0.0 : ((r == p) ? (x[r] + alpha) * inv : x[r] * inv);
             }
             __syncwarp();
-            if (b > ts && b < rank) {
+            if (found && b > cur && b < m3) {
                 // the reflector is streamed from shared memory twice (dot, then update) instead of being held in registers
                 const double2* v2 = reinterpret_cast<const double2*>(vrow);
                 double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                for (int r2 = ts / 2; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; d0 = fma(q.x, x[2 * r2], d0); d1 = fma(q.y, x[2 * r2 + 1], d1); }
+                for (int r2 = p / 2; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; d0 = fma(q.x, x[2 * r2], d0); d1 = fma(q.y, x[2 * r2 + 1], d1); }
                 const double d = -2.0 * (d0 + d1);
 #pragma unroll
-                for (int r2 = ts / 2; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; x[2 * r2] = fma(d, q.x, x[2 * r2]); x[2 * r2 + 1] = fma(d, q.y, x[2 * r2 + 1]); }
+                for (int r2 = p / 2; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; x[2 * r2] = fma(d, q.x, x[2 * r2]); x[2 * r2 + 1] = fma(d, q.y, x[2 * r2 + 1]); }
             }
+            if (found) { ++cur; ++rank; }
         }
     }
     if (b == 0 && s < SB) {
-        if (live) sc[SC_META] = (double)rank;               // from here on: the number of reflectors
+        if (live) { sc[SC_META] = (double)rank; if (dropped) atomicOr(&s_bad[s], 1); }   // SC_META: from here on the number of reflectors
         ctx[s * CX_STRIDE + CX_NQ] = live ? (double)(MAXV - rank) : 0.0;
     }
 }

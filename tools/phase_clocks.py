@@ -20,7 +20,7 @@ for it in range(3):
 ws = dm._ws[("gram", dev[0].device)].view(torch.float64).cpu().numpy()
 per = ws.size // 148
 ws = ws[:148 * per].reshape(148, per)
-names = os.environ.get("PHASE_NAMES", "qcols,fill,M,stage+sincos,chains,feet+sblocks,chol,wcols,qbuild").split(",")
+names = os.environ.get("PHASE_NAMES", "qcols,fill,M,stage+sincos,chains,feet,qbuild").split(",")
 clk = ws[:, 210 * 64 + 3: 210 * 64 + 3 + len(names)]
 tot = clk.sum(1).mean()
 spc = N / 148.0
