@@ -35,16 +35,9 @@ constexpr int GRAM_WARPS = GRAM_THREADS / 32;
 #ifndef SYSID_FSB
 #define SYSID_FSB 24
 #endif
-#ifndef SYSID_FILL_CHAINS
-#define SYSID_FILL_CHAINS 1
-#endif
-#ifndef SYSID_RPI
-#define SYSID_RPI 1
-#endif
 constexpr int MMA_UNROLL = SYSID_MMA_UNROLL;
 constexpr int FTS = SYSID_FTS;                 // samples per tile round
 constexpr int FSB = SYSID_FSB;                 // samples per super-batch (F phases)
-constexpr int FILL_RPI = SYSID_RPI;            // rows per fill item
 constexpr int FROWS = FTS * MAXV;
 constexpr int FTILE = FROWS * TILE_LD;
 static_assert(FROWS % 4 == 0 && FSB % FTS == 0, "k-steps of 4 rows");
@@ -125,8 +118,9 @@ __device__ __forceinline__ void store_dispatch(int w, double* __restrict__ parti
 constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
 
 // All F phases of one super-batch, executed by a group of NT threads (index t) separated by SYNC().
-#define SYSID_F_PHASES(SB, NT, SYNC, CONTACT)                                                                            \
+#define SYSID_F_PHASES(SB, NT, SYNC, CONTACT, AFTER_STAGE)                                                               \
     phase_stage<SB, NT>(M, args.io, base, args.N, inp, t);                                                               \
+    AFTER_STAGE                                                                                                          \
     SYNC();                                                                                                              \
     for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, ctx, scr, s_bad, it);              \
     SYNC();                                                                                                              \
@@ -201,8 +195,9 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         const long long base = sb * FSB;
         // The Gram accumulators (56 registers per thread) are parked in this CTA's partial-Gram slot (L2-resident, 107 KB)
         // while the F phases run, so that those phases get the whole register file instead of spilling around them.
-        if (sb != (long long)blockIdx.x) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
-        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_QBASIS)
+        // (stored after the staging loads are in flight: the store has to wait for the previous M phase's DMMAs anyway)
+#define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+        SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_QBASIS, SYSID_PARK_ACC)
         if (sb != (long long)blockIdx.x) load_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
         else {
 #pragma unroll
@@ -411,11 +406,11 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
     __syncthreads();
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * RSB;
-        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_PROJ)
+        SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_PROJ, )
         if (t < RSB) s_bad[t] = 0;
         const int nsub = (int)min((long long)(RSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
         for (int sub = 0; sub < nsub; ++sub) {
-            phase_fill<TILE_SAMPLES, TILE_LD, GRAM_THREADS, 1>(M, ctx, tile, sub * TILE_SAMPLES, 1, t);
+            phase_fill_chains<TILE_SAMPLES, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * TILE_SAMPLES, 1, t);
             __syncthreads();
             for (int row = warp; row < TILE_ROWS; row += GRAM_WARPS) {
                 const int rr = row % MAXV;

@@ -12,15 +12,22 @@
 //   * Brought to the body frame, el = R_i^T (dl + da x p_i), ea = R_i^T da, the ten entries of the row are closed
 //     forms in (omega, alpha, acc) of the body (bodyRegressor^T applied to (el; ea)): ~110 flops per (body, row).
 //
+//   * The null-space projector is P = Q Q^T with Q an orthonormal basis of null(J_c) (18 x nq, nq = 18 - rank J_c), so
+//     A^T A = (Q^T Ytilde)^T (Q^T Ytilde): the Gram kernel contracts nq rows per sample (12-15 with one or two feet
+//     down, 6 with four) instead of 18.  Row k of Q^T Ytilde has exactly the form above with column k of Q in place of
+//     row r of P.
+//
 // Phases (a group of NT threads, barriers between them; `t` is the thread's index in the group):
-//   chains    lane per (sample, leaf chain): sin/cos, poses relative to the base, spatial velocity / gravity-biased
-//             acceleration down the chain -> X_j = (R_j, p_j), a_j, b9_j = (omega, alpha, acc)
-//   feet      thread per (sample, stance slot): world-aligned lever arm and leg columns of the contact Jacobian
-//   sblocks   thread per (sample, pair of stance feet): 3x3 block of S = J_c J_c^T
-//   chol      lane per sample: Cholesky S = L L^T, dependent rows dropped (pinv semantics)
-//   wcols     thread per (sample, dof): column of W = L^-1 J_c by forward substitution
-//   proj      thread per (sample, row): packed lower triangle of P = I - W^T W
-//   fill      thread per (sample, body, row group) + per (sample, row group) for the friction / torque columns -> tile rows
+//   stage     coalesced copy of the super-batch's channel values into shared memory
+//   sincos    thread per (sample, joint); non-finite probe of the sample's column
+//   chains    two lanes per (sample, leaf chain): poses relative to the base -> X_j = (R_j, p_j), a_j;  spatial
+//             velocity / gravity-biased acceleration down the chain -> b9_j = (omega, alpha, acc)
+//   feet      thread per (sample, stance slot, chain joint): world-aligned lever arm and leg columns of J_c
+//   Gram kernel:  qbuild  16 lanes per sample: Householder QR of J_c^T (rank rule of pinv), reflectors to shared memory
+//                 qcols   thread per (sample, basis vector): Q = H_0 ... H_{rank-1} [e_rank ..]
+//                 fill_q  lane per (sample, basis vector, chain group) -> packed tile rows
+//   rmse kernel:  sblocks / chol / wcols / proj  S = J_c J_c^T -> Cholesky -> W = L^-1 J_c -> packed P = I - W^T W
+//                 fill_chains  lane per (sample, dof row, chain group) -> the 18 projected rows
 //
 // The contact Jacobian keeps pinocchio's exact semantics for an UN-normalised logged quaternion (float32 logs are
 // off unit norm by ~3e-8; assuming an orthonormal R_b moves P by ~2e-10, above the parity gate):
@@ -663,115 +670,6 @@ __device__ __forceinline__ void body_row(const double* __restrict__ b9, double e
     double2* d2 = reinterpret_cast<double2*>(dst);      // 10 * body and the row pitch are even: 16-byte aligned
 #pragma unroll
     for (int k = 0; k < 5; ++k) d2[k] = make_double2(o[2 * k], o[2 * k + 1]);
-}
-
-// One item = one (sample, body, group of RPI consecutive rows) -> RPI x 10 entries of the projected row block (the rows
-// of a group share the Pluecker axes, pose and body motion loads and give the thread RPI independent dependency
-// chains), or one (sample, row group) -> the friction and torque columns plus the zero padding.
-// TS samples starting at local sample s0 -> rows [0, TS*MAXV) of `tile`.
-template <int TS, int LD, int NT, int RPI>
-__device__ __forceinline__ void phase_fill(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
-                                           int s0, int friction, int t) {
-    constexpr int NRG = MAXV / RPI;
-    static_assert(MAXV % RPI == 0, "row groups");
-    const int nb = M.nb, np = M.nparams, nd = M.nd;
-    const int per_sample = NRG * (nb + 1);
-    for (int it = t; it < TS * per_sample; it += NT) {
-        const int sl = it / per_sample, rem = it - sl * per_sample;
-        const int ib = rem / NRG, r0 = RPI * (rem - ib * NRG);   // ib in [0, nb]: body ib+1, or nb = friction/torque item
-        const double* c = ctx + (s0 + sl) * CX_STRIDE;
-        const double* P = c + CX_P;
-        const double wsq = c[CX_W];
-        double* row = tile + (sl * MAXV + r0) * LD;
-        // entry (r, cc) of the symmetric P from its packed lower triangle
-        auto Pe = [&](int r, int cc) { return (cc <= r) ? P[r * (r + 1) / 2 + cc] : P[cc * (cc + 1) / 2 + r]; };
-        if (ib < nb) {
-            double* dst = row + 10 * ib;
-            if (wsq == 0.0) {
-#pragma unroll
-                for (int g = 0; g < RPI; ++g)
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) reinterpret_cast<double2*>(dst + g * LD)[k] = make_double2(0.0, 0.0);
-                continue;
-            }
-            const int i = ib + 1;
-            double d[RPI][6];          // (dl; da) of each row
-#pragma unroll
-            for (int g = 0; g < RPI; ++g)
-#pragma unroll
-                for (int k = 0; k < 6; ++k) d[g][k] = Pe(r0 + g, k);
-            for (int j = i; j > 1; j = M.parent[j]) {
-                const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
-                double pj[RPI];
-#pragma unroll
-                for (int g = 0; g < RPI; ++g) pj[g] = Pe(r0 + g, 4 + j);
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double2 ak = A2[k];
-#pragma unroll
-                    for (int g = 0; g < RPI; ++g) { d[g][2 * k] = fma(pj[g], ak.x, d[g][2 * k]); d[g][2 * k + 1] = fma(pj[g], ak.y, d[g][2 * k + 1]); }
-                }
-            }
-            double e[RPI][6];          // (el; ea) of each row
-            if (i > 1) {
-                const double* X = c + CX_X + 12 * (i - 2);
-                const double p0 = X[9], p1 = X[10], p2 = X[11];
-                double u[RPI][3];
-#pragma unroll
-                for (int g = 0; g < RPI; ++g) {
-                    u[g][0] = d[g][0] + (d[g][4] * p2 - d[g][5] * p1);
-                    u[g][1] = d[g][1] + (d[g][5] * p0 - d[g][3] * p2);
-                    u[g][2] = d[g][2] + (d[g][3] * p1 - d[g][4] * p0);
-                }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const double x0 = X[k], x1 = X[3 + k], x2 = X[6 + k];
-#pragma unroll
-                    for (int g = 0; g < RPI; ++g) {
-                        e[g][k] = x0 * u[g][0] + x1 * u[g][1] + x2 * u[g][2];
-                        e[g][3 + k] = x0 * d[g][3] + x1 * d[g][4] + x2 * d[g][5];
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int g = 0; g < RPI; ++g)
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) e[g][k] = d[g][k];
-            }
-            const double* b9 = c + CX_B9 + B9S * ib;
-#pragma unroll
-            for (int g = 0; g < RPI; ++g)
-                body_row(b9, e[g][0] * wsq, e[g][1] * wsq, e[g][2] * wsq, e[g][3] * wsq, e[g][4] * wsq, e[g][5] * wsq, dst + g * LD);
-        } else {
-            double tau[RPI];
-#pragma unroll
-            for (int g = 0; g < RPI; ++g) tau[g] = 0.0;
-            const int ntail = friction ? 2 * nd + 1 : 1;
-            if (wsq != 0.0) {
-                for (int jj = 0; jj < nd; ++jj) {
-                    const double tq = c[CX_TAU + jj];
-                    const double dqv = c[CX_DQ + jj];
-                    const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
-#pragma unroll
-                    for (int g = 0; g < RPI; ++g) {
-                        const double pj = Pe(r0 + g, 6 + jj) * wsq;
-                        tau[g] = fma(pj, tq, tau[g]);
-                        if (friction) { row[g * LD + np + jj] = pj * dqv; row[g * LD + np + nd + jj] = pj * sg; }
-                    }
-                }
-            } else if (friction) {
-                for (int jj = 0; jj < 2 * nd; ++jj)
-#pragma unroll
-                    for (int g = 0; g < RPI; ++g) row[g * LD + np + jj] = 0.0;
-            }
-            // without friction columns the torque column follows the body columns directly
-#pragma unroll
-            for (int g = 0; g < RPI; ++g) {
-                row[g * LD + np + ntail - 1] = tau[g];
-                for (int k = np + ntail; k < CW; ++k) row[g * LD + k] = 0.0;
-            }
-        }
-    }
 }
 
 // ---------------------------------------------------------------------------------------------- tile fill, chain walk
