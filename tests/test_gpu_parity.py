@@ -148,6 +148,32 @@ def test_host_streaming_entry_equals_device_entry():
     assert H.rel(st.cpu().numpy(), full) <= 1e-13
 
 
+def test_rank_deficient_contact_jacobian_matches_pinv():
+    """Two contact frames on the same point make J_c rank deficient whenever both are in stance: numpy's pinv (the reference,
+    src/sys_identification.py:134) projects onto the true null space; the fused path (Householder QR with the pinv rank
+    rule) and the per-sample path (Cholesky with dropped pivots) must agree with it and count the samples in info[0]."""
+    import copy
+    flat = copy.deepcopy(H.flat_model("solo12"))
+    flat.ee_joint = np.array(flat.ee_joint).copy(); flat.ee_offset = np.array(flat.ee_offset).copy()
+    flat.ee_joint[1] = flat.ee_joint[0]; flat.ee_offset[1] = flat.ee_offset[0]          # foot 1 duplicates foot 0
+    N = 64
+    q, dq, ddq, cnt = synth_log = H.synth.make_trajectory(flat, N, 77)
+    tau = H.synth.synth_tau(flat, N, 3)
+    cnt = np.array(cnt); cnt[0, :] = 1.0; cnt[1, ::2] = 1.0; cnt[1, 1::2] = 0.0             # both duplicates down on even samples
+    data = (q, dq, ddq, tau, cnt)
+    dm = _dev(flat)
+    dev = _up(data)
+    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    G, r, s, n = H.split_stats(dm.gram_accumulate(*dev, info=info).cpu().numpy(), 154)
+    t = H.oracle_tree(flat)
+    A, b = H.dy.stacked_system(t, *data, flat.ee_names)
+    assert H.rel(G, A.T @ A) <= 1e-11 and H.rel(r, A.T @ b) <= 1e-11 and abs(s - b @ b) <= 1e-11 * (b @ b)
+    assert info.cpu().tolist()[0] == N // 2 and info.cpu().tolist()[1] == 0
+    _, _, P = dm.projected_batch(*dev, want_P=True)
+    Po = np.array([H.dy.null_space_projector(t, q[:, i], cnt[:, i], flat.ee_names) for i in range(8)])
+    assert np.abs(P[:8].cpu().numpy() - Po).max() <= 1e-11
+
+
 def test_api_errors_are_reported_not_thrown_across_the_abi():
     from system_identification_b200 import _lib
     from system_identification_b200.ops import DeviceModel
