@@ -1,0 +1,72 @@
+"""Bootstrap resampling of the identification (BASELINE.json configs[4]: B resamples of one log, many Gram + LMI solves).
+
+The reference has no bootstrap; this is the batched use of its path that the drop-in makes affordable: every resample is
+the reference's identification (demo/solo_identification.py:67-88) of a log in which sample (or block) i appears w_bi
+times.  Because the fused kernel returns ADDITIVE sufficient statistics, a resample never re-reads the log more than
+once:
+
+  block == 1   sample-level bootstrap: one weighted sysid_gram_accumulate launch per resample (multinomial weights),
+  block  > 1   moving-block bootstrap for time series: one launch per block of `block` consecutive samples, then
+               stats_b = sum_k w_bk stats_k for all resamples at once (a (B x K) @ (K x c^2+c+2) product),
+
+followed by ONE batched sysid_sdp_solve launch (one thread block per resample).  Under torch.distributed the resamples
+shard by problem over the ranks (no data-path collective) and are gathered on every rank.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import distributed as D
+from .ops import sdp_solve, to_device
+
+
+def bootstrap_weights(n_units, B, seed):
+    """(B, n_units) multinomial multiplicities, rows summing to n_units (numpy default_rng(seed): reproducible on the host)."""
+    rng = np.random.default_rng(seed)
+    return rng.multinomial(n_units, np.full(n_units, 1.0 / n_units), size=B).astype(np.float64)
+
+
+def bootstrap_identify(sysid, q, dq, ddq, tau, cnt, B=1024, block=1, seed=1005, lambda_reg=1e-1, tol=1e-10, max_iters=1000,
+                       reg_type="constant_pullback", friction=True, return_stats=False):
+    """Returns x (B, c) = [phi | b_v | b_c] per resample (numpy), the solver info array, and optionally the (B, slen) stats."""
+    from .solver import NEWTON_STEPS_PER_IPM_ITER
+    dm = sysid.device_model
+    rank, ws = D.world()
+    dev = [a if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64) else to_device(a) for a in (q, dq, ddq, tau, cnt)]
+    N = dev[0].shape[1]
+    L, nd = sysid.get_num_links(), (sysid.joints_dof if friction else 0)
+    c = 10 * L + 2 * nd
+    slen = dm.stats_len(friction)
+    block = int(max(1, block))
+    K = (N + block - 1) // block
+    W = bootstrap_weights(K, B, seed)                       # identical on every rank
+    lo, hi = D.shard_bounds(B, rank, ws)                    # this rank's resamples
+    Wl = torch.from_numpy(W[lo:hi]).to(dev[0].device)
+    nb = hi - lo
+    if block == 1:
+        stats = torch.zeros((nb, slen), dtype=torch.float64, device=dev[0].device)
+        for b in range(nb):
+            dm.gram_accumulate(*dev, friction=friction, weights=Wl[b].contiguous(), stats=stats[b])
+    else:
+        per_block = torch.zeros((K, slen), dtype=torch.float64, device=dev[0].device)
+        for k in range(K):
+            sl = [a[:, k * block:min(N, (k + 1) * block)] for a in dev]
+            dm.gram_accumulate(*sl, friction=friction, stats=per_block[k])
+        stats = Wl @ per_block                              # (nb, slen): every statistic is additive over blocks
+    x = torch.empty((nb, c), dtype=torch.float64, device=dev[0].device)
+    info = None
+    if nb > 0:
+        x, info = sdp_solve(stats, L, nd, sysid.get_phi_prior(), sysid.get_bounding_ellipsoids(), sysid.get_robot_mass(),
+                            lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER, reg_type=reg_type,
+                            batch=nb)
+    if ws > 1:
+        import torch.distributed as dist
+        sizes = [D.shard_bounds(B, r, ws) for r in range(ws)]
+        full = torch.zeros((B, c), dtype=torch.float64, device=dev[0].device)
+        full[lo:hi] = x
+        dist.all_reduce(full, op=dist.ReduceOp.SUM)         # disjoint row ranges: a gather
+        x = full
+        del sizes
+    out = (x.cpu().numpy(), info)
+    return out + (stats,) if return_stats else out

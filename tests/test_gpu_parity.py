@@ -148,6 +148,32 @@ def test_host_streaming_entry_equals_device_entry():
     assert H.rel(st.cpu().numpy(), full) <= 1e-13
 
 
+def test_bootstrap_resamples_equal_replicated_logs():
+    """BASELINE configs[4] in miniature: every bootstrap resample's statistics equal those of the log with its samples
+    (or blocks) physically repeated, and the batched LMI solve of the resamples matches the oracle's solve."""
+    from oracle import sdp as osdp
+    from system_identification_b200.bootstrap import bootstrap_identify, bootstrap_weights
+    from system_identification_b200.sys_identification import SystemIdentification
+    flat, data = H.small_log("solo12", 300, seed=9)
+    si = SystemIdentification.from_flat_model(flat)
+    dm = si.device_model
+    dev = _up(data)
+    for block, B in ((1, 5), (25, 6)):
+        x, info, stats = bootstrap_identify(si, *dev, B=B, block=block, seed=1005, return_stats=True)
+        K = (300 + block - 1) // block
+        W = bootstrap_weights(K, B, 1005)
+        assert x.shape == (B, 154) and np.allclose(W.sum(1), K) and all(int(i["status"]) in (0, 1) for i in info)
+        for b in (0, B - 1):
+            idx = np.concatenate([np.arange(k * block, min(300, (k + 1) * block)) for k in range(K) for _ in range(int(W[b, k]))])
+            rep = dm.gram_accumulate(*(a[:, idx].contiguous() for a in dev)).cpu().numpy()
+            assert H.rel(stats[b].cpu().numpy(), rep) <= 1e-12
+        G, r, s, n = H.split_stats(stats[0].cpu().numpy(), 154)
+        prob = osdp.build_problem(G, r, s, n, 13, flat.phi_prior, flat.robot_mass, flat.ellipsoids, 12)
+        xo, _ = osdp.solve_alm(prob)
+        assert H.rel(x[0], xo) <= TOL_PHI
+    assert np.abs(x[0] - x[1]).max() > 0           # resamples differ
+
+
 def test_rank_deficient_contact_jacobian_matches_pinv():
     """Two contact frames on the same point make J_c rank deficient whenever both are in stance: numpy's pinv (the reference,
     src/sys_identification.py:134) projects onto the true null space; the fused path (Householder QR with the pinv rank
