@@ -33,6 +33,7 @@ FLOP_PER_SAMPLE = 18 * 154 * 155 + 2 * 18 * 154          # 435 204: lower-triang
 BYTES_PER_SAMPLE = 8 * (19 + 18 + 18 + 12 + 2)            # 552 B of fp64 input per G1-12 sample
 FP64_PEAK_FALLBACK_TFLOPS = 35.77                         # profiles/fp64_peak_r01.json: cuBLAS DGEMM 8192^3 on this pool
 CPU_SAMPLE = int(os.environ.get("SYSID_BENCH_CPU_SAMPLES", 150_000))
+WORKLOAD = f"{ROBOT} {N_SAMPLES}-sample log (BASELINE configs[3]), regressor+projector+Gram with friction columns, c=154"
 
 
 def parse():
@@ -107,8 +108,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{ROBOT} {N_SAMPLES}-sample log, regressor+projector+Gram (CPU arm runs a bounded sample)",
-                   "samples_per_step": n, "friction_columns": True, "c": 154},
+        "config": {"workload": WORKLOAD, "samples_per_step": n,
+                   "note": "the CPU arm times a bounded sample of the same log per step (samples/s is size-independent: the work is linear in N)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
                          "note": "pinocchio/cvxpy/MOSEK are not installable in this image; oracle/sysid_oracle.c restates the reference's per-sample arithmetic"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -268,7 +269,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{ROBOT} {N_SAMPLES}-sample log (BASELINE configs[3]), regressor+projector+Gram with friction columns, c=154",
+            "config": {"workload": WORKLOAD,
                        "samples_per_rank": n_loc, "sharding": f"contiguous time shards over {world} rank(s), one NCCL all-reduce of {c * c + c + 2} fp64",
                        "l2": "256 MiB buffer rewritten between timed iterations (inputs per rank: %.0f MB)" % (BYTES_PER_SAMPLE * n_loc / 1e6)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
