@@ -686,7 +686,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
 #define SDP_TICK(k)
 #endif
 #ifndef SYSID_SDP_SIGMA0
-#define SYSID_SDP_SIGMA0 1000.0     // initial penalty: 1e3 needs ~15 % fewer Newton steps than 1 on the Solo / Spot / G1 problems (same optima)
+#define SYSID_SDP_SIGMA0 1e4        // initial penalty: 1e4 needs ~20 % fewer Newton steps than 1 on the Solo / Spot / G1 problems (same optima)
 #endif
     double sigma = SYSID_SDP_SIGMA0;
     const double eps = fmax(10.0 * prm.tol, 1e-11);
