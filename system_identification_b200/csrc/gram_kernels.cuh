@@ -1,14 +1,16 @@
 // Stage 1+2 kernels: fused regressor -> projector -> Gram accumulation (never writes the stacked regressor),
 // plus the small debug/compat kernels that DO write per-sample blocks (parity tests, per-sample API).
 //
-// Fused kernel: one persistent CTA (512 threads, 16 warps) per SM, ~200 KB shared memory, phases separated by
+// Fused kernel: one persistent CTA (512 threads, 16 warps) per SM, ~218 KB shared memory, phases separated by
 // CTA barriers:
-//   F phases  (phases.cuh) for a super-batch of FSB samples: chains -> feet -> S blocks -> Cholesky -> W columns ->
-//             P = I - W^T W; per-sample context (P, Pluecker axes, poses, body motions) stays in shared memory
+//   F phases  (phases.cuh) for a super-batch of FSB samples: stage -> sincos -> chains -> feet -> qbuild -> qcols;
+//             the per-sample context (null-space basis Q of J_c, Pluecker axes, poses, body motions) stays in shared
+//             memory; the Gram accumulators are parked in the CTA's partial-Gram slot (L2) meanwhile
 //   per round of FTS samples:
-//     fill    all threads, one (sample, body, row) item each -> the 18 x 160 projected row block of each sample
-//     M       all warps: DMMA (mma.sync m8n8k4 f64) rank-(18 FTS) update of the 160 x 160 lower-triangular Gram held in
-//             registers (210 8x8 tiles, 13-14 per warp, tables in gram_tiles.inc)
+//     fill    lane per (sample, basis vector, chain group) -> the rows Q^T [Y | friction | tau] of each sample, packed
+//             (18 - rank J_c rows per sample, at most 18 FTS = 72 in all, zero-padded to a multiple of 4)
+//     M       all warps: DMMA (mma.sync m8n8k4 f64), one k-step per 4 packed rows, on the 160 x 160 lower-triangular Gram
+//             held in registers (210 8x8 tiles, 13-14 per warp, tables in gram_tiles.inc)
 // Why phased and not warp-specialised: on B200 a DFMA warp that shares an SM sub-partition with saturating DMMA warps
 // gets one issue slot per ~80-110 clk (tools/fp64_mix.cu, profiles/fp64_mix_r01.json), so producers starve exactly when
 // consumers are busy; a specialised variant of this kernel measured 24-30 Msamples/s (profiles/phase_clocks_r01_*.txt).
