@@ -22,6 +22,13 @@
  *   sysid_filtfilt / sysid_savgol  the scipy.signal.filtfilt / savgol_filter calls of read_data
  *                             reference demo/solo_identification.py:15-32 (the step immediately before the path)
  *   sysid_predict_rmse        SystemIdentification.print_tau_prediction_rmse   reference src/sys_identification.py:421-437
+ *   sysid_dat_scan / sysid_dat_parse   np.loadtxt(path + name + "_robot_q.dat", delimiter='\t', dtype=np.float32): the five
+ *                             loads of read_data   reference spot_identification.py:9-14, demo/solo_identification.py:9-14
+ *   sysid_fd_rate / sysid_contact_from_tau   the row loops of calculate_low_motor_ddq (joint and body angular
+ *                             accelerations by finite differences of the tick, contact labels from the ankle torques)
+ *                             reference g1-data/low_ddq_contact_tick.py:46-81, low_ddq_tick.py:19-33, low_ddq.py:19-33
+ *   sysid_round_dat           np.savetxt(fmt='%.6f') then np.loadtxt(dtype=np.float32): what csv2dat + read_data do to
+ *                             a CSV column   reference g1-data/csv2dat.py:50-55
  *
  * Conventions
  *   - extern "C", plain pointers and sizes; no torch / CUDA types in signatures (stream is a void* cudaStream_t).
@@ -149,6 +156,36 @@ int sysid_filtfilt(const double* b_host, int32_t nb, const double* a_host, int32
 size_t sysid_savgol_workspace_bytes(int32_t window_length);
 int sysid_savgol(int32_t window_length, int32_t polyorder, const double* x, double* y, int32_t channels, int64_t N,
                  int64_t ld, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Log ingest.
+ * sysid_dat_scan + sysid_dat_parse = np.loadtxt(file, delimiter=<delimiter>, dtype=np.float32 | np.float64) for the text
+ * np.savetxt(fmt='%.6f', delimiter='\t') writes (reference g1-data/csv2dat.py:50-55): `text` is the file's bytes in DEVICE
+ * memory (4-byte aligned, trailing blank lines trimmed by the caller).  scan counts rows and columns (dims_host[0..1], HOST;
+ * it synchronises the stream because the caller sizes `out` from it) and leaves the field offsets in the workspace; parse
+ * converts every field into out (rows x cols, leading dimension ld, fp64; round_float32 != 0: rounded through float32
+ * and widened, which is what dtype=np.float32 yields).  Conversion is exact (equal to strtod's) on the fields it accepts:
+ * up to 2^53 as a digit string with a decimal exponent within +-22, which covers every "%.6f" field below 9.007e9, plus
+ * nan / inf.  Anything else is counted, never guessed: info_host = {bad fields, index of the first, misplaced row ends,
+ * fields found}; with info_host non-null the call synchronises and returns SYSID_ERR_INVALID when any count is non-zero
+ * (np.loadtxt raises ValueError in those cases). */
+size_t sysid_dat_workspace_bytes(int64_t nbytes);
+int sysid_dat_scan(const void* text, int64_t nbytes, int32_t delimiter, void* workspace, size_t workspace_bytes,
+                   int64_t* dims_host, void* stream);
+int sysid_dat_parse(const void* text, int64_t nbytes, int32_t delimiter, void* workspace, size_t workspace_bytes,
+                    int64_t rows, int64_t cols, double* out, int64_t ld, int32_t round_float32, int64_t* info_host, void* stream);
+
+/* The row loop of calculate_low_motor_ddq (reference g1-data/low_ddq_contact_tick.py:46-70), all channels at once:
+ * y[ch][0] = NaN; for i >= 1 with dt = tick[i] - tick[i-1], dx = x[ch][i] - x[ch][i-1]:  dt > 0 -> (dx * scale) / dt;
+ * else dx == 0 -> 0; else NaN.  scale = 1000 for millisecond ticks (low_ddq_tick.py:28), 1 for low_ddq.py:27. */
+int sysid_fd_rate(const double* tick, const double* x, double* y, int32_t channels, int64_t N, int64_t ld_x, int64_t ld_y,
+                  double scale, void* stream);
+/* out[i] = tau[i] >= hi ? 1 : (tau[i] > lo ? 2 : 0): the contact labels of low_ddq_contact_tick.py:72-81 (hi 10, lo -5). */
+int sysid_contact_from_tau(const double* tau, double* out, int64_t N, double hi, double lo, void* stream);
+/* y = the value x has after np.savetxt(fmt='%.6f') and np.loadtxt (to_float32 != 0: with dtype=np.float32), computed
+ * without the text: exact decimal rounding (ties to even on the exact binary value, as printf does) and the correctly
+ * rounded read-back.  y may alias x. */
+int sysid_round_dat(const double* x, double* y, int32_t channels, int64_t N, int64_t ld_x, int64_t ld_y, int32_t to_float32,
+                    void* stream);
 
 /* LMI-constrained fit (reference src/solver.py:123-210).  All pointers in the desc are HOST pointers. */
 enum { SYSID_REG_CONSTANT_PULLBACK = 0, SYSID_REG_EUCLIDEAN = 1 };

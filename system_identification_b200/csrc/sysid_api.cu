@@ -22,8 +22,18 @@ struct sysid_model {
 };
 
 namespace {
-
 thread_local char g_err[512] = "";
+}
+
+// the other translation units of the library (ingest_api.cu) record their error text through this
+namespace sysid {
+int set_error(int code, const char* message) {
+    snprintf(g_err, sizeof(g_err), "%s", message);
+    return code;
+}
+}  // namespace sysid
+
+namespace {
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
