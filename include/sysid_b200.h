@@ -22,6 +22,9 @@
  *   sysid_filtfilt / sysid_savgol  the scipy.signal.filtfilt / savgol_filter calls of read_data
  *                             reference demo/solo_identification.py:15-32 (the step immediately before the path)
  *   sysid_predict_rmse        SystemIdentification.print_tau_prediction_rmse   reference src/sys_identification.py:421-437
+ *   sysid_tsqr                Solver.solve_llsq_svd: np.linalg.svd of the stacked regressor   reference src/solver.py:32-39
+ *                             (the stack is first reduced to its (c+1) x (c+1) triangular factor on the device)
+ *   sysid_physical_consistency  SystemIdentification.get_physical_consistency   reference src/sys_identification.py:324-389
  *   sysid_dat_scan / sysid_dat_parse   np.loadtxt(path + name + "_robot_q.dat", delimiter='\t', dtype=np.float32): the five
  *                             loads of read_data   reference spot_identification.py:9-14, demo/solo_identification.py:9-14
  *   sysid_fd_rate / sysid_contact_from_tau   the row loops of calculate_low_motor_ddq (joint and body angular
@@ -186,6 +189,22 @@ int sysid_contact_from_tau(const double* tau, double* out, int64_t N, double hi,
  * rounded read-back.  y may alias x. */
 int sysid_round_dat(const double* x, double* y, int32_t channels, int64_t N, int64_t ld_x, int64_t ld_y, int32_t to_float32,
                     void* stream);
+
+/* Communication-avoiding QR of the stacked system [A | b] (A: rows x c row-major, b: rows or NULL; device): R_out receives
+ * the (c+1) x (c+1) upper-triangular factor [R z; 0 rho] (row-major, zeros below the diagonal), R^T R = A^T A, z = Q^T b,
+ * rho = the least-squares residual norm (up to sign).  R has the singular values and right singular vectors of A, so
+ * Solver.solve_llsq_svd (reference src/solver.py:32-39) is V diag(1/sigma_i, sigma_i > 1e-15 sigma_max) U_R^T z with
+ * U_R S V^T the SVD of the c x c R -- without squaring the condition number as the Gram route would.  Deterministic. */
+size_t sysid_tsqr_workspace_bytes(int32_t c);
+int sysid_tsqr(const double* A, const double* b, int64_t rows, int32_t c, double* R_out, void* workspace, size_t workspace_bytes,
+               void* stream);
+
+/* get_physical_consistency (reference src/sys_identification.py:324-389) for `batch` parameter vectors (phi + i phi_stride,
+ * 10 num_links each, reference order m, h, Ixx Ixy Ixz Iyy Iyz Izz): out[i][0..4][link] = min eig I_bar, min eig of the 6x6
+ * spatial inertia, min eig J, min eig C, tr(J Q).  Matrices the reference builds as np.float32 are rounded entry by entry
+ * to float32; eigenvalues by fp64 Jacobi (the reference's float32 LAPACK answer agrees to float32 precision). */
+int sysid_physical_consistency(const double* phi, int64_t phi_stride, int32_t batch, int32_t num_links, const double* semi_axes,
+                               const double* centers, double* out, void* stream);
 
 /* LMI-constrained fit (reference src/solver.py:123-210).  All pointers in the desc are HOST pointers. */
 enum { SYSID_REG_CONSTANT_PULLBACK = 0, SYSID_REG_EUCLIDEAN = 1 };

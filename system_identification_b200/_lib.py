@@ -80,6 +80,9 @@ _SIGNATURES = {
     "sysid_fd_rate": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_double, _P]),
     "sysid_contact_from_tau": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, _P]),
     "sysid_round_dat": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P]),
+    "sysid_tsqr_workspace_bytes": (C.c_size_t, [C.c_int32]),
+    "sysid_tsqr": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P]),
+    "sysid_physical_consistency": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "sysid_sdp_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sysid_sdp_solve": (C.c_int, [C.POINTER(SdpDesc), _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "sysid_predict_rmse": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),

@@ -21,6 +21,7 @@ UNITS = {
     "sysid_api.cu": ["sysid_api.cu", "gram_kernels.cuh", "kinematics.cuh", "phases.cuh", "model.cuh", "sdp_kernels.cuh",
                      "filter_kernels.cuh", "gram_tiles.inc", HEADER],
     "ingest_api.cu": ["ingest_api.cu", "ingest_kernels.cuh", HEADER],
+    "extras_api.cu": ["extras_api.cu", "tsqr_kernels.cuh", HEADER],
 }
 SOURCES = list(UNITS)
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

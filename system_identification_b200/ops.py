@@ -199,6 +199,55 @@ def gram_from_stack(A, b, stats=None):
     return stats
 
 
+def tsqr(A, b=None):
+    """Triangular factor of the stacked system [A | b] (A (rows, c), b (rows) CUDA fp64): returns the (c+1, c+1) upper
+    triangle [R z; 0 rho] (sysid_tsqr).  Used by Solver.solve_llsq_svd (reference src/solver.py:32-39)."""
+    _require_cuda()
+    lib = _lib.load()
+    if A.dtype != torch.float64 or not A.is_cuda or A.dim() != 2 or not A.is_contiguous():
+        raise ValueError("A: expected contiguous CUDA float64 (rows, c)")
+    rows, c = A.shape
+    if b is not None:
+        b = b.to(device=A.device, dtype=torch.float64).contiguous()
+        if b.numel() != rows:
+            raise ValueError("b: length must equal the rows of A")
+    R = torch.empty((c + 1, c + 1), dtype=torch.float64, device=A.device)
+    nbytes = lib.sysid_tsqr_workspace_bytes(c)
+    if nbytes == 0:
+        raise ValueError(f"tsqr: c = {c} is outside the compiled envelope")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
+    _lib.check(lib.sysid_tsqr(_ptr(A), _ptr(b), rows, c, _ptr(R), _ptr(ws), ws.numel(), _stream()))
+    return R
+
+
+def llsq_svd_from_triangle(R_aug, rcond=1e-15):
+    """Minimum-norm least-squares solution from the TSQR triangle: SVD of the small c x c R on the device (library call on
+    a 130 x 130 matrix), singular values <= rcond * sigma_max dropped (np.linalg.pinv's rule, reference src/solver.py:37)."""
+    c = R_aug.shape[0] - 1
+    R, z = R_aug[:c, :c], R_aug[:c, c]
+    U, S, Vh = torch.linalg.svd(R, full_matrices=False)
+    Sinv = torch.where(S > rcond * S.max(), 1.0 / S, torch.zeros_like(S))
+    return Vh.T @ (Sinv * (U.T @ z)), S
+
+
+def physical_consistency(phi, num_links, ellipsoids):
+    """get_physical_consistency (reference src/sys_identification.py:324-389) for a batch of parameter vectors on the
+    device.  phi: (batch, >= 10 num_links) CUDA fp64 (or 1-D).  Returns a CUDA tensor (batch, 5, num_links):
+    min eig I_bar, min eig I (6x6), min eig J, min eig C, tr(J Q)."""
+    _require_cuda()
+    lib = _lib.load()
+    phi = phi if phi.dim() == 2 else phi.unsqueeze(0)
+    if phi.dtype != torch.float64 or not phi.is_cuda or phi.stride(1) != 1 or phi.shape[1] < 10 * num_links:
+        raise ValueError("phi: expected CUDA float64 (batch, >= 10 * num_links) with unit inner stride")
+    sa = torch.tensor(np.array([e["semi_axes"] for e in ellipsoids], dtype=np.float64).reshape(-1), device=phi.device)
+    ce = torch.tensor(np.array([e["center"] for e in ellipsoids], dtype=np.float64).reshape(-1), device=phi.device)
+    if sa.numel() != 3 * num_links or ce.numel() != 3 * num_links:
+        raise ValueError("bounding_ellipsoids do not match num_links")
+    out = torch.empty((phi.shape[0], 5, num_links), dtype=torch.float64, device=phi.device)
+    _lib.check(lib.sysid_physical_consistency(_ptr(phi), phi.stride(0) if phi.shape[0] > 1 else phi.shape[1], phi.shape[0], num_links, _ptr(sa), _ptr(ce), _ptr(out), _stream()))
+    return out
+
+
 def sdp_solve(stats, num_links, ndof, phi_prior, ellipsoids, total_mass, lambda_reg=1e-1, tol=1e-10, max_iters=0,
               reg_type="constant_pullback", epsilon=1e-6, batch=1):
     """Persistent-kernel (semismooth-Newton augmented Lagrangian) solve of reference Solver.solve_fully_consistent (src/solver.py:123-210).

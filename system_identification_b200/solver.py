@@ -68,19 +68,19 @@ class Solver():
 
     # -------------- Unconstrained Solver -------------- #
     def solve_llsq_svd(self):
-        """Minimum-norm least squares through the thin SVD of the full stack (reference src/solver.py:32-39).
-        Not on the accelerated path (no demo calls it): library SVD on the device, numpy's pinv cutoff."""
+        """Minimum-norm least squares of the full stack (reference src/solver.py:32-39: thin SVD, pinv of diag(Sigma),
+        V Sigma^+ U^T tau).  The rows x c stack is reduced on the device to its c x c triangular factor R and z = Q^T tau
+        (sysid_tsqr: blocked Householder, no Gram, so the 1e-15 cutoff of pinv means what it means in the reference);
+        R has the singular values and right singular vectors of the stack, and the answer is V Sigma^+ U_R^T z."""
         import torch
-        from .ops import _require_cuda
+        from .ops import _require_cuda, llsq_svd_from_triangle, tsqr
         _require_cuda()
         if self._Y is None:
             raise ValueError("solve_llsq_svd needs the stacked regressor (Solver built from_stats has none)")
-        Y = torch.as_tensor(np.asarray(self._Y, dtype=np.float64), device="cuda")
-        tau = torch.as_tensor(np.asarray(self._tau, dtype=np.float64), device="cuda")
-        U, S, Vh = torch.linalg.svd(Y, full_matrices=False)
-        cutoff = 1e-15 * S.max()
-        Sinv = torch.where(S > cutoff, 1.0 / S, torch.zeros_like(S))
-        return (Vh.T @ (Sinv * (U.T @ tau))).cpu().numpy()
+        Y = torch.as_tensor(np.ascontiguousarray(np.asarray(self._Y, dtype=np.float64)), device="cuda")
+        tau = torch.as_tensor(np.ascontiguousarray(np.asarray(self._tau, dtype=np.float64).reshape(-1)), device="cuda")
+        x, self._singular_values = llsq_svd_from_triangle(tsqr(Y, tau))
+        return x.cpu().numpy()
 
     # ------------ Constrained Solver (LMI) ------------ #
     def _device_stats(self):

@@ -153,6 +153,15 @@ class SystemIdentification(object):
             out[4].append(np.trace(J @ Qf))
         return out
 
+    def get_physical_consistency_batch(self, phis):
+        """get_physical_consistency for many parameter vectors at once (e.g. bootstrap resamples) on the device:
+        phis (batch, 10 L) -> numpy (batch, 5, L) = [min eig I_bar, min eig I, min eig J, min eig C, tr(J Q)] per link."""
+        import torch
+        from .ops import physical_consistency
+        t = phis if isinstance(phis, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(np.asarray(phis, dtype=np.float64)))
+        t = t.to(device="cuda", dtype=torch.float64)
+        return physical_consistency(t.contiguous(), self._num_links, self._bounding_ellipsoids).cpu().numpy()
+
     def get_full_regressor_force(self, q, dq, ddq, tau, ee_force, cnt):
         raise NotImplementedError(
             "get_full_regressor_force (reference src/sys_identification.py:391-399) has no caller in the reference and "
