@@ -18,6 +18,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "phases.cuh"
+#include "tmem_park.cuh"
 
 namespace sysid {
 
@@ -183,6 +184,11 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
     if (tid < 3) s_stat[tid] = 0.0;
     if (tid < FSB) s_bad[tid] = 0;
+#ifndef SYSID_PARK_L2
+    __shared__ uint32_t s_tmem;
+    if (warp == 0) tmem_alloc(&s_tmem, TMEM_PARK_COLS);
+    tmem_fence_before_sync();
+#endif
     double acc[GRAM_MAXNT][2];
     double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
     const long long nsb = (args.N + FSB - 1) / FSB;
@@ -190,18 +196,34 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     long long clkF = 0, clkC = 0, clkM = 0, clk0, clkSub[6] = {0, 0, 0, 0, 0, 0};
 #endif
     __syncthreads();
+#ifndef SYSID_PARK_L2
+    tmem_fence_after_sync();
+    // this warp's parking columns: lane quarter warp % 4 (the only TMEM lanes a warp can reach), column block warp / 4
+    const uint32_t tpark = s_tmem + (((uint32_t)(warp & 3) * 32u) << 16) + (uint32_t)(warp >> 2) * 64u;
+#endif
 #ifdef SYSID_PHASE_CLOCKS
     clk0 = clock64();
 #endif
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * FSB;
-        // The Gram accumulators (56 registers per thread) are parked in this CTA's partial-Gram slot (L2-resident, 107 KB)
-        // while the F phases run, so that those phases get the whole register file instead of spilling around them.
+        // The Gram accumulators (56 registers per thread) are parked while the F phases run, so that those phases get the
+        // whole register file instead of spilling around them: in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 115 KB of the
+        // SM's otherwise idle 256 KB), which replaced a round trip through the CTA's partial-Gram slot in L2
+        // (-DSYSID_PARK_L2 restores that path for A/B timing).
         // (stored after the staging loads are in flight: the store has to wait for the previous M phase's DMMAs anyway)
+#ifdef SYSID_PARK_L2
 #define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+#else
+#define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) tmem_park<GRAM_MAXNT>(tpark, acc);
+#endif
         SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_QBASIS, SYSID_PARK_ACC)
-        if (sb != (long long)blockIdx.x) load_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
-        else {
+        if (sb != (long long)blockIdx.x) {
+#ifdef SYSID_PARK_L2
+            load_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+#else
+            tmem_unpark<GRAM_MAXNT>(tpark, acc);
+#endif
+        } else {
 #pragma unroll
             for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
         }
@@ -219,6 +241,10 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         }
     }
     store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+#ifndef SYSID_PARK_L2
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(s_tmem, TMEM_PARK_COLS);
+#endif
     if (tid == 0) {
         partial[GRAM_NTILES * 64 + 0] = s_stat[0];
         partial[GRAM_NTILES * 64 + 1] = s_stat[1];
