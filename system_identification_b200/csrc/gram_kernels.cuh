@@ -172,6 +172,14 @@ struct GramArgs {
 #define F_TICK(k)
 #endif
 
+// Accumulator parking policy: default = the accumulators live in tensor memory and visit registers only for the M phases
+// (every other phase gets the whole register file: zero spills).  -DSYSID_PARK_F_ONLY: parked only across the F phases;
+// -DSYSID_PARK_L2: the pre-TMEM path through the partial-Gram slot in L2.  Measured on the 1M-sample G1 log:
+// 46.9 (L2) -> 50.4 (F only) -> 53.4 Msamples/s (default).
+#if !defined(SYSID_PARK_L2) && !defined(SYSID_PARK_F_ONLY)
+#define SYSID_PARK_FILL 1
+#endif
+
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     extern __shared__ __align__(16) double smem[];
@@ -206,17 +214,24 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #endif
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * FSB;
-        // The Gram accumulators (56 registers per thread) are parked while the F phases run, so that those phases get the
-        // whole register file instead of spilling around them: in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 115 KB of the
-        // SM's otherwise idle 256 KB), which replaced a round trip through the CTA's partial-Gram slot in L2
-        // (-DSYSID_PARK_L2 restores that path for A/B timing).
-        // (stored after the staging loads are in flight: the store has to wait for the previous M phase's DMMAs anyway)
-#ifdef SYSID_PARK_L2
+        // The Gram accumulators (56 registers per thread) are parked in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 115 KB of
+        // the SM's otherwise idle 256 KB) whenever no M phase is running, so that the F phases and the tile fill get the
+        // whole register file instead of spilling around them; see the policy note above the kernel.
+#if defined(SYSID_PARK_L2)
 #define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+#elif defined(SYSID_PARK_FILL)
+#define SYSID_PARK_ACC                                   // already parked: the accumulators only visit registers for the M phases
 #else
 #define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) tmem_park<GRAM_MAXNT>(tpark, acc);
 #endif
         SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_QBASIS, SYSID_PARK_ACC)
+#if defined(SYSID_PARK_FILL)
+        if (sb == (long long)blockIdx.x) {
+#pragma unroll
+            for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+            tmem_park<GRAM_MAXNT>(tpark, acc);
+        }
+#else
         if (sb != (long long)blockIdx.x) {
 #ifdef SYSID_PARK_L2
             load_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
@@ -227,6 +242,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #pragma unroll
             for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
         }
+#endif
         if (t < FSB) s_bad[t] = 0;
         PHASE_TICK(clkF)
         prefetch_inputs<FSB, GRAM_THREADS>(M, args.io, (sb + gridDim.x) * FSB, args.N, t);     // lands in L2 during the rounds below
@@ -235,11 +251,24 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
             const int ksteps = phase_fill_q<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
             __syncthreads();
             PHASE_TICK(clkC)
+#if defined(SYSID_PARK_FILL)
+            tmem_unpark<GRAM_MAXNT>(tpark, acc);
+#endif
             mma_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, tile, ksteps, lane, acc);
+#if defined(SYSID_PARK_FILL)
+            tmem_park<GRAM_MAXNT>(tpark, acc);
+#endif
             __syncthreads();
             PHASE_TICK(clkM)
         }
     }
+#if defined(SYSID_PARK_FILL)
+    if ((long long)blockIdx.x < nsb) tmem_unpark<GRAM_MAXNT>(tpark, acc);
+    else {
+#pragma unroll
+        for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+    }
+#endif
     store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
 #ifndef SYSID_PARK_L2
     __syncthreads();

@@ -176,13 +176,21 @@ __device__ double dat_ratio(unsigned long long M, unsigned long long D) {
 // rounded IEEE multiplication or division gives the correctly rounded value ("%.6f" text below 9.007e9).  Longer digit
 // strings (M < 2^64, -19 <= e <= 0) go through the integer division of dat_ratio.  Anything else (20+ significant
 // digits, large exponents, garbage) returns false: counted and reported, never approximated.
-__device__ __forceinline__ bool dat_lower_eq(const unsigned char* s, int n, const char* word, int wl) {
+// (the field is read in place from the staged text through an accessor: s[i] = byte i of the field)
+struct DatSmemField {
+    const unsigned* sm; int p0;
+    __device__ __forceinline__ unsigned operator[](int i) const { return dat_byte(sm, p0 + i); }
+};
+
+template <typename S>
+__device__ __forceinline__ bool dat_lower_eq(const S& s, int a, int n, const char* word, int wl) {
     if (n != wl) return false;
-    for (int k = 0; k < wl; ++k) if ((s[k] | 0x20) != (unsigned char)word[k]) return false;
+    for (int k = 0; k < wl; ++k) if ((s[a + k] | 0x20u) != (unsigned)(unsigned char)word[k]) return false;
     return true;
 }
 
-__device__ bool dat_convert(const unsigned char* s, int n, double* out) {
+template <typename S>
+__device__ bool dat_convert(const S& s, int n, double* out) {
     int a = 0, b = n;
     while (a < b && (s[a] == ' ' || s[a] == '\r')) ++a;
     while (b > a && (s[b - 1] == ' ' || s[b - 1] == '\r')) --b;
@@ -191,8 +199,8 @@ __device__ bool dat_convert(const unsigned char* s, int n, double* out) {
     if (s[a] == '+' || s[a] == '-') { neg = (s[a] == '-'); ++a; }
     if (a == b) return false;
     if ((s[a] | 0x20) == 'n' || (s[a] | 0x20) == 'i') {
-        if (dat_lower_eq(s + a, b - a, "nan", 3)) { *out = neg ? -__longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double(0x7ff8000000000000LL); return true; }
-        if (dat_lower_eq(s + a, b - a, "inf", 3) || dat_lower_eq(s + a, b - a, "infinity", 8)) {
+        if (dat_lower_eq(s, a, b - a, "nan", 3)) { *out = neg ? -__longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double(0x7ff8000000000000LL); return true; }
+        if (dat_lower_eq(s, a, b - a, "inf", 3) || dat_lower_eq(s, a, b - a, "infinity", 8)) {
             *out = neg ? -__longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff0000000000000LL); return true;
         }
         return false;
@@ -275,19 +283,17 @@ dat_parse_kernel(const DatParseArgs g) {
         const unsigned c = dat_byte(sm, p);
         const bool isdelim = (c == '\n') || (c == g.delim);
         if (start) {
-            // gather the field (it may run into the halo)
-            unsigned char buf[DAT_MAXFIELD + 1];
+            // the field ends at the next delimiter or at the end of the text (it may run into the halo)
             int len = 0;
             bool closed = false;
             unsigned term = '\n';
             for (int e = p; e < DAT_BLOCK_BYTES + DAT_HALO; ++e) {
                 const unsigned ce = dat_byte(sm, e);
                 if (ce == '\n' || ce == g.delim || b0 + e >= g.nbytes) { closed = true; term = (b0 + e >= g.nbytes) ? (unsigned)'\n' : ce; break; }
-                if (len < DAT_MAXFIELD) buf[len] = (unsigned char)ce;
                 ++len;
             }
             double v = __longlong_as_double(0x7ff8000000000000LL);
-            bool ok = closed && len <= DAT_MAXFIELD && dat_convert(buf, len, &v);
+            bool ok = closed && len <= DAT_MAXFIELD && dat_convert(DatSmemField{sm, p}, len, &v);
             const long long row = idx / g.cols, col = idx - row * g.cols;
             if (!ok) { ++nbad; if (idx < firstbad) firstbad = idx; v = __longlong_as_double(0x7ff8000000000000LL); }
             if (row < g.rows) g.out[row * g.ld + col] = g.round_f32 ? (double)__double2float_rn(v) : v;
