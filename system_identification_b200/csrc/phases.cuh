@@ -40,17 +40,19 @@ namespace sysid {
 // ---- per-sample context (doubles) ------------------------------------------------------------------------
 constexpr int NPACK = MAXV * (MAXV + 1) / 2;        // 171
 constexpr int NQMAX = MAXV - 3;                     // a sample with a stance foot has at most 15 null-space directions
-constexpr int CX_Q = 0;                             // [NQMAX][MAXV] orthonormal basis of null(J_c), one vector per row (Gram kernel)
+constexpr int QLD = MAXV + 1;                       // pitch of a basis vector: odd, so the lanes of the tile fill (one vector each, same
+                                                    // coordinate) read 16 distinct banks instead of colliding in pairs (pitch 18: k and k + 8)
+constexpr int CX_Q = 0;                             // [NQMAX][QLD] orthonormal basis of null(J_c), one vector per row (Gram kernel)
 constexpr int CX_P = CX_Q;                          // [171] packed lower triangle of P, same slot (rmse kernel)
-constexpr int CX_W = CX_Q + NQMAX * MAXV;           // sqrt(weight); 0 => sample contributes nothing
+constexpr int CX_W = CX_Q + NQMAX * QLD;            // sqrt(weight); 0 => sample contributes nothing
 constexpr int CX_NQ = CX_W + 1;                     // number of basis vectors (= rows of the sample's block); MAXV with no stance foot: Q = I, not stored
-constexpr int CX_A = CX_NQ + 1;                     // [MAXD][6] Pluecker axis (m; z) of every revolute joint
+constexpr int CX_A = CX_NQ + 2;                     // [MAXD][6] Pluecker axis (m; z) of every revolute joint (one pad before: 16-byte alignment)
 constexpr int CX_X = CX_A + 6 * MAXD;               // [MAXD][12] R (9, row-major), p (3) relative to the base
 constexpr int B9S = 10;                             // body-motion record: omega, alpha, acc + 1 pad (16-byte loads)
 constexpr int CX_B9 = CX_X + 12 * MAXD;             // [MAXB][B9S] omega, alpha, acc (local frame)
 constexpr int CX_DQ = CX_B9 + B9S * MAXB;           // [MAXD]
 constexpr int CX_TAU = CX_DQ + MAXD;                // [MAXD]
-constexpr int CX_STRIDE = CX_TAU + MAXD;            // 642 == 2 (mod 16): lanes of consecutive samples hit distinct banks
+constexpr int CX_STRIDE = CX_TAU + MAXD;            // 658 == 2 (mod 16): lanes of consecutive samples hit distinct banks
 // temporaries living in the P slot until `proj` overwrites it
 constexpr int CXT_S = CX_P;                         // [78] packed S, then L
 constexpr int CXT_JL = CX_P + 78;                   // [MAXEE][MAXCH][3] leg columns of J_c
@@ -584,9 +586,9 @@ __device__ __forceinline__ void phase_qcols(long long base, long long N, double*
 #pragma unroll
         for (int r2 = 0; r2 < MAXV / 2; ++r2) { const double2 q = v2[r2]; x[2 * r2] = fma(d, q.x, x[2 * r2]); x[2 * r2 + 1] = fma(d, q.y, x[2 * r2 + 1]); }
     }
-    double2* q2 = reinterpret_cast<double2*>(ctx + s * CX_STRIDE + CX_Q + k * MAXV);
+    double* qk = ctx + s * CX_STRIDE + CX_Q + k * QLD;       // odd pitch: scalar stores, conflict-free across the sample's lanes
 #pragma unroll
-    for (int r2 = 0; r2 < MAXV / 2; ++r2) q2[r2] = make_double2(x[2 * r2], x[2 * r2 + 1]);
+    for (int r = 0; r < MAXV; ++r) qk[r] = x[r];
 }
 
 // ---------------------------------------------------------------------------------------------- P = I - W^T W
@@ -790,7 +792,7 @@ __device__ __forceinline__ int phase_fill_q(const DevModel& M, const double* __r
     const double* c = ctx + (s0 + sl) * CX_STRIDE;
     const double wsq = c[CX_W];
     const bool ident = (nq == MAXV);                      // no stance foot: Q = I
-    const double* Qk = c + CX_Q + k * MAXV;
+    const double* Qk = c + CX_Q + k * QLD;
     double* row = tile + rowi * LD;
     auto Qe = [&](int cc) { return ident ? ((cc == k) ? 1.0 : 0.0) : Qk[cc]; };
     for (int g = t / GL; g <= ngroups; g += NT / GL) {
@@ -820,22 +822,42 @@ __device__ __forceinline__ int phase_fill_q(const DevModel& M, const double* __r
         } else {
             // root body (its Pluecker rows are the identity, pose = identity) ...
             body_row(c + CX_B9, Qe(0) * wsq, Qe(1) * wsq, Qe(2) * wsq, Qe(3) * wsq, Qe(4) * wsq, Qe(5) * wsq, row);
-            // ... and the friction / torque columns plus the zero padding
-            double tau = 0.0;
+            // ... and the friction / torque columns plus the zero padding, as 16-byte stores where the layout allows
+            // (columns np.., np + nd.. and the torque column all start on even offsets for the robots of the envelope)
             const int ntail = friction ? 2 * nd + 1 : 1;
-            for (int jj = 0; jj < nd; ++jj) {
-                const double pj = Qe(6 + jj) * wsq;
-                tau = fma(pj, c[CX_TAU + jj], tau);
-                if (friction) {
-                    const double dqv = c[CX_DQ + jj];
-                    const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
-                    row[np + jj] = pj * dqv;
-                    row[np + nd + jj] = pj * sg;
+            if (((np | nd) & 1) == 0) {
+                double tau = 0.0;
+                for (int jj = 0; jj < nd; jj += 2) {
+                    const double p0 = Qe(6 + jj) * wsq, p1 = Qe(7 + jj) * wsq;
+                    const double2 tq = *reinterpret_cast<const double2*>(c + CX_TAU + jj);
+                    tau = fma(p0, tq.x, tau); tau = fma(p1, tq.y, tau);
+                    if (friction) {
+                        const double2 dv = *reinterpret_cast<const double2*>(c + CX_DQ + jj);
+                        const double s0v = (dv.x > 0.0) ? 1.0 : ((dv.x < 0.0) ? -1.0 : (dv.x == 0.0 ? 0.0 : dv.x));   // numpy sign: sign(nan)=nan
+                        const double s1v = (dv.y > 0.0) ? 1.0 : ((dv.y < 0.0) ? -1.0 : (dv.y == 0.0 ? 0.0 : dv.y));
+                        *reinterpret_cast<double2*>(row + np + jj) = make_double2(p0 * dv.x, p1 * dv.y);
+                        *reinterpret_cast<double2*>(row + np + nd + jj) = make_double2(p0 * s0v, p1 * s1v);
+                    }
                 }
+                // the torque column sits on an even offset; everything after it is padding
+                *reinterpret_cast<double2*>(row + np + ntail - 1) = make_double2(tau, 0.0);
+                for (int cc = np + ntail + 1; cc < CW; cc += 2) *reinterpret_cast<double2*>(row + cc) = make_double2(0.0, 0.0);
+            } else {
+                double tau = 0.0;
+                for (int jj = 0; jj < nd; ++jj) {
+                    const double pj = Qe(6 + jj) * wsq;
+                    tau = fma(pj, c[CX_TAU + jj], tau);
+                    if (friction) {
+                        const double dqv = c[CX_DQ + jj];
+                        const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
+                        row[np + jj] = pj * dqv;
+                        row[np + nd + jj] = pj * sg;
+                    }
+                }
+                // without friction columns the torque column follows the body columns directly
+                row[np + ntail - 1] = tau;
+                for (int cc = np + ntail; cc < CW; ++cc) row[cc] = 0.0;
             }
-            // without friction columns the torque column follows the body columns directly
-            row[np + ntail - 1] = tau;
-            for (int cc = np + ntail; cc < CW; ++cc) row[cc] = 0.0;
         }
     }
     return ksteps;
