@@ -90,7 +90,14 @@ def load_dat(source, delimiter="\t", dtype=np.float32, device=None):
     rc = lib.sysid_dat_parse(_ptr(text), n, ord(delimiter), _ptr(ws), ws.numel(), rows, cols, _ptr(out), cols, 1 if f32 else 0,
                              info, _stream())
     if rc == -1:
-        raise ValueError(lib.sysid_last_error().decode())
+        msg = lib.sysid_last_error().decode()
+        if info[0] > 0:                              # name the offending text, as np.loadtxt does (error path only)
+            cuts = np.flatnonzero((raw[:n] == ord(delimiter)) | (raw[:n] == 0x0A))
+            k = int(info[1])
+            lo = int(cuts[k - 1]) + 1 if k > 0 else 0
+            hi = int(cuts[k]) if k < cuts.size else n
+            msg += f": {bytes(raw[lo:hi])!r}" + ("" if isinstance(source, (bytes, bytearray, memoryview)) else f" in {os.fspath(source)}")
+        raise ValueError(msg)
     _lib.check(rc)
     return out
 

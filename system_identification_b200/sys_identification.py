@@ -181,8 +181,9 @@ class SystemIdentification(object):
 
     # ------------------------------------------------------------------ batched entry points (new)
     def _upload(self, q, dq, ddq, tau, cnt):
+        import torch
         from .ops import to_device
-        return tuple(to_device(np.asarray(a)) for a in (q, dq, ddq, tau, cnt))
+        return tuple(to_device(a if isinstance(a, torch.Tensor) else np.asarray(a)) for a in (q, dq, ddq, tau, cnt))
 
     def gram(self, q, dq, ddq, tau, cnt, friction=True, weights=None):
         """Fused regressor+projector+Gram over all columns of the five (channels x N) arrays -> device stats tensor."""

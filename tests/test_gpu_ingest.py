@@ -145,3 +145,46 @@ def test_cache_round_trip(tmp_path):
     back = ingest.load_cache(str(tmp_path / "cache"))
     for a, b in zip(back, data):
         assert same(a, b)
+
+
+def test_g1_driver_on_dat_files_equals_loadtxt_route(tmp_path, capsys, monkeypatch):
+    """BASELINE configs[2] end to end: a G1 log in the csv2dat .dat layout -> g1_identification.py (device parse + filter +
+    fused identify) prints the reference's tables, and the parameters equal those identified from the same files read by
+    np.loadtxt + scipy.signal.filtfilt (the reference's read_data) to solver precision."""
+    import sys
+    import scipy.signal as signal
+    sys.path.insert(0, H.ROOT)
+    import g1_identification
+    from system_identification_b200 import ingest
+    from system_identification_b200.identify import identify
+    from system_identification_b200.sys_identification import SystemIdentification
+    flat = H.flat_model("g1_12dof")
+    si = SystemIdentification.from_flat_model(flat)
+    dm = si.device_model
+
+    def regress(q, dq, ddq, cnt):
+        from system_identification_b200.ops import to_device
+        dev = tuple(to_device(a) for a in (q, dq, ddq, np.zeros((12, q.shape[1])), cnt))
+        Y = dm.regressor_batch(*dev[:3]).cpu().numpy()
+        _, _, P = dm.projected_batch(*dev, want_P=True)
+        return Y, P.cpu().numpy()
+    data, _, _, _ = H.identifiable_log(flat, 300, 91, regress)          # the log of test_end_to_end_identify_vs_oracle
+    d = str(tmp_path) + os.sep
+    for key, arr in zip(("low_q", "dq", "ddq", "tau", "contact"), data):
+        np.savetxt(d + f"g1_robot_{key}.dat", arr, delimiter="\t", fmt="%.6f")            # what csv2dat.py:50-55 writes
+    # the reference's read_data on the same files (spot_identification.py:9-24)
+    ref = [np.loadtxt(d + f"g1_robot_{k}.dat", delimiter="\t", dtype=np.float32) for k in ("low_q", "dq", "ddq", "tau", "contact")]
+    b, a = signal.butter(5, 0.15, btype="low", analog=False)
+    ref[1], ref[2], ref[3] = (signal.filtfilt(b, a, v, axis=1) for v in ref[1:4])
+    phi_ref = identify(si, *[np.asarray(v, dtype=np.float64) for v in ref])
+    # the device route
+    q, dq, ddq, tau, cnt = ingest.read_data(d, "g1", "butterworth", q_name="low_q")
+    assert same(q, ref[0]) and same(cnt, ref[4])
+    assert np.abs(dq.cpu().numpy() - ref[1]).max() <= 1e-10 * np.abs(ref[1]).max()
+    phi_dev = identify(si, q, dq, ddq, tau, cnt)
+    assert H.rel(phi_dev, phi_ref) <= 1e-6
+    # and the driver itself
+    monkeypatch.setattr(sys, "argv", ["g1_identification.py", "--data", d])
+    g1_identification.main()
+    out = capsys.readouterr().out
+    assert "Identified" in out and "Prior" in out
