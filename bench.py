@@ -115,7 +115,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- clocks
@@ -287,7 +287,7 @@ def run_ours(args):
         if cpu_thr is not None:
             line["cpu_baseline"] = {"value": cpu_thr, "unit": UNIT, "cores": cpu_cores, "kind": "port",
                                     "sample": f"first {min(CPU_SAMPLE, N_SAMPLES)} samples of the same log, oracle/sysid_oracle.c with OpenMP ({cpu_dt:.1f} s)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -341,7 +341,30 @@ def identifiable_tau(flat, dm, dev, seed):
     return out
 
 
+# Rank 0 prints exactly ONE line on stdout.  Libraries do not know that (NCCL writes its version banner to stdout whenever
+# NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the whole run and the JSON line is
+# written to the saved descriptor.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, data)
+
+
 if __name__ == "__main__":
+    capture_stdout()
     a = parse()
     if a.impl == "reference":
         run_reference(a)
