@@ -255,7 +255,24 @@ struct DatParseArgs {
     int round_f32;
 };
 
-// pass 3: every thread converts the fields that START in its 32-byte slice.
+// bit p of the result: byte p of the thread's slice is a delimiter (the field delimiter or a newline)
+__device__ __forceinline__ unsigned dat_slice_delim_mask(const unsigned* sm, int tid, unsigned delim) {
+    unsigned m = 0;
+#pragma unroll
+    for (int w = 0; w < DAT_SLICE / 4; ++w) {
+        const unsigned v = sm[dat_sidx(1 + tid * (DAT_SLICE / 4) + w)];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned c = (v >> (8 * k)) & 0xffu;
+            m |= (unsigned)((c == '\n') | (c == delim)) << (4 * w + k);
+        }
+    }
+    return m;
+}
+
+// pass 3: every thread converts the fields that START in its 32-byte slice.  The starts are collected in a bit mask
+// first and the fields are then converted one ordinal at a time, so the lanes of a warp run the conversion loop together
+// (their j-th fields) instead of one after the other at 32 different byte offsets.
 __global__ void __launch_bounds__(DAT_THREADS)
 dat_parse_kernel(const DatParseArgs g) {
     __shared__ unsigned sm[DAT_SWORDS];
@@ -264,7 +281,8 @@ dat_parse_kernel(const DatParseArgs g) {
     const long long b0 = (long long)blockIdx.x * DAT_BLOCK_BYTES;
     dat_stage(g.text, g.nbytes, b0, sm, tid);
     __syncthreads();
-    int nl, n = dat_slice_delims(sm, tid, g.delim, &nl);
+    const unsigned dmask = dat_slice_delim_mask(sm, tid, g.delim);
+    const int n = __popc(dmask);
     // exclusive scan of the slice counts over the block
     int x = n;
 #pragma unroll
@@ -273,34 +291,36 @@ dat_parse_kernel(const DatParseArgs g) {
     __syncthreads();
     int wbase = 0;
     for (int k = 0; k < warp; ++k) wbase += s_w[k];
-    long long idx = g.blkoff[blockIdx.x] + wbase + x - n;        // index of the field the slice's first byte belongs to
+    const long long idx0 = g.blkoff[blockIdx.x] + wbase + x - n;  // index of the field the slice's first byte belongs to
     const int p0 = tid * DAT_SLICE;
+    // a field starts at the first byte of the text and after every delimiter; bytes past the end of the text start nothing
+    const unsigned prev = dat_byte(sm, p0 - 1);
+    const unsigned first = (b0 + p0 == 0 || prev == '\n' || prev == g.delim) ? 1u : 0u;
+    unsigned smask = (dmask << 1) | first;
+    const long long left = g.nbytes - (b0 + p0);
+    if (left < DAT_SLICE) smask &= (left <= 0) ? 0u : ((1u << (int)left) - 1u);
     long long nbad = 0, firstbad = 0x7fffffffffffffffLL, nragged = 0;
-    for (int p = p0; p < p0 + DAT_SLICE; ++p) {
-        if (b0 + p >= g.nbytes) break;
-        const unsigned prev = dat_byte(sm, p - 1);
-        const bool start = (b0 + p == 0) || prev == '\n' || prev == g.delim;
-        const unsigned c = dat_byte(sm, p);
-        const bool isdelim = (c == '\n') || (c == g.delim);
-        if (start) {
-            // the field ends at the next delimiter or at the end of the text (it may run into the halo)
-            int len = 0;
-            bool closed = false;
-            unsigned term = '\n';
-            for (int e = p; e < DAT_BLOCK_BYTES + DAT_HALO; ++e) {
-                const unsigned ce = dat_byte(sm, e);
-                if (ce == '\n' || ce == g.delim || b0 + e >= g.nbytes) { closed = true; term = (b0 + e >= g.nbytes) ? (unsigned)'\n' : ce; break; }
-                ++len;
-            }
-            double v = __longlong_as_double(0x7ff8000000000000LL);
-            bool ok = closed && len <= DAT_MAXFIELD && dat_convert(DatSmemField{sm, p}, len, &v);
-            const long long row = idx / g.cols, col = idx - row * g.cols;
-            if (!ok) { ++nbad; if (idx < firstbad) firstbad = idx; v = __longlong_as_double(0x7ff8000000000000LL); }
-            if (row < g.rows) g.out[row * g.ld + col] = g.round_f32 ? (double)__double2float_rn(v) : v;
-            // a row ends exactly where a newline is: the terminator of the last column, and of no other
-            if (closed && ((term == '\n') != (col == g.cols - 1))) ++nragged;
+    while (smask) {
+        const int o = __ffs(smask) - 1;
+        smask &= smask - 1;
+        const int p = p0 + o;
+        const long long idx = idx0 + __popc(dmask & ((1u << o) - 1u));
+        // the field ends at the next delimiter or at the end of the text (it may run into the halo)
+        int len = 0;
+        bool closed = false;
+        unsigned term = '\n';
+        for (int e = p; e < DAT_BLOCK_BYTES + DAT_HALO; ++e) {
+            const unsigned ce = dat_byte(sm, e);
+            if (ce == '\n' || ce == g.delim || b0 + e >= g.nbytes) { closed = true; term = (b0 + e >= g.nbytes) ? (unsigned)'\n' : ce; break; }
+            ++len;
         }
-        if (isdelim) ++idx;
+        double v = __longlong_as_double(0x7ff8000000000000LL);
+        const bool ok = closed && len <= DAT_MAXFIELD && dat_convert(DatSmemField{sm, p}, len, &v);
+        const long long row = idx / g.cols, col = idx - row * g.cols;
+        if (!ok) { ++nbad; if (idx < firstbad) firstbad = idx; v = __longlong_as_double(0x7ff8000000000000LL); }
+        if (row < g.rows) g.out[row * g.ld + col] = g.round_f32 ? (double)__double2float_rn(v) : v;
+        // a row ends exactly where a newline is: the terminator of the last column, and of no other
+        if (closed && ((term == '\n') != (col == g.cols - 1))) ++nragged;
     }
     // block totals -> header (integer atomics: order-independent)
     if (nbad | nragged) {
