@@ -449,14 +449,14 @@ int sysid_filtfilt(const double* b_host, int32_t nb, const double* a_host, int32
     g.fstate = Y1 + (size_t)channels * g.Next;
     g.sstate = g.fstate + (size_t)channels * g.nchunks * FILT_MAXS;
     const long long items = (long long)channels * g.nchunks;
-    const unsigned grid = (unsigned)((items + 127) / 128);
+    const unsigned grid = (unsigned)((items + FILT_THREADS - 1) / FILT_THREADS);
     for (int dir = 0; dir < 2; ++dir) {
         g.backward = dir;
         g.x = dir ? Y1 : x;
         g.y = dir ? y : Y1;
-        filt_chunk_kernel<0><<<grid, 128, 0, st>>>(c, g);
-        filt_scan_kernel<<<(channels + 63) / 64, 64, 0, st>>>(c, g);
-        filt_chunk_kernel<1><<<grid, 128, 0, st>>>(c, g);
+        filt_chunk_kernel<0><<<grid, FILT_THREADS, 0, st>>>(c, g);
+        filt_scan_kernel<<<channels, FILT_SCAN_THREADS, 0, st>>>(c, g);
+        filt_chunk_kernel<1><<<grid, FILT_THREADS, 0, st>>>(c, g);
         CUDA_TRY(cudaGetLastError());
     }
     return SYSID_OK;
