@@ -27,6 +27,7 @@ struct FiltCoef {
     double a[FILT_MAXS + 1];          // a[0] == 1 (normalised on the host)
     double zi[FILT_MAXS];
     double phiL[FILT_MAXS][FILT_MAXS];   // Phi^FILT_CHUNK
+    double phiM[FILT_MAXS][FILT_MAXS];   // Phi^(FILT_CHUNK * seg): one segment of the chaining kernel
 };
 
 struct FiltArgs {
@@ -36,6 +37,7 @@ struct FiltArgs {
     double* sstate;         // [channels][nchunks][FILT_MAXS] true chunk-initial states
     long long N, ld, Next;
     int channels, padlen, nchunks, backward;
+    int seg;                // chunks per thread of the chaining kernel: ceil(nchunks / FILT_SCAN_THREADS)
     int pad_float32;        // the log was float32 (np.loadtxt(dtype=float32), reference quirk Q8): scipy then forms the odd
                             // extension in float32 before lfilter widens it -- reproduce that rounding of the pad samples
 };
@@ -132,45 +134,60 @@ __global__ void __launch_bounds__(FILT_THREADS) filt_chunk_kernel(const __grid_c
     }
 }
 
-// Kernel S: one block per channel.  The chain s_{k+1} = Phi^L s_k + f_k is sequential, but its inputs are not: the block
-// stages FILT_SCAN_TILE chunk states at a time in shared memory (coalesced), thread 0 chains through the tile replacing
-// every f_k by the true initial state s_k, and the block writes the tile back.  (One thread per channel reading f_k from
-// global memory paid a DRAM/L2 round trip per chunk: ~2 ms per direction for 3 907 chunks.)
-constexpr int FILT_SCAN_TILE = 512;
+// Kernel S: one block per channel chains the chunks, s_{k+1} = Phi^L s_k + f_k, as a two-level scan of these affine maps:
+// every thread folds its segment of `seg` consecutive chunks from a zero state, thread 0 chains the FILT_SCAN_THREADS
+// segment results with Phi^(L seg), and every thread re-runs its segment from its true initial state, writing s_k.
+// (History of this kernel, 48 channels x 3 907 chunks: one thread per channel reading f_k from global memory, an L2 round
+// trip per chunk: ~2 ms per direction; the same chain out of shared memory: 0.51 ms; two levels: see DESIGN 4.4.)
 constexpr int FILT_SCAN_THREADS = 256;
 
+__device__ __forceinline__ void filt_affine(const double (&phi)[FILT_MAXS][FILT_MAXS], double (&s)[FILT_MAXS], const double* __restrict__ f) {
+    double nx[FILT_MAXS];
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) nx[e] = f[e];
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e)
+#pragma unroll
+        for (int q = 0; q < FILT_MAXS; ++q) nx[e] = fma(phi[e][q], s[q], nx[e]);
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) s[e] = nx[e];
+}
+
 __global__ void __launch_bounds__(FILT_SCAN_THREADS) filt_scan_kernel(const __grid_constant__ FiltCoef c, const FiltArgs g) {
-    __shared__ double buf[FILT_SCAN_TILE * FILT_MAXS];
+    __shared__ double segs[FILT_SCAN_THREADS][FILT_MAXS + 1];
     const int ch = blockIdx.x, tid = threadIdx.x;
     if (ch >= g.channels) return;
+    const double* fs = g.fstate + (size_t)ch * g.nchunks * FILT_MAXS;
+    double* ss = g.sstate + (size_t)ch * g.nchunks * FILT_MAXS;
+    const int k0 = tid * g.seg, k1 = (k0 + g.seg < g.nchunks) ? k0 + g.seg : g.nchunks;
     double s[FILT_MAXS];
+    // level 1: the segment from a zero state
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) s[e] = 0.0;
+    for (int k = k0; k < k1; ++k) filt_affine(c.phiL, s, fs + (size_t)k * FILT_MAXS);
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) segs[tid][e] = s[e];
+    __syncthreads();
+    // level 2: chain the segments; segs[j] becomes the true state at the start of segment j
     if (tid == 0) {
         const double x0 = filt_input(g, ch, 0);
 #pragma unroll
         for (int e = 0; e < FILT_MAXS; ++e) s[e] = c.zi[e] * x0;
-    }
-    const double* fs = g.fstate + (size_t)ch * g.nchunks * FILT_MAXS;
-    double* ss = g.sstate + (size_t)ch * g.nchunks * FILT_MAXS;
-    for (int k0 = 0; k0 < g.nchunks; k0 += FILT_SCAN_TILE) {
-        const int nk = (g.nchunks - k0 < FILT_SCAN_TILE) ? g.nchunks - k0 : FILT_SCAN_TILE;
-        for (int e = tid; e < nk * FILT_MAXS; e += FILT_SCAN_THREADS) buf[e] = fs[(size_t)k0 * FILT_MAXS + e];
-        __syncthreads();
-        if (tid == 0) {
-            for (int k = 0; k < nk; ++k) {
-                double nx[FILT_MAXS];
+        for (int j = 0; j < FILT_SCAN_THREADS; ++j) {
+            double f[FILT_MAXS];
 #pragma unroll
-                for (int e = 0; e < FILT_MAXS; ++e) { nx[e] = buf[k * FILT_MAXS + e]; buf[k * FILT_MAXS + e] = s[e]; }
-#pragma unroll
-                for (int e = 0; e < FILT_MAXS; ++e)
-#pragma unroll
-                    for (int f = 0; f < FILT_MAXS; ++f) nx[e] = fma(c.phiL[e][f], s[f], nx[e]);
-#pragma unroll
-                for (int e = 0; e < FILT_MAXS; ++e) s[e] = nx[e];
-            }
+            for (int e = 0; e < FILT_MAXS; ++e) { f[e] = segs[j][e]; segs[j][e] = s[e]; }
+            filt_affine(c.phiM, s, f);
         }
-        __syncthreads();
-        for (int e = tid; e < nk * FILT_MAXS; e += FILT_SCAN_THREADS) ss[(size_t)k0 * FILT_MAXS + e] = buf[e];
-        __syncthreads();
+    }
+    __syncthreads();
+    // level 3: the segment again, from its true initial state
+#pragma unroll
+    for (int e = 0; e < FILT_MAXS; ++e) s[e] = segs[tid][e];
+    for (int k = k0; k < k1; ++k) {
+#pragma unroll
+        for (int e = 0; e < FILT_MAXS; ++e) ss[(size_t)k * FILT_MAXS + e] = s[e];
+        filt_affine(c.phiL, s, fs + (size_t)k * FILT_MAXS);
     }
 }
 

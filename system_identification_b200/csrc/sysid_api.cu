@@ -439,12 +439,28 @@ int sysid_filtfilt(const double* b_host, int32_t nb, const double* a_host, int32
             std::memcpy(P, Q, sizeof(P));
         }
         for (int i = 0; i < FILT_MAXS; ++i) for (int j = 0; j < FILT_MAXS; ++j) c.phiL[i][j] = (double)P[i][j];
+        // Phi^(FILT_CHUNK seg) for the segments of the chaining kernel: binary powering of Phi^FILT_CHUNK
+        const long long next = N + 2 * (long long)padlen;
+        const int nchunks = (int)((next + FILT_CHUNK - 1) / FILT_CHUNK);
+        int seg = (nchunks + FILT_SCAN_THREADS - 1) / FILT_SCAN_THREADS;
+        long double R[FILT_MAXS][FILT_MAXS] = {};
+        for (int i = 0; i < FILT_MAXS; ++i) R[i][i] = 1.0L;
+        for (int e = seg; e > 0; e >>= 1) {
+            if (e & 1) {
+                for (int i = 0; i < FILT_MAXS; ++i) for (int j = 0; j < FILT_MAXS; ++j) { long double t = 0; for (int k = 0; k < FILT_MAXS; ++k) t += R[i][k] * P[k][j]; Q[i][j] = t; }
+                std::memcpy(R, Q, sizeof(R));
+            }
+            for (int i = 0; i < FILT_MAXS; ++i) for (int j = 0; j < FILT_MAXS; ++j) { long double t = 0; for (int k = 0; k < FILT_MAXS; ++k) t += P[i][k] * P[k][j]; Q[i][j] = t; }
+            std::memcpy(P, Q, sizeof(P));
+        }
+        for (int i = 0; i < FILT_MAXS; ++i) for (int j = 0; j < FILT_MAXS; ++j) c.phiM[i][j] = (double)R[i][j];
     }
     cudaStream_t st = (cudaStream_t)stream;
     FiltArgs g{};
     g.N = N; g.ld = ld; g.Next = N + 2 * (long long)padlen; g.channels = channels; g.padlen = padlen;
     g.pad_float32 = pad_float32 ? 1 : 0;
     g.nchunks = (int)((g.Next + FILT_CHUNK - 1) / FILT_CHUNK);
+    g.seg = (g.nchunks + FILT_SCAN_THREADS - 1) / FILT_SCAN_THREADS;
     double* Y1 = (double*)workspace;
     g.fstate = Y1 + (size_t)channels * g.Next;
     g.sstate = g.fstate + (size_t)channels * g.nchunks * FILT_MAXS;
