@@ -54,7 +54,7 @@ static_assert(GRAM_SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 constexpr int TILE_SAMPLES = 4;
 constexpr int TILE_ROWS = TILE_SAMPLES * MAXV;
 constexpr int TILE_DOUBLES = TILE_ROWS * TILE_LD;
-constexpr int RSB = 16;                        // rmse kernel: samples per super-batch
+constexpr int RSB = 24;                        // rmse kernel: samples per super-batch
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -429,12 +429,18 @@ sample_batch_kernel(const __grid_constant__ DevModel M, const BatchArgs args) {
 
 // ------------------------------------------------------------------------------------------------------------
 // tau-prediction error pass (reference print_tau_prediction_rmse): e_i = (P Y phi - P S^T tau)[6:]
-// Same F/C phases; instead of the M phase each row of the tile is dotted with [phi; 0; 0; -1].
+// Same F phases and explicit projector as before, but Y phi is formed the way recursive Newton-Euler forms it instead of
+// row by row: every body's wrench (f; n) = bodyRegressor(omega, alpha, acc) phi_i in closed form (the transpose of
+// body_row: f = m acc + alpha x h + omega x (omega x h), n = h x acc + I alpha + omega x (I omega), with phi_i read in the
+// regressor's column order), carried to the base frame (F = R f, N = R n + p x F), summed over the subtree of every joint and
+// projected on the joint's Pluecker axis; the six base rows are the total wrench.  ~1.5 k flops per sample instead of the
+// 28 k of eighteen projected tile rows, and no tile.  (69 -> see profiles/ for the measured rate.)
 // partial per CTA: [sum_i ||e_i||^2, per-joint sum of squares (MAXD), count]
 // ------------------------------------------------------------------------------------------------------------
 constexpr int RMSE_PARTIAL = MAXD + 2;
-constexpr size_t RMSE_SMEM_BYTES = sizeof(double) * (TILE_DOUBLES + RSB * CX_STRIDE);
-static_assert(RSB * (SC_STRIDE + IN_CHANNELS) <= TILE_DOUBLES, "rmse scratch aliases the tile");
+constexpr int RMSE_FRONT = RSB * (SC_STRIDE + IN_CHANNELS);          // F-phase scratch + staged inputs; wrenches afterwards
+static_assert(RSB * (MAXB * 6 + MAXV) <= RMSE_FRONT, "wrenches and the row vector fit the scratch region");
+constexpr size_t RMSE_SMEM_BYTES = sizeof(double) * (RMSE_FRONT + RSB * CX_STRIDE);
 
 struct RmseArgs {
     SampleIO io; long long N; const double* phi; double* partial;
@@ -443,16 +449,17 @@ struct RmseArgs {
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
     extern __shared__ __align__(16) double smem[];
-    double* tile = smem;
-    double* ctx = smem + TILE_DOUBLES;
-    double* scr = smem;                        // aliases the tile
+    double* ctx = smem + RMSE_FRONT;
+    double* scr = smem;
     double* inp = smem + RSB * SC_STRIDE;
+    double* Wb = smem;                         // [RSB][MAXB][6] base-frame wrenches (after the F phases)
+    double* G = smem + RSB * MAXB * 6;         // [RSB][MAXV]    Y phi - S^T tau
     __shared__ double s_x[CW];
     __shared__ double s_acc[RMSE_PARTIAL];
     __shared__ int s_bad[RSB];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
-    const int np = M.nparams, nd = M.nd;
-    if (tid < CW) s_x[tid] = (tid < np) ? args.phi[tid] : ((tid == np + 2 * nd) ? -1.0 : 0.0);
+    const int tid = threadIdx.x, t = tid;
+    const int np = M.nparams, nd = M.nd, nb = M.nb, nv = M.nv;
+    if (tid < CW) s_x[tid] = (tid < np) ? args.phi[tid] : 0.0;
     if (tid < RMSE_PARTIAL) s_acc[tid] = 0.0;
     if (tid < RSB) s_bad[tid] = 0;
     __shared__ double s_stat[3];
@@ -465,26 +472,77 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
         const long long base = sb * RSB;
         SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_PROJ, )
         if (t < RSB) s_bad[t] = 0;
-        const int nsub = (int)min((long long)(RSB / TILE_SAMPLES), (args.N - base + TILE_SAMPLES - 1) / TILE_SAMPLES);
-        for (int sub = 0; sub < nsub; ++sub) {
-            phase_fill_chains<TILE_SAMPLES, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * TILE_SAMPLES, 1, t);
-            __syncthreads();
-            for (int row = warp; row < TILE_ROWS; row += GRAM_WARPS) {
-                const int rr = row % MAXV;
-                if (rr < 6 || rr >= M.nv) continue;
-                const long long i = base + sub * TILE_SAMPLES + row / MAXV;
-                if (i >= args.N) continue;
-                double d = 0.0;
-                for (int col = lane; col < CW; col += 32) {
-                    const double xv = s_x[col];
-                    if (xv != 0.0) d += tile[row * TILE_LD + col] * xv;
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-                if (lane == 0) { atomicAdd(&s_acc[0], d * d); atomicAdd(&s_acc[1 + (rr - 6)], d * d); }
+        // wrench of every body in the base frame: thread per (sample, body)
+        for (int it = t; it < RSB * nb; it += GRAM_THREADS) {
+            const int s = it / nb, bi = it - s * nb;           // body bi <-> joint bi + 1
+            if (base + s >= args.N) continue;
+            const double* c = ctx + s * CX_STRIDE;
+            const double* b9 = c + CX_B9 + B9S * bi;
+            const double* ph = s_x + 10 * bi;
+            const double w0 = b9[0], w1 = b9[1], w2 = b9[2], al0 = b9[3], al1 = b9[4], al2 = b9[5], ac0 = b9[6], ac1 = b9[7], ac2 = b9[8];
+            const double m = ph[0], h0 = ph[1], h1 = ph[2], h2 = ph[3];
+            const double Ixx = ph[4], Ixy = ph[5], Iyy = ph[6], Ixz = ph[7], Iyz = ph[8], Izz = ph[9];     // the regressor's column order
+            // f = m acc + alpha x h + omega x (omega x h)
+            const double wh0 = w1 * h2 - w2 * h1, wh1 = w2 * h0 - w0 * h2, wh2 = w0 * h1 - w1 * h0;
+            const double f0 = m * ac0 + (al1 * h2 - al2 * h1) + (w1 * wh2 - w2 * wh1);
+            const double f1 = m * ac1 + (al2 * h0 - al0 * h2) + (w2 * wh0 - w0 * wh2);
+            const double f2 = m * ac2 + (al0 * h1 - al1 * h0) + (w0 * wh1 - w1 * wh0);
+            // n = h x acc + I alpha + omega x (I omega)
+            const double Iw0 = Ixx * w0 + Ixy * w1 + Ixz * w2, Iw1 = Ixy * w0 + Iyy * w1 + Iyz * w2, Iw2 = Ixz * w0 + Iyz * w1 + Izz * w2;
+            const double n0 = (h1 * ac2 - h2 * ac1) + (Ixx * al0 + Ixy * al1 + Ixz * al2) + (w1 * Iw2 - w2 * Iw1);
+            const double n1 = (h2 * ac0 - h0 * ac2) + (Ixy * al0 + Iyy * al1 + Iyz * al2) + (w2 * Iw0 - w0 * Iw2);
+            const double n2 = (h0 * ac1 - h1 * ac0) + (Ixz * al0 + Iyz * al1 + Izz * al2) + (w0 * Iw1 - w1 * Iw0);
+            double* out = Wb + (s * MAXB + bi) * 6;
+            if (bi == 0) { out[0] = f0; out[1] = f1; out[2] = f2; out[3] = n0; out[4] = n1; out[5] = n2; }
+            else {
+                const double* X = c + CX_X + 12 * (bi - 1);     // R (row-major) and p of the body's joint relative to the base
+                const double F0 = X[0] * f0 + X[1] * f1 + X[2] * f2, F1 = X[3] * f0 + X[4] * f1 + X[5] * f2, F2 = X[6] * f0 + X[7] * f1 + X[8] * f2;
+                const double p0 = X[9], p1 = X[10], p2 = X[11];
+                out[0] = F0; out[1] = F1; out[2] = F2;
+                out[3] = X[0] * n0 + X[1] * n1 + X[2] * n2 + (p1 * F2 - p2 * F1);
+                out[4] = X[3] * n0 + X[4] * n1 + X[5] * n2 + (p2 * F0 - p0 * F2);
+                out[5] = X[6] * n0 + X[7] * n1 + X[8] * n2 + (p0 * F1 - p1 * F0);
             }
-            __syncthreads();
         }
+        __syncthreads();
+        // (Y phi - S^T tau)[c]: thread per (sample, row)
+        for (int it = t; it < RSB * nv; it += GRAM_THREADS) {
+            const int s = it / nv, ci = it - s * nv;
+            if (base + s >= args.N) continue;
+            const double* c = ctx + s * CX_STRIDE;
+            const double* ws = Wb + s * MAXB * 6;
+            double g;
+            if (ci < 6) {
+                g = 0.0;
+                for (int bi = 0; bi < nb; ++bi) g += ws[bi * 6 + ci];
+            } else {
+                const int j = ci - 4;                            // joint of the row (row 6 <-> joint 2)
+                const unsigned mask = M.submask[j];
+                double S[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+                for (int bi = 1; bi < nb; ++bi)
+                    if ((mask >> (bi + 1)) & 1u) {
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) S[k] += ws[bi * 6 + k];
+                    }
+                const double* a = c + CX_A + 6 * (j - 2);
+                g = a[0] * S[0] + a[1] * S[1] + a[2] * S[2] + a[3] * S[3] + a[4] * S[4] + a[5] * S[5] - c[CX_TAU + (ci - 6)];
+            }
+            G[s * MAXV + ci] = g;
+        }
+        __syncthreads();
+        // e = (P g)[6 + k], thread per (sample, joint)
+        for (int it = t; it < RSB * nd; it += GRAM_THREADS) {
+            const int s = it / nd, k = it - s * nd, r = 6 + k;
+            if (base + s >= args.N) continue;
+            const double* c = ctx + s * CX_STRIDE;
+            const double* P = c + CX_P;
+            const double* gs = G + s * MAXV;
+            double e = 0.0;
+            for (int cc = 0; cc < nv; ++cc) e = fma(P[pk(r, cc)], gs[cc], e);
+            e *= c[CX_W];
+            atomicAdd(&s_acc[0], e * e); atomicAdd(&s_acc[1 + k], e * e);
+        }
+        __syncthreads();
     }
     if (tid < RMSE_PARTIAL - 1) args.partial[(size_t)blockIdx.x * RMSE_PARTIAL + tid] = s_acc[tid];
 }

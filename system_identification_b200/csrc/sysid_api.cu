@@ -169,6 +169,8 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
     }
     // tile fill: (chains x split + 1) lane groups of 96 lanes; use up to two groups per chain while all fit one pass
     M.fill_split = ((M.nfch * 2 + 1) * 96 <= GRAM_THREADS) ? 2 : 1;
+    for (int i = 1; i < d->njoints; ++i)
+        for (int k = i; k >= 1; k = M.parent[k]) M.submask[k] |= 1u << i;       // i is in the subtree of each of its ancestors
     int rc = device_sm_count(&m->sm_count);
     if (rc != SYSID_OK) { delete m; return rc; }
     *out = m;
