@@ -38,7 +38,6 @@ struct DevModel {
     int32_t fch_len[MAXD];
     int32_t fch_own[MAXD];
     int32_t fch[MAXD][MAXCH];
-    int32_t fchp[MAXD][MAXCH];       // fch | (c (c + 1) / 2 << 8) with c = 4 + fch: packed-triangle offset of the joint's P column
     int32_t fill_split;              // bodies of a chain are dealt round-robin to this many lane groups of the tile fill
     uint32_t submask[MAXJ];          // bit i set: body (joint) i lies in the subtree of joint j, j itself included (evaluation pass)
 };

@@ -674,96 +674,13 @@ __device__ __forceinline__ void body_row(const double* __restrict__ b9, double e
     for (int k = 0; k < 5; ++k) d2[k] = make_double2(o[2 * k], o[2 * k + 1]);
 }
 
-// ---------------------------------------------------------------------------------------------- tile fill, chain walk
-// Lanes are grouped by (leaf chain, split index): a lane owns one (sample, row) of its group, walks the chain from the
-// root accumulating (dl; da) incrementally (6 FMAs per joint instead of re-summing the ancestors per body), and emits
-// the ten entries of every body e of the chain with e % split == its split index.  One more group emits the root body
-// and the friction / torque / padding columns.  Groups are padded to whole warps so that a warp never diverges.
-template <int TS, int LD, int NT>
-__device__ __forceinline__ void phase_fill_chains(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
-                                                  int s0, int friction, int t) {
-    constexpr int GL = ((TS * MAXV + 31) / 32) * 32;     // lanes per group
-    static_assert(NT % 32 == 0 && GL <= NT, "groups are whole warps");
-    const int split = M.fill_split, ngroups = M.nfch * split;
-    const int np = M.nparams, nd = M.nd;
-    const int l = t % GL;
-    if (l >= TS * MAXV) return;
-    const int sl = l / MAXV, r = l - sl * MAXV;
-    const double* c = ctx + (s0 + sl) * CX_STRIDE;
-    const double* P = c + CX_P;
-    const double wsq = c[CX_W];
-    double* row = tile + (sl * MAXV + r) * LD;
-    auto Pe = [&](int cc) { return (cc <= r) ? P[r * (r + 1) / 2 + cc] : P[cc * (cc + 1) / 2 + r]; };
-    for (int g = t / GL; g <= ngroups; g += NT / GL) {
-        if (g < ngroups) {
-            const int ch = (split == 1) ? g : (g >> 1), q = (split == 1) ? 0 : (g & 1);      // split is 1 or 2
-            const int len = M.fch_len[ch], own = M.fch_own[ch];
-            // body e of the chain is emitted by split index e mod split, tracked by a counter (no integer division)
-            if (wsq == 0.0) {
-                for (int e = 0, turn = 0; e < len; ++e, turn = (turn + 1 == split) ? 0 : turn + 1)
-                    if (e >= own && turn == q) {
-                        double2* d2 = reinterpret_cast<double2*>(row + 10 * (M.fch[ch][e] - 1));
-#pragma unroll
-                        for (int k = 0; k < 5; ++k) d2[k] = make_double2(0.0, 0.0);
-                    }
-                continue;
-            }
-            double d[6];           // (dl; da), pre-multiplied by sqrt(weight)
-#pragma unroll
-            for (int k = 0; k < 6; ++k) d[k] = Pe(k) * wsq;
-            const int rowbase = r * (r + 1) / 2;
-            for (int e = 0, turn = 0; e < len; ++e, turn = (turn + 1 == split) ? 0 : turn + 1) {
-                const int jp = M.fchp[ch][e], j = jp & 0xff, cc = 4 + j;
-                const double pj = P[(cc <= r) ? rowbase + cc : (jp >> 8) + r] * wsq;
-                const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { const double2 ak = A2[k]; d[2 * k] = fma(pj, ak.x, d[2 * k]); d[2 * k + 1] = fma(pj, ak.y, d[2 * k + 1]); }
-                if (e >= own && turn == q) {
-                    const double2* X2 = reinterpret_cast<const double2*>(c + CX_X + 12 * (j - 2));
-                    const double2 x01 = X2[0], x23 = X2[1], x45 = X2[2], x67 = X2[3], x8p = X2[4], p12 = X2[5];
-                    const double p0 = x8p.y, p1 = p12.x, p2 = p12.y;
-                    const double u0 = d[0] + (d[4] * p2 - d[5] * p1), u1 = d[1] + (d[5] * p0 - d[3] * p2), u2 = d[2] + (d[3] * p1 - d[4] * p0);
-                    // (el; ea) = (R^T u; R^T da), R row-major in x01..x8p
-                    const double el0 = x01.x * u0 + x23.y * u1 + x67.x * u2, el1 = x01.y * u0 + x45.x * u1 + x67.y * u2, el2 = x23.x * u0 + x45.y * u1 + x8p.x * u2;
-                    const double ea0 = x01.x * d[3] + x23.y * d[4] + x67.x * d[5], ea1 = x01.y * d[3] + x45.x * d[4] + x67.y * d[5], ea2 = x23.x * d[3] + x45.y * d[4] + x8p.x * d[5];
-                    body_row(c + CX_B9 + B9S * (j - 1), el0, el1, el2, ea0, ea1, ea2, row + 10 * (j - 1));
-                }
-            }
-        } else {
-            // root body (its Pluecker rows are the identity, pose = identity) ...
-            if (wsq == 0.0) {
-#pragma unroll
-                for (int k = 0; k < 5; ++k) reinterpret_cast<double2*>(row)[k] = make_double2(0.0, 0.0);
-            } else {
-                body_row(c + CX_B9, Pe(0) * wsq, Pe(1) * wsq, Pe(2) * wsq, Pe(3) * wsq, Pe(4) * wsq, Pe(5) * wsq, row);
-            }
-            // ... and the friction / torque columns plus the zero padding
-            double tau = 0.0;
-            const int ntail = friction ? 2 * nd + 1 : 1;
-            if (wsq != 0.0) {
-                for (int jj = 0; jj < nd; ++jj) {
-                    const double pj = Pe(6 + jj) * wsq;
-                    tau = fma(pj, c[CX_TAU + jj], tau);
-                    if (friction) {
-                        const double dqv = c[CX_DQ + jj];
-                        const double sg = (dqv > 0.0) ? 1.0 : ((dqv < 0.0) ? -1.0 : (dqv == 0.0 ? 0.0 : dqv));   // numpy sign: sign(nan)=nan
-                        row[np + jj] = pj * dqv;
-                        row[np + nd + jj] = pj * sg;
-                    }
-                }
-            } else if (friction) {
-                for (int jj = 0; jj < 2 * nd; ++jj) row[np + jj] = 0.0;
-            }
-            // without friction columns the torque column follows the body columns directly
-            row[np + ntail - 1] = tau;
-            for (int k = np + ntail; k < CW; ++k) row[k] = 0.0;
-        }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------- tile fill, null-space rows
-// As phase_fill_chains, but a lane owns one (sample, basis vector q_k) instead of one (sample, dof row): its tile row is
-// q_k^T Ytilde, so a sample contributes nq = 18 - rank(J_c) rows, packed one after the other.  Returns (to every
+// Lanes are grouped by (leaf chain, split index): a lane owns one (sample, basis vector q_k) of its group, walks the chain
+// from the root accumulating (dl; da) = q_k^T [I_6; a_j ...] incrementally (6 FMAs per joint instead of re-summing the
+// ancestors per body) and emits the ten entries of every body e of the chain with e % split == its split index.  One
+// more group emits the root body and the friction / torque / padding columns.  Groups are padded to whole warps so that
+// a warp never diverges.  Its tile row is q_k^T Ytilde, so a sample contributes nq = 18 - rank(J_c) rows, packed one
+// after the other.  Returns (to every
 // thread) the number of k-steps of 4 rows the round occupies; rows up to that multiple of 4 are zero-filled.
 template <int TS, int LD, int NT>
 __device__ __forceinline__ int phase_fill_q(const DevModel& M, const double* __restrict__ ctx, double* __restrict__ tile,
@@ -784,7 +701,10 @@ __device__ __forceinline__ int phase_fill_q(const DevModel& M, const double* __r
     for (int e = t; e < (4 * ksteps - rows) * CW; e += NT) tile[(rows + e / CW) * LD + (e % CW)] = 0.0;   // pad rows of the last k-step
     const int l = t % GL;
     if (l >= TS * MAXV) return ksteps;
-    const int sl = l / MAXV, k = l - sl * MAXV;
+    // basis-vector index slowest: a stance sample has at most 15 vectors, so slots 4 k + sl with k >= 15 (the group's third
+    // warp) are all idle unless a sample of the round is in flight, and that warp retires at once instead of running the
+    // whole walk for the five lanes a sample-major order left in it
+    const int k = l / TS, sl = l - k * TS;
     int rowi = 0, nq = 0;
 #pragma unroll
     for (int u = 0; u < TS; ++u) if (u == sl) { rowi = off[u] + k; nq = off[u + 1] - off[u]; }

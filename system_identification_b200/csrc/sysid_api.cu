@@ -159,7 +159,7 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
             if (has_child[j]) continue;
             const int c = M.nfch++;
             int len = depth[j], e = len;
-            for (int k = j; k > 1; k = M.parent[k]) { M.fch[c][--e] = k; M.fchp[c][e] = k | (((4 + k) * (5 + k) / 2) << 8); }
+            for (int k = j; k > 1; k = M.parent[k]) M.fch[c][--e] = k;
             M.fch_len[c] = len;
             int own = 0;
             while (own < len && owned[M.fch[c][own]]) ++own;
