@@ -26,8 +26,7 @@ HERE = os.path.dirname(os.path.realpath(__file__))
 def read_csv_log(csv_path, q_name, filter_type):
     """Logger CSV -> (q, dq, ddq, tau, contact) on the device: the reference's low_ddq_contact_tick.py + csv2dat.py +
     read_data composed without intermediate files (all 12 motors in ddq: csv2dat.py:36 drops motor 0)."""
-    import pandas as pd
-    log = ingest.csv_to_log(pd.read_csv(csv_path))
+    log = ingest.csv_to_log(ingest.load_csv(csv_path))         # the CSV text is parsed on the device (no pandas)
     q, dq, ddq, tau, cnt = log[q_name], log["dq"], log["ddq"], log["tau"], log["contact"]
     # the first row of the finite differences is NaN (low_ddq_contact_tick.py:38-43 leaves it so): drop that sample
     q, dq, ddq, tau, cnt = (a[:, 1:].contiguous() for a in (q, dq, ddq, tau, cnt))

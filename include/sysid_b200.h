@@ -25,7 +25,7 @@
  *   sysid_tsqr                Solver.solve_llsq_svd: np.linalg.svd of the stacked regressor   reference src/solver.py:32-39
  *                             (the stack is first reduced to its (c+1) x (c+1) triangular factor on the device)
  *   sysid_physical_consistency  SystemIdentification.get_physical_consistency   reference src/sys_identification.py:324-389
- *   sysid_dat_scan / sysid_dat_parse   np.loadtxt(path + name + "_robot_q.dat", delimiter='\t', dtype=np.float32): the five
+ *   sysid_dat_scan / sysid_dat_parse / sysid_dat_parse_ex   np.loadtxt(path + name + "_robot_q.dat", delimiter='\t', dtype=np.float32): the five
  *                             loads of read_data   reference spot_identification.py:9-14, demo/solo_identification.py:9-14
  *   sysid_fd_rate / sysid_contact_from_tau   the row loops of calculate_low_motor_ddq (joint and body angular
  *                             accelerations by finite differences of the tick, contact labels from the ankle torques)
@@ -176,6 +176,13 @@ int sysid_dat_scan(const void* text, int64_t nbytes, int32_t delimiter, void* wo
                    int64_t* dims_host, void* stream);
 int sysid_dat_parse(const void* text, int64_t nbytes, int32_t delimiter, void* workspace, size_t workspace_bytes,
                     int64_t rows, int64_t cols, double* out, int64_t ld, int32_t round_float32, int64_t* info_host, void* stream);
+/* The same with options, for the logger CSV the G1 scripts start from (pd.read_csv, reference g1-data/csv2dat.py:15,
+ * low_ddq_contact_tick.py:21; pass the text AFTER its header line, delimiter ','): SYSID_DAT_TRANSPOSE writes element
+ * (row, col) to out[col * ld + row], so a row-per-sample CSV lands channel-major; SYSID_DAT_EMPTY_IS_NAN reads an empty
+ * field as NaN (what pandas does) instead of counting it as an error (what np.loadtxt does). */
+enum { SYSID_DAT_ROUND_FLOAT32 = 1, SYSID_DAT_TRANSPOSE = 2, SYSID_DAT_EMPTY_IS_NAN = 4 };
+int sysid_dat_parse_ex(const void* text, int64_t nbytes, int32_t delimiter, void* workspace, size_t workspace_bytes,
+                       int64_t rows, int64_t cols, double* out, int64_t ld, int32_t flags, int64_t* info_host, void* stream);
 
 /* The row loop of calculate_low_motor_ddq (reference g1-data/low_ddq_contact_tick.py:46-70), all channels at once:
  * y[ch][0] = NaN; for i >= 1 with dt = tick[i] - tick[i-1], dx = x[ch][i] - x[ch][i-1]:  dt > 0 -> (dx * scale) / dt;

@@ -77,6 +77,7 @@ _SIGNATURES = {
     "sysid_dat_workspace_bytes": (C.c_size_t, [C.c_int64]),
     "sysid_dat_scan": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_size_t, _P, _P]),
     "sysid_dat_parse": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_size_t, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P]),
+    "sysid_dat_parse_ex": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_size_t, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P]),
     "sysid_fd_rate": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_double, _P]),
     "sysid_contact_from_tau": (C.c_int, [_P, _P, C.c_int64, C.c_double, C.c_double, _P]),
     "sysid_round_dat": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P]),

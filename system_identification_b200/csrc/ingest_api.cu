@@ -74,15 +74,24 @@ int sysid_dat_scan(const void* text, int64_t nbytes, int32_t delimiter, void* wo
 
 int sysid_dat_parse(const void* text, int64_t nbytes, int32_t delimiter, void* workspace, size_t workspace_bytes,
                     int64_t rows, int64_t cols, double* out, int64_t ld, int32_t round_float32, int64_t* info_host, void* stream) {
+    return sysid_dat_parse_ex(text, nbytes, delimiter, workspace, workspace_bytes, rows, cols, out, ld,
+                              round_float32 ? SYSID_DAT_ROUND_FLOAT32 : 0, info_host, stream);
+}
+
+int sysid_dat_parse_ex(const void* text, int64_t nbytes, int32_t delimiter, void* workspace, size_t workspace_bytes,
+                       int64_t rows, int64_t cols, double* out, int64_t ld, int32_t flags, int64_t* info_host, void* stream) {
+    const int32_t round_float32 = flags & SYSID_DAT_ROUND_FLOAT32;
+    const bool transpose = (flags & SYSID_DAT_TRANSPOSE) != 0;
     if (!text || !workspace || !out) return fail(SYSID_ERR_INVALID, "null argument");
-    if (nbytes <= 0 || rows <= 0 || cols <= 0 || ld < cols) return fail(SYSID_ERR_INVALID, "bad nbytes/rows/cols/ld");
+    if (nbytes <= 0 || rows <= 0 || cols <= 0 || ld < (transpose ? rows : cols)) return fail(SYSID_ERR_INVALID, "bad nbytes/rows/cols/ld");
     if (workspace_bytes < sysid_dat_workspace_bytes(nbytes)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     DatHeader* hdr = (DatHeader*)workspace;
     DatParseArgs g;
     g.text = (const unsigned char*)text; g.nbytes = nbytes; g.delim = (unsigned)delimiter;
     g.blkoff = (const long long*)((char*)workspace + sizeof(DatHeader)); g.hdr = hdr;
-    g.rows = rows; g.cols = cols; g.out = out; g.ld = ld; g.round_f32 = round_float32;
+    g.rows = rows; g.cols = cols; g.out = out; g.ld = ld; g.round_f32 = round_float32 ? 1 : 0;
+    g.transpose = transpose ? 1 : 0; g.empty_nan = (flags & SYSID_DAT_EMPTY_IS_NAN) ? 1 : 0;
     dat_parse_kernel<<<(unsigned)dat_blocks(nbytes), DAT_THREADS, 0, st>>>(g);
     CUDA_TRY(cudaGetLastError());
     if (info_host) {

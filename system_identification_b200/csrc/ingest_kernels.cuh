@@ -150,12 +150,10 @@ dat_offsets_kernel(long long* __restrict__ blk, long long nblk, const unsigned c
 __device__ __constant__ double DAT_P10[23] = {1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
                                               1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
 
-// M / D correctly rounded (ties to even) for 64-bit integers, D = 10^k: long digit strings ("%.6f" above 9.007e9,
-// 17-digit CSV fields).  N = M 2^s with s chosen so that the integer quotient has at least 56 bits; the remainder is
+// M / D correctly rounded (ties to even) for 64-bit integers: long digit strings ("%.6f" above 9.007e9, 17-digit CSV
+// fields) are M / 10^k = (M / 5^k) 2^-k with 5^k < 2^63 for k <= 27; the power of two is exact.  N = M 2^s with s chosen so that the integer quotient has at least 56 bits; the remainder is
 // the sticky bit.
-__device__ __constant__ unsigned long long DAT_U10[20] = {1ULL, 10ULL, 100ULL, 1000ULL, 10000ULL, 100000ULL, 1000000ULL, 10000000ULL,
-    100000000ULL, 1000000000ULL, 10000000000ULL, 100000000000ULL, 1000000000000ULL, 10000000000000ULL, 100000000000000ULL,
-    1000000000000000ULL, 10000000000000000ULL, 100000000000000000ULL, 1000000000000000000ULL, 10000000000000000000ULL};
+__device__ __constant__ unsigned long long DAT_U5[28] = {1ULL, 5ULL, 25ULL, 125ULL, 625ULL, 3125ULL, 15625ULL, 78125ULL, 390625ULL, 1953125ULL, 9765625ULL, 48828125ULL, 244140625ULL, 1220703125ULL, 6103515625ULL, 30517578125ULL, 152587890625ULL, 762939453125ULL, 3814697265625ULL, 19073486328125ULL, 95367431640625ULL, 476837158203125ULL, 2384185791015625ULL, 11920928955078125ULL, 59604644775390625ULL, 298023223876953125ULL, 1490116119384765625ULL, 7450580596923828125ULL};
 
 __device__ double dat_ratio(unsigned long long M, unsigned long long D) {
     const int bm = 64 - __clzll((long long)M), bd = 64 - __clzll((long long)D);
@@ -174,7 +172,7 @@ __device__ double dat_ratio(unsigned long long M, unsigned long long D) {
 // One decimal field -> double, exactly as strtod would round it.  Clinger's exact path: the digits form an integer
 // M <= 2^53 and the decimal exponent e satisfies |e| <= 22, so M and 10^|e| are both exact doubles and ONE correctly
 // rounded IEEE multiplication or division gives the correctly rounded value ("%.6f" text below 9.007e9).  Longer digit
-// strings (M < 2^64, -19 <= e <= 0) go through the integer division of dat_ratio.  Anything else (20+ significant
+// strings and smaller exponents (M < 2^64, -27 <= e <= 0) go through the integer division of dat_ratio.  Anything else (20+ significant
 // digits, large exponents, garbage) returns false: counted and reported, never approximated.
 // (the field is read in place from the staged text through an accessor: s[i] = byte i of the field)
 struct DatSmemField {
@@ -234,14 +232,13 @@ __device__ bool dat_convert(const S& s, int n, double* out) {
     }
     double v;
     if (mant == 0) v = 0.0;
-    else if (mant <= (1ULL << 53)) {
+    else if (mant <= (1ULL << 53) && e10 >= -22 && e10 <= 22) {
         const double m = (double)mant;                         // exact
         if (e10 == 0) v = m;
-        else if (e10 < 0 && e10 >= -22) v = __ddiv_rn(m, DAT_P10[-e10]);      // both exact: one rounding
-        else if (e10 > 0 && e10 <= 22) v = __dmul_rn(m, DAT_P10[e10]);
-        else return false;
+        else if (e10 < 0) v = __ddiv_rn(m, DAT_P10[-e10]);     // both exact: one rounding
+        else v = __dmul_rn(m, DAT_P10[e10]);
     } else if (e10 == 0) v = __ull2double_rn(mant);            // integer -> double is correctly rounded
-    else if (e10 < 0 && e10 >= -19) v = dat_ratio(mant, DAT_U10[-e10]);
+    else if (e10 < 0 && e10 >= -27) v = scalbn(dat_ratio(mant, DAT_U5[-e10]), e10);
     else return false;
     *out = neg ? -v : v;
     return true;
@@ -253,6 +250,8 @@ struct DatParseArgs {
     long long rows, cols;
     double* out; long long ld;
     int round_f32;
+    int transpose;       // out is cols x rows (element (row, col) at out[col * ld + row]): a row-major CSV lands channel-major
+    int empty_nan;       // an empty field is NaN (pandas.read_csv) instead of an error (np.loadtxt)
 };
 
 // bit p of the result: byte p of the thread's slice is a delimiter (the field delimiter or a newline)
@@ -315,10 +314,10 @@ dat_parse_kernel(const DatParseArgs g) {
             ++len;
         }
         double v = __longlong_as_double(0x7ff8000000000000LL);
-        const bool ok = closed && len <= DAT_MAXFIELD && dat_convert(DatSmemField{sm, p}, len, &v);
+        const bool ok = closed && len <= DAT_MAXFIELD && ((len == 0 && g.empty_nan) || dat_convert(DatSmemField{sm, p}, len, &v));
         const long long row = idx / g.cols, col = idx - row * g.cols;
         if (!ok) { ++nbad; if (idx < firstbad) firstbad = idx; v = __longlong_as_double(0x7ff8000000000000LL); }
-        if (row < g.rows) g.out[row * g.ld + col] = g.round_f32 ? (double)__double2float_rn(v) : v;
+        if (row < g.rows) g.out[g.transpose ? col * g.ld + row : row * g.ld + col] = g.round_f32 ? (double)__double2float_rn(v) : v;
         // a row ends exactly where a newline is: the terminator of the last column, and of no other
         if (closed && ((term == '\n') != (col == g.cols - 1))) ++nragged;
     }

@@ -4,6 +4,7 @@ kernel consumes, without np.loadtxt and without the per-row pandas loops.
     q = load_dat(path + "g1_robot_low_q.dat")              # np.loadtxt(..., delimiter='\\t', dtype=np.float32)
     q, dq, ddq, tau, cnt = read_data(path, "spot", "butterworth")   # reference spot_identification.py:9-33, on the device
     log = csv_to_log(pd.read_csv("run.csv"))                # low_ddq_contact_tick.py + csv2dat.py + read_data, no files
+    log = csv_to_log(load_csv("run.csv"))                   # ... and without pandas: the CSV text parsed on the device
 
 The arithmetic is done by libsysid_b200.so (csrc/ingest_kernels.cuh): sysid_dat_scan / sysid_dat_parse, sysid_fd_rate,
 sysid_contact_from_tau, sysid_round_dat.  No CPU fallback: without the library or a CUDA device these calls raise.
@@ -102,6 +103,59 @@ def load_dat(source, delimiter="\t", dtype=np.float32, device=None):
     return out
 
 
+def load_csv(source, device=None):
+    """pd.read_csv(source) for an all-numeric logger CSV (reference g1-data/csv2dat.py:15, low_ddq_contact_tick.py:21),
+    parsed on the device: returns {column name: CUDA float64 (N,) tensor} (rows of one channel-major (columns, N) tensor, so
+    csv_to_log takes it as it is).  Every field is converted exactly (strtod's value; pandas' default parser is off by an
+    ulp on ~15 % of 17-digit fields); an empty field is NaN, as in pandas.  A 10^6-row log is ~2 GB of text: seconds of
+    pandas, tens of milliseconds here plus the upload."""
+    lib = _lib.load()
+    dev = _dev(device)
+    if isinstance(source, (bytes, bytearray, memoryview)):
+        raw = np.frombuffer(source, dtype=np.uint8)
+    else:
+        raw = np.fromfile(os.fspath(source), dtype=np.uint8)
+    nl = np.flatnonzero(raw[:1 << 20] == 0x0A)
+    if nl.size == 0:
+        raise ValueError("no header line")
+    names = [c.strip().strip('"') for c in bytes(raw[:nl[0]]).decode("utf-8").rstrip("\r").split(",")]
+    body = raw[nl[0] + 1:]
+    n = body.size
+    while n > 0 and body[n - 1] in (0x0A, 0x0D, 0x20):
+        n -= 1
+    if n == 0:
+        raise ValueError("input contained no data")
+    n += 1 if n < body.size and body[n] == 0x0A else 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        host = torch.from_numpy(body[:n])
+    text = torch.empty(n + 16, dtype=torch.uint8, device=dev)
+    text[:n].copy_(host)
+    ws = torch.empty(lib.sysid_dat_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    dims = (C.c_int64 * 2)()
+    rc = lib.sysid_dat_scan(_ptr(text), n, ord(","), _ptr(ws), ws.numel(), dims, _stream())
+    if rc == -1 and dims[0] > 0:
+        raise ValueError(lib.sysid_last_error().decode())
+    _lib.check(rc)
+    rows, cols = int(dims[0]), int(dims[1])
+    if cols != len(names):
+        raise ValueError(f"header names {len(names)} columns, the rows hold {cols}")
+    out = torch.empty((cols, rows), dtype=torch.float64, device=dev)
+    info = (C.c_int64 * 4)()
+    rc = lib.sysid_dat_parse_ex(_ptr(text), n, ord(","), _ptr(ws), ws.numel(), rows, cols, _ptr(out), rows, 2 | 4, info, _stream())
+    if rc == -1:
+        msg = lib.sysid_last_error().decode()
+        if info[0] > 0:
+            cuts = np.flatnonzero((body[:n] == ord(",")) | (body[:n] == 0x0A))
+            k = int(info[1])
+            lo = int(cuts[k - 1]) + 1 if k > 0 else 0
+            hi = int(cuts[k]) if k < cuts.size else n
+            msg += f": {bytes(body[lo:hi])!r} (column {names[k % cols]!r})"
+        raise ValueError(msg)
+    _lib.check(rc)
+    return {name: out[i] for i, name in enumerate(names)}
+
+
 def read_data(path, robot_name, filter_type, q_name="q"):
     """The reference's read_data (spot_identification.py:9-33; demo/solo_identification.py:9-33) on the device: the five
     .dat files parsed by load_dat as float32, then the same filter.  q_name selects `<robot>_robot_<q_name>.dat`
@@ -155,7 +209,10 @@ def round_dat(x, float32=True):
 
 
 def _rows(columns, names):
-    return np.stack([np.asarray(columns[c], dtype=np.float64) for c in names])
+    cols = [columns[c] for c in names]
+    if all(isinstance(c, torch.Tensor) for c in cols):
+        return torch.stack([c.to(dtype=torch.float64) for c in cols])          # load_csv output: already on the device
+    return np.stack([np.asarray(c.cpu() if isinstance(c, torch.Tensor) else c, dtype=np.float64) for c in cols])
 
 
 def csv_to_log(columns, tick_col="low_tick", scale=1000.0, relabel_contact=True, fix_ddq_off_by_one=True, float32=True):
@@ -173,7 +230,7 @@ def csv_to_log(columns, tick_col="low_tick", scale=1000.0, relabel_contact=True,
     missing = [c for c in set(LOW_Q_COLS + ODOM_Q_COLS + DQ_COLS + TAU_COLS + ACCEL_COLS + [tick_col]) if c not in columns]
     if missing:
         raise ValueError(f"Missing columns in CSV: {sorted(missing)}")
-    tick = np.asarray(columns[tick_col], dtype=np.float64)
+    tick = columns[tick_col] if isinstance(columns[tick_col], torch.Tensor) else np.asarray(columns[tick_col], dtype=np.float64)
     motors = range(G1_MOTORS) if fix_ddq_off_by_one else range(1, G1_MOTORS)
     rates = fd_rate(tick, _rows(columns, GYRO_COLS + [f"low_motor_{i}_dq" for i in motors]), scale)
     ddq = torch.cat([_as_dev2d(_rows(columns, ACCEL_COLS)), rates], dim=0)

@@ -188,3 +188,27 @@ def test_g1_driver_on_dat_files_equals_loadtxt_route(tmp_path, capsys, monkeypat
     g1_identification.main()
     out = capsys.readouterr().out
     assert "Identified" in out and "Prior" in out
+
+
+def test_load_csv_equals_exact_pandas_and_feeds_csv_to_log(gold):
+    """The logger CSV parsed on the device: every column equals pandas' round-trip parse (the exact decimal -> double
+    conversion; pandas' default parser differs from it by an ulp on some fields), empty fields are NaN, and csv_to_log on
+    the device-parsed columns reproduces the reference pipeline's .dat arrays like the pandas route does."""
+    import pandas as pd
+    from system_identification_b200 import ingest
+    text = gold["csv_text"].tobytes()
+    cols = ingest.load_csv(text)
+    ref = pd.read_csv(io.BytesIO(text), float_precision="round_trip")
+    assert list(cols) == list(ref.columns)
+    for name in ref.columns:
+        assert same(cols[name], ref[name].to_numpy().astype(np.float64)), name
+    log = ingest.csv_to_log(cols, fix_ddq_off_by_one=False)
+    for name in FILES:
+        assert same(log[name], gold["loadtxt_" + name]), name
+    # empty fields are NaN (pandas), ragged rows and garbage raise
+    small = ingest.load_csv(b"a,b,c\n1.5,,3\n4,5,6\n")
+    assert same(small["b"], np.array([np.nan, 5.0])) and same(small["c"], np.array([3.0, 6.0]))
+    with pytest.raises(ValueError):
+        ingest.load_csv(b"a,b\n1,2\n3\n")
+    with pytest.raises(ValueError, match="column 'b'"):
+        ingest.load_csv(b"a,b\n1,x\n")
