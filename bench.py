@@ -76,6 +76,10 @@ def cpu_port_throughput(flat, data, n_samples, threads=0, repeats=1):
     from oracle import urdf_tree as ut
     from oracle.cbuild import COracle
     co = COracle(ut.tree_from_flat(flat), flat.ee_names)
+    if threads <= 0:
+        # every core this process may run on, set explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+        # otherwise turn the all-cores CPU arm into a single-thread run whenever N > 1
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     sub = tuple(a[:, :n_samples] for a in data)
     best = None
     used = 1
