@@ -177,3 +177,19 @@ def test_butterworth_design_matches_scipy_and_fixture():
         assert np.abs(b - bs).max() <= 1e-14 * np.abs(bs).max() and np.abs(a - as_).max() <= 1e-13 * np.abs(as_).max()
     with pytest.raises(ValueError):
         butter_lowpass(5, 1.5)
+
+
+def test_ingest_column_lists_match_the_reference_scripts():
+    """Host logic of the ingest row without a GPU: the product's column lists are csv2dat.py's (restated independently in
+    the oracle, which is pinned against the script's own output), and the device entry points refuse to run on a CPU."""
+    from oracle import ingest as oi
+    from system_identification_b200 import ingest
+    assert ingest.LOW_Q_COLS == oi.LOW_Q_COLS and ingest.ODOM_Q_COLS == oi.ODOM_Q_COLS
+    assert ingest.DQ_COLS == oi.DQ_COLS and ingest.TAU_COLS == oi.TAU_COLS
+    assert ingest.ACCEL_COLS + ["body_ang_acceleration_" + a for a in "xyz"] + [f"low_motor_{i}_ddq" for i in range(12)] == oi.ddq_cols(True)
+    import torch
+    if not torch.cuda.is_available():
+        for call in (lambda: ingest.load_dat(b"1.0\t2.0\n"), lambda: ingest.load_csv(b"a,b\n1,2\n"),
+                     lambda: ingest.fd_rate(np.arange(4.0), np.zeros((2, 4))), lambda: ingest.round_dat(np.zeros(3))):
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                call()
