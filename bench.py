@@ -317,32 +317,9 @@ def measure_fp64_peak(torch):
 
 
 def identifiable_tau(flat, dm, dev, seed):
-    """tau = least-squares joint torques reproducing P (Y phi_true + friction) + noise, built on the device in chunks
-    with library calls (data generation only, outside every timed region)."""
-    import numpy as np
-    import torch
-    q, dq, ddq, tau, cnt = dev
-    N = q.shape[1]
-    rng = np.random.default_rng(seed)
-    phi_true = torch.from_numpy(flat.body_params[1:].reshape(-1) * (1 + 0.05 * rng.standard_normal(10 * flat.nbodies))).cuda()
-    bv = torch.from_numpy(rng.uniform(0, 0.2, flat.joints_dof)).cuda()
-    bc = torch.from_numpy(rng.uniform(0, 0.5, flat.joints_dof)).cuda()
-    out = torch.empty_like(tau)
-    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
-    for lo in range(0, N, 32768):
-        hi = min(N, lo + 32768)
-        sl = [a[:, lo:hi].contiguous() for a in (q, dq, ddq, tau, cnt)]
-        Y = dm.regressor_batch(*sl[:3])
-        _, _, P = dm.projected_batch(*sl, want_P=True)
-        F = torch.einsum("nrc,c->nr", Y, phi_true)
-        rhs = torch.einsum("nrk,nk->nr", P, F)
-        PS = P[:, :, 6:]
-        sol = torch.einsum("ndk,nk->nd", torch.linalg.pinv(PS), rhs)                     # (n, d) minimum-norm least squares
-        dqj = sl[1][6:, :].T
-        t = sol + bv * dqj + bc * torch.sign(dqj) + 0.5 * torch.randn(sol.shape, generator=gen, device="cuda", dtype=torch.float64)
-        out[:, lo:hi] = t.T
-        del Y, P, F, rhs, PS, sol
-    return out
+    """Ground-truth torques for the e2e solve (data generation, outside every timed region)."""
+    from system_identification_b200.synth import identifiable_tau_device
+    return identifiable_tau_device(flat, dm, dev, seed)
 
 
 # Rank 0 prints exactly ONE line on stdout.  Libraries do not know that (NCCL writes its version banner to stdout whenever

@@ -15,6 +15,7 @@
  *                             reference demo/solo_identification.py:36-55,79-84 and src/solver.py:186-190
  *   sysid_gram_accumulate_host  the same call for arrays still in host memory, exactly as read_data leaves them
  *                             (reference demo/solo_identification.py:9-33): upload and kernel overlap chunk by chunk
+ *   sysid_gram_accumulate_host_ex  the same for the mixed float32 / float64 arrays read_data really returns (quirk Q8)
  *   sysid_gram_from_stack     same statistics from an already stacked (rows x c) matrix, for callers that built
  *                             Y_proj/B_v/B_c through the per-sample API and hand them to Solver(...)  src/solver.py:6-29
  *   sysid_sdp_solve           Solver.solve_fully_consistent: cvxpy problem + problem.solve(solver=cp.MOSEK)
@@ -139,6 +140,18 @@ int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, c
                                const double* tau_host, const double* contact_host, int64_t N, int64_t ld_host,
                                const double* weights_host, int32_t friction, double* stats, int64_t* info,
                                void* workspace, size_t workspace_bytes, int64_t chunk, void* stream);
+
+/* The same call for host arrays of MIXED precision, which is what the reference's read_data actually returns
+ * (demo/solo_identification.py:10-14: np.loadtxt(dtype=float32) for all five; dq / ddq / tau become float64 through
+ * scipy's filtfilt, q and contact stay float32 -- SURVEY quirk Q8).  arrays_host[5] = {q, dq, ddq, tau, contact},
+ * dtypes[a] in {SYSID_DTYPE_F64, SYSID_DTYPE_F32}, lds_host[a] = leading dimension of array a in ELEMENTS.  float32
+ * arrays cross PCIe as float32 and are widened exactly on the device. */
+#define SYSID_DTYPE_F64 0
+#define SYSID_DTYPE_F32 1
+int sysid_gram_accumulate_host_ex(const sysid_model* model, const void* const* arrays_host, const int32_t* dtypes,
+                                  const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,
+                                  double* stats, int64_t* info, void* workspace, size_t workspace_bytes, int64_t chunk,
+                                  void* stream);
 
 /* Same statistics from a stacked matrix A (rows x c, row-major, device) and vector b (rows). */
 int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,

@@ -59,6 +59,7 @@ class COracle:
         self.nv, self.nb = tree.nv, tree.njoints - 1
         self.nd = self.nb - 1
         self.lib.oracle_gram_accumulate.restype = C.c_int
+        self.lib.oracle_tau_rmse.restype = C.c_int
 
     def _p(self, a):
         return a.ctypes.data_as(C.POINTER(C.c_double))
@@ -71,6 +72,17 @@ class COracle:
         used = self.lib.oracle_gram_accumulate(C.byref(self.t), *[self._p(a) for a in arrs], C.c_int64(N), C.c_int64(N),
                                                C.c_int(1 if friction else 0), C.c_int(nthreads), self._p(stats))
         return stats, used
+
+    def tau_rmse(self, q, dq, ddq, tau, cnt, phi, nthreads=0):
+        """(total mean-square, per-joint RMSE) of reference print_tau_prediction_rmse (src/sys_identification.py:421-437)."""
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (q, dq, ddq, tau, cnt)]
+        N = arrs[0].shape[1]
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        assert phi.size == 10 * self.nb
+        out = np.zeros(1 + self.nd)
+        self.lib.oracle_tau_rmse(C.byref(self.t), *[self._p(a) for a in arrs], C.c_int64(N), C.c_int64(N), self._p(phi),
+                                 C.c_int(nthreads), self._p(out))
+        return float(out[0]), out[1:].copy()
 
     def blocks(self, q, dq, ddq, tau, cnt, friction=True):
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (q, dq, ddq, tau, cnt)]

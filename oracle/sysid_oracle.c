@@ -312,3 +312,51 @@ void oracle_sample_blocks(const oracle_tree* T, const double* q, const double* d
                     Y ? Y + (size_t)i * nv * np : NULL, P ? P + (size_t)i * nv * nv : NULL);
     }
 }
+
+/* Torque-prediction error pass, reference src/sys_identification.py:421-437 (print_tau_prediction_rmse):
+ *   predicted_i = (P Y phi)[6:], measured_i = (P S^T tau)[6:];  out[0] = mean_i ||e_i||^2 (quirk Q7: no root),
+ *   out[1 + k] = sqrt(mean_i e_ik^2).  phi multiplies the pinocchio-ordered regressor as it is (quirk Q1). */
+int oracle_tau_rmse(const oracle_tree* T, const double* q, const double* dq, const double* ddq, const double* tau,
+                    const double* cnt, int64_t N, int64_t ld, const double* phi, int nthreads, double* out) {
+    const int nb = T->njoints - 1, nv = 6 + nb - 1, nq = 7 + nb - 1, nd = nb - 1, np = 10 * nb;
+    int used = 1;
+    double tot = 0.0, pj[MAXV];
+    for (int k = 0; k < MAXV; ++k) pj[k] = 0.0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+#pragma omp single
+        used = omp_get_num_threads();
+#endif
+        double* A = (double*)malloc(sizeof(double) * (size_t)nv * np);
+        double bq[MAXV], qs[64], dqs[MAXV], ddqs[MAXV], taus[MAXV], cs[MAXEE], ltot = 0.0, lpj[MAXV];
+        for (int k = 0; k < MAXV; ++k) lpj[k] = 0.0;
+#pragma omp for schedule(static)
+        for (int64_t i = 0; i < N; ++i) {
+            for (int k = 0; k < nq; ++k) qs[k] = q[k * ld + i];
+            for (int k = 0; k < nv; ++k) { dqs[k] = dq[k * ld + i]; ddqs[k] = ddq[k * ld + i]; }
+            for (int k = 0; k < nd; ++k) taus[k] = tau[k * ld + i];
+            for (int k = 0; k < T->n_ee; ++k) cs[k] = cnt[k * ld + i];
+            sample_rows(T, nv, np, nd, 0, qs, dqs, ddqs, taus, cs, A, bq, NULL, NULL);
+            for (int k = 0; k < nd; ++k) {
+                const double* Ar = A + (size_t)(6 + k) * np;
+                double e = 0.0;
+                for (int c = 0; c < np; ++c) e += Ar[c] * phi[c];
+                e -= bq[6 + k];
+                ltot += e * e; lpj[k] += e * e;
+            }
+        }
+#pragma omp critical
+        {
+            tot += ltot;
+            for (int k = 0; k < nd; ++k) pj[k] += lpj[k];
+        }
+        free(A);
+    }
+    out[0] = tot / (double)N;
+    for (int k = 0; k < nd; ++k) out[1 + k] = sqrt(pj[k] / (double)N);
+    return used;
+}

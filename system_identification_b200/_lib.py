@@ -68,6 +68,7 @@ _SIGNATURES = {
     "sysid_gram_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
     "sysid_gram_host_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
     "sysid_gram_accumulate_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
+    "sysid_gram_accumulate_host_ex": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
     "sysid_gram_from_stack": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P]),
     "sysid_gram_from_stack_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "sysid_filtfilt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),

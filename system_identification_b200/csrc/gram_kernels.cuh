@@ -531,19 +531,35 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
         }
         __syncthreads();
         // e = (P g)[6 + k], thread per (sample, joint)
+        // squared errors go to the (dead) wrench region; thread k then adds its joint's column sample by sample, so the
+        // per-CTA sums have ONE summation order (no atomics: the pass is bit-reproducible, like the Gram)
         for (int it = t; it < RSB * nd; it += GRAM_THREADS) {
             const int s = it / nd, k = it - s * nd, r = 6 + k;
-            if (base + s >= args.N) continue;
-            const double* c = ctx + s * CX_STRIDE;
-            const double* P = c + CX_P;
-            const double* gs = G + s * MAXV;
             double e = 0.0;
-            for (int cc = 0; cc < nv; ++cc) e = fma(P[pk(r, cc)], gs[cc], e);
-            e *= c[CX_W];
-            atomicAdd(&s_acc[0], e * e); atomicAdd(&s_acc[1 + k], e * e);
+            if (base + s < args.N) {
+                const double* c = ctx + s * CX_STRIDE;
+                const double* P = c + CX_P;
+                const double* gs = G + s * MAXV;
+                for (int cc = 0; cc < nv; ++cc) e = fma(P[pk(r, cc)], gs[cc], e);
+                e *= c[CX_W];
+            }
+            Wb[s * MAXD + k] = e * e;
         }
         __syncthreads();
+        if (tid < nd) {
+            double a = s_acc[1 + tid];
+            for (int s = 0; s < RSB; ++s) a += Wb[s * MAXD + tid];
+            s_acc[1 + tid] = a;
+        }
+        // the next super-batch's `stage` writes only the staged inputs and is followed by a barrier before anything touches Wb
     }
+    __syncthreads();
+    if (tid == 0) {
+        double a = 0.0;
+        for (int k = 0; k < nd; ++k) a += s_acc[1 + k];
+        s_acc[0] = a;
+    }
+    __syncthreads();
     if (tid < RMSE_PARTIAL - 1) args.partial[(size_t)blockIdx.x * RMSE_PARTIAL + tid] = s_acc[tid];
 }
 

@@ -280,23 +280,42 @@ size_t sysid_gram_host_workspace_bytes(const sysid_model* model, int64_t chunk) 
     if (!model || chunk <= 0) return 0;
     const DevModel& M = model->dev;
     const size_t per_sample = (size_t)M.nq + 2 * (size_t)M.nv + (size_t)M.nd + (size_t)M.n_ee + 1;
-    return sysid_gram_workspace_bytes(model) + 2 * sizeof(double) * per_sample * (size_t)chunk + 256;
+    // two fp64 staging buffers + two float32 landing buffers (float32 host arrays are widened on the device)
+    return sysid_gram_workspace_bytes(model) + 2 * (sizeof(double) + sizeof(float)) * per_sample * (size_t)chunk + 512;
 }
 
-int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, const double* dq_host, const double* ddq_host,
-                               const double* tau_host, const double* contact_host, int64_t N, int64_t ld_host,
-                               const double* weights_host, int32_t friction, double* stats, int64_t* info,
-                               void* workspace, size_t workspace_bytes, int64_t chunk, void* stream) {
-    if (!model || !q_host || !dq_host || !ddq_host || !tau_host || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
-    if (model->dev.n_ee > 0 && !contact_host) return fail(SYSID_ERR_INVALID, "null contact array");
-    if (N < 0 || ld_host < N || chunk <= 0) return fail(SYSID_ERR_INVALID, "bad N/ld/chunk");
+namespace {
+// float32 landing buffer -> fp64 staging buffer (exact widening, what numpy does when the reference mixes its float32 q /
+// contact arrays into fp64 arithmetic): channels x n, both with leading dimension ld
+__global__ void widen_f32_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t ld, int channels) {
+    const int64_t total = (int64_t)channels * n;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t ch = e / n, i = e - ch * n;
+        dst[ch * ld + i] = (double)src[ch * ld + i];
+    }
+}
+}  // namespace
+
+int sysid_gram_accumulate_host_ex(const sysid_model* model, const void* const* arrays_host, const int32_t* dtypes,
+                                  const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,
+                                  double* stats, int64_t* info, void* workspace, size_t workspace_bytes, int64_t chunk,
+                                  void* stream) {
+    if (!model || !arrays_host || !dtypes || !lds_host || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    const DevModel& M = model->dev;
+    const int channels[5] = {M.nq, M.nv, M.nv, M.nd, M.n_ee};
+    for (int a = 0; a < 5; ++a) {
+        if (channels[a] > 0 && !arrays_host[a]) return fail(SYSID_ERR_INVALID, a == 4 ? "null contact array" : "null argument");
+        if (dtypes[a] != SYSID_DTYPE_F64 && dtypes[a] != SYSID_DTYPE_F32) return fail(SYSID_ERR_INVALID, "dtype must be SYSID_DTYPE_F64 or SYSID_DTYPE_F32");
+        if (lds_host[a] < N) return fail(SYSID_ERR_INVALID, "bad N/ld/chunk");
+    }
+    if (N < 0 || chunk <= 0) return fail(SYSID_ERR_INVALID, "bad N/ld/chunk");
     if (N == 0) return SYSID_OK;
     if (workspace_bytes < sysid_gram_host_workspace_bytes(model, chunk)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
-    const DevModel& M = model->dev;
     cudaStream_t st = (cudaStream_t)stream;
     const size_t gram_ws = (sysid_gram_workspace_bytes(model) + 255) & ~(size_t)255;
     const size_t per_sample = (size_t)M.nq + 2 * (size_t)M.nv + (size_t)M.nd + (size_t)M.n_ee + 1;
     double* stage[2] = {(double*)((char*)workspace + gram_ws), (double*)((char*)workspace + gram_ws) + per_sample * (size_t)chunk};
+    float* land[2] = {(float*)(stage[1] + per_sample * (size_t)chunk), (float*)(stage[1] + per_sample * (size_t)chunk) + per_sample * (size_t)chunk};
     cudaStream_t cp = nullptr;
     cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, start = nullptr;
     int rc = SYSID_OK;
@@ -315,33 +334,56 @@ int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, c
     // the staging buffers may still be read by earlier work on `stream`
     HOST_TRY(cudaEventRecord(start, st));
     HOST_TRY(cudaStreamWaitEvent(cp, start, 0));
-    const size_t W = sizeof(double);
     long long k = 0;
     for (int64_t lo = 0; lo < N; lo += chunk, ++k) {
         const int b = (int)(k & 1);
         const int64_t n = (N - lo < chunk) ? (N - lo) : chunk;
         if (k >= 2) HOST_TRY(cudaStreamWaitEvent(cp, consumed[b], 0));
-        double* dq_ = stage[b] + (size_t)M.nq * chunk;
-        double* ddq_ = dq_ + (size_t)M.nv * chunk;
-        double* tau_ = ddq_ + (size_t)M.nv * chunk;
-        double* cnt_ = tau_ + (size_t)M.nd * chunk;
-        double* w_ = cnt_ + (size_t)M.n_ee * chunk;
-        HOST_TRY(cudaMemcpy2DAsync(stage[b], chunk * W, q_host + lo, ld_host * W, n * W, M.nq, cudaMemcpyHostToDevice, cp));
-        HOST_TRY(cudaMemcpy2DAsync(dq_, chunk * W, dq_host + lo, ld_host * W, n * W, M.nv, cudaMemcpyHostToDevice, cp));
-        HOST_TRY(cudaMemcpy2DAsync(ddq_, chunk * W, ddq_host + lo, ld_host * W, n * W, M.nv, cudaMemcpyHostToDevice, cp));
-        HOST_TRY(cudaMemcpy2DAsync(tau_, chunk * W, tau_host + lo, ld_host * W, n * W, M.nd, cudaMemcpyHostToDevice, cp));
-        if (M.n_ee > 0) HOST_TRY(cudaMemcpy2DAsync(cnt_, chunk * W, contact_host + lo, ld_host * W, n * W, M.n_ee, cudaMemcpyHostToDevice, cp));
-        if (weights_host) HOST_TRY(cudaMemcpyAsync(w_, weights_host + lo, n * W, cudaMemcpyHostToDevice, cp));
+        double* dst[6];
+        size_t off = 0;
+        for (int a = 0; a < 5; ++a) { dst[a] = stage[b] + off * (size_t)chunk; off += (size_t)channels[a]; }
+        dst[5] = stage[b] + off * (size_t)chunk;
+        for (int a = 0; a < 5; ++a) {
+            if (channels[a] == 0) continue;
+            if (dtypes[a] == SYSID_DTYPE_F64) {
+                HOST_TRY(cudaMemcpy2DAsync(dst[a], chunk * sizeof(double), (const double*)arrays_host[a] + lo, lds_host[a] * sizeof(double),
+                                           n * sizeof(double), channels[a], cudaMemcpyHostToDevice, cp));
+            } else {
+                float* l = land[b] + (dst[a] - stage[b]);
+                HOST_TRY(cudaMemcpy2DAsync(l, chunk * sizeof(float), (const float*)arrays_host[a] + lo, lds_host[a] * sizeof(float),
+                                           n * sizeof(float), channels[a], cudaMemcpyHostToDevice, cp));
+            }
+        }
+        if (weights_host) HOST_TRY(cudaMemcpyAsync(dst[5], weights_host + lo, n * sizeof(double), cudaMemcpyHostToDevice, cp));
         HOST_TRY(cudaEventRecord(copied[b], cp));
         HOST_TRY(cudaStreamWaitEvent(st, copied[b], 0));
-        rc = sysid_gram_accumulate(model, stage[b], dq_, ddq_, tau_, M.n_ee > 0 ? cnt_ : nullptr, n, chunk, weights_host ? w_ : nullptr,
-                                   friction, stats, info, workspace, gram_ws, st);
+        for (int a = 0; a < 5; ++a)
+            if (channels[a] > 0 && dtypes[a] == SYSID_DTYPE_F32) {
+                const int64_t total = (int64_t)channels[a] * n;
+                const int blocks = (int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184);
+                widen_f32_kernel<<<blocks, 256, 0, st>>>(land[b] + (dst[a] - stage[b]), dst[a], n, chunk, channels[a]);
+                HOST_TRY(cudaGetLastError());
+            }
+        rc = sysid_gram_accumulate(model, dst[0], dst[1], dst[2], dst[3], M.n_ee > 0 ? dst[4] : nullptr, n, chunk,
+                                   weights_host ? dst[5] : nullptr, friction, stats, info, workspace, gram_ws, st);
         if (rc != SYSID_OK) { cleanup(); return rc; }
         HOST_TRY(cudaEventRecord(consumed[b], st));
     }
 #undef HOST_TRY
     cleanup();
     return SYSID_OK;
+}
+
+int sysid_gram_accumulate_host(const sysid_model* model, const double* q_host, const double* dq_host, const double* ddq_host,
+                               const double* tau_host, const double* contact_host, int64_t N, int64_t ld_host,
+                               const double* weights_host, int32_t friction, double* stats, int64_t* info,
+                               void* workspace, size_t workspace_bytes, int64_t chunk, void* stream) {
+    if (!model || !q_host || !dq_host || !ddq_host || !tau_host) return fail(SYSID_ERR_INVALID, "null argument");
+    const void* arrays[5] = {q_host, dq_host, ddq_host, tau_host, contact_host};
+    const int32_t dt[5] = {SYSID_DTYPE_F64, SYSID_DTYPE_F64, SYSID_DTYPE_F64, SYSID_DTYPE_F64, SYSID_DTYPE_F64};
+    const int64_t lds[5] = {ld_host, ld_host, ld_host, ld_host, ld_host};
+    return sysid_gram_accumulate_host_ex(model, arrays, dt, lds, N, weights_host, friction, stats, info, workspace,
+                                         workspace_bytes, chunk, stream);
 }
 
 int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_t c, double* stats,

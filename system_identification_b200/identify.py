@@ -15,21 +15,17 @@ from .ops import to_device, sdp_solve
 
 
 def _host_streamable(arrays, weights):
-    """True when all five arrays are host float64, 2-D, unit inner stride, one common leading dimension."""
-    ts = []
+    """True when all five arrays are host float64 / float32 (what the reference's read_data returns: float32 q and
+    contact, float64 dq / ddq / tau -- demo/solo_identification.py:10-33), 2-D with unit inner stride."""
     for a in arrays:
         if isinstance(a, np.ndarray):
-            if a.dtype != np.float64 or a.ndim != 2 or a.strides[1] != 8:
+            if a.dtype not in (np.float64, np.float32) or a.ndim != 2 or a.strides[1] != a.itemsize:
                 return False
-            ts.append(a.strides[0])
         elif isinstance(a, torch.Tensor):
-            if a.is_cuda or a.dtype != torch.float64 or a.dim() != 2 or a.stride(1) != 1:
+            if a.is_cuda or a.dtype not in (torch.float64, torch.float32) or a.dim() != 2 or a.stride(1) != 1:
                 return False
-            ts.append(a.stride(0) * 8)
         else:
             return False
-    if len(set(ts)) != 1:
-        return False
     if weights is not None:
         w = weights
         if isinstance(w, np.ndarray):

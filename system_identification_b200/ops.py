@@ -123,17 +123,20 @@ class DeviceModel:
 
     def gram_accumulate_host(self, q, dq, ddq, tau, cnt, friction=True, weights=None, stats=None, info=None, chunk=131072,
                              device=None):
-        """gram_accumulate for arrays still in HOST memory (float64 torch CPU tensors or numpy arrays, channel-major with
-        unit inner stride and one common leading dimension; pinned memory for full PCIe speed): the upload is chunked and
-        overlapped with the kernel inside the library (sysid_gram_accumulate_host).  Returns the device statistics."""
+        """gram_accumulate for arrays still in HOST memory: float64 OR float32 torch CPU tensors / numpy arrays, channel-major
+        with unit inner stride (pinned memory for full PCIe speed) -- exactly what the reference's read_data returns
+        (float32 q / contact, float64 dq / ddq / tau; demo/solo_identification.py:10-33).  The upload is chunked and
+        overlapped with the kernel inside the library (sysid_gram_accumulate_host_ex); float32 arrays cross PCIe as float32
+        and are widened exactly on the device.  Returns the device statistics."""
         hs = []
         for a, ch, name in ((q, self.nq, "q"), (dq, self.nv, "dq"), (ddq, self.nv, "ddq"), (tau, self.nd, "tau"), (cnt, self.n_ee, "contact")):
             t = torch.from_numpy(a) if isinstance(a, np.ndarray) else a
-            if t.is_cuda or t.dtype != torch.float64 or t.dim() != 2 or t.shape[0] != ch or t.stride(1) != 1:
-                raise ValueError(f"{name}: expected a host float64 array of shape ({ch}, N) with unit inner stride")
+            if t.is_cuda or t.dtype not in (torch.float64, torch.float32) or t.dim() != 2 or t.shape[0] != ch or t.stride(1) != 1:
+                raise ValueError(f"{name}: expected a host float64/float32 array of shape ({ch}, N) with unit inner stride")
             hs.append(t)
         N = hs[0].shape[1]
-        ld = self._common_ld(*hs)
+        if any(t.shape[1] != N for t in hs):
+            raise ValueError("all sample arrays must have the same number of columns")
         device = torch.device(device or "cuda")
         if stats is None:
             stats = torch.zeros(self.stats_len(friction), dtype=torch.float64, device=device)
@@ -146,11 +149,12 @@ class DeviceModel:
         nbytes = self.lib.sysid_gram_host_workspace_bytes(self.handle, chunk)
         ws = self._workspace("gram_host", nbytes, device)
         self._keepalive = (hs, wh)        # the host arrays must outlive the asynchronous copies
-        _lib.check(self.lib.sysid_gram_accumulate_host(self.handle, C.c_void_p(hs[0].data_ptr()), C.c_void_p(hs[1].data_ptr()),
-                                                       C.c_void_p(hs[2].data_ptr()), C.c_void_p(hs[3].data_ptr()),
-                                                       C.c_void_p(hs[4].data_ptr()) if self.n_ee > 0 else None, N, ld,
-                                                       C.c_void_p(wh.data_ptr()) if wh is not None else None,
-                                                       1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), chunk, _stream()))
+        ptrs = (C.c_void_p * 5)(*[t.data_ptr() if t.shape[0] > 0 else None for t in hs])
+        dts = (C.c_int32 * 5)(*[0 if t.dtype == torch.float64 else 1 for t in hs])
+        lds = (C.c_int64 * 5)(*[max(t.stride(0), N) if t.shape[0] > 1 else N for t in hs])
+        _lib.check(self.lib.sysid_gram_accumulate_host_ex(self.handle, ptrs, dts, lds, N,
+                                                          C.c_void_p(wh.data_ptr()) if wh is not None else None,
+                                                          1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), chunk, _stream()))
         return stats
 
     def predict_rmse(self, q, dq, ddq, tau, cnt, phi):

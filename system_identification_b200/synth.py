@@ -159,3 +159,33 @@ def torques_from_truth(model: FlatModel, Y, P, dq, phi_true_pin, b_v, b_c, noise
     tau += (b_v[:, None] * dqj.T + b_c[:, None] * np.sign(dqj.T))
     tau += noise * rng.standard_normal(tau.shape)
     return tau
+
+
+def identifiable_tau_device(flat: FlatModel, dm, dev, seed, perturb=0.05, bv_max=0.2, bc_max=0.5, noise=0.5, chunk=32768):
+    """Device version of torques_from_truth for full-size logs (20 k .. 1 M samples): tau = the least-squares joint
+    torques reproducing P (Y phi_true) + friction + noise, built chunk by chunk from the library's own per-sample
+    operators and torch library calls.  Data generation only -- never inside a timed region.
+    dm: ops.DeviceModel; dev: the five CUDA arrays (tau is only used for its shape).  Returns a CUDA (d, N) tensor."""
+    import torch
+    q, dq, ddq, tau, cnt = dev
+    N = q.shape[1]
+    rng = np.random.default_rng(seed)
+    phi_true = torch.from_numpy(flat.body_params[1:].reshape(-1) * (1 + perturb * rng.standard_normal(10 * flat.nbodies))).cuda()
+    bv = torch.from_numpy(rng.uniform(0, bv_max, flat.joints_dof)).cuda()
+    bc = torch.from_numpy(rng.uniform(0, bc_max, flat.joints_dof)).cuda()
+    out = torch.empty((flat.joints_dof, N), dtype=torch.float64, device=q.device)
+    gen = torch.Generator(device="cuda"); gen.manual_seed(seed)
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        sl = [a[:, lo:hi].contiguous() for a in (q, dq, ddq, tau, cnt)]
+        Y = dm.regressor_batch(*sl[:3])
+        _, _, P = dm.projected_batch(*sl, want_P=True)
+        F = torch.einsum("nrc,c->nr", Y, phi_true)
+        rhs = torch.einsum("nrk,nk->nr", P, F)
+        PS = P[:, :, 6:]
+        sol = torch.einsum("ndk,nk->nd", torch.linalg.pinv(PS), rhs)                     # (n, d) minimum-norm least squares
+        dqj = sl[1][6:, :].T
+        t = sol + bv * dqj + bc * torch.sign(dqj) + noise * torch.randn(sol.shape, generator=gen, device="cuda", dtype=torch.float64)
+        out[:, lo:hi] = t.T
+        del Y, P, F, rhs, PS, sol
+    return out

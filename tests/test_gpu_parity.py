@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 TOL_Y = 1e-10          # max-abs entry error / max-abs entry, per sample (north_star)
 TOL_GRAM = 1e-12       # relative Frobenius
 TOL_PHI = 1e-4         # global l2 and per-link-block l2, relative
-TOL_RMSE = 5e-3
+TOL_RMSE = 1e-9         # the evaluation pass is a deterministic fp64 quantity (north_star's 0.5 % gate is far looser)
 
 
 def _dev(flat):
@@ -315,8 +315,102 @@ def test_end_to_end_identify_vs_oracle(name):
     assert H.rel(phi_s, phi_f) <= 1e-6 and phi_s.shape == (130,) and sol._b_v.value.shape == (12,)
 
 
+def _device_identifiable_tau(flat, dm, dev, seed):
+    from system_identification_b200.synth import identifiable_tau_device
+    return identifiable_tau_device(flat, dm, dev, seed)
+
+
+TOL_RMSE_FULL = 1e-9   # deterministic fp64 quantity: the evaluation pass vs the oracle's C twin
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_full_size_20k_vs_oracle(name):
+    """BASELINE configs[0-2] at their real size (N = 20 000): the fused Gram against the oracle's C twin at 1e-12,
+    identify() against BOTH oracle solves (semismooth-Newton ALM and log-barrier) of the ORACLE's own statistics at 1e-4
+    global and per link, and the evaluation pass against the oracle's at 1e-9."""
+    from oracle import sdp as osdp
+    from oracle.cbuild import COracle
+    from system_identification_b200.sys_identification import SystemIdentification
+    N, c = 20000, 154
+    flat = H.flat_model(name)
+    q, dq, ddq, cnt = H.synth.make_trajectory(flat, N, H.synth.SEEDS[name])
+    si = SystemIdentification.from_flat_model(flat)
+    dm = si.device_model
+    dev = list(_up((q, dq, ddq, np.zeros((12, N)), cnt)))
+    dev[3] = _device_identifiable_tau(flat, dm, dev, seed=23)
+    tau = dev[3].cpu().numpy()
+    data = (q, dq, ddq, tau, cnt)
+    co = COracle(H.oracle_tree(flat), flat.ee_names)
+    so, _ = co.gram(*data)
+    Go, ro, s_o, n_o = H.split_stats(so, c)
+    st = dm.gram_accumulate(*dev)
+    assert _loaded_native()
+    G, r, s, n = H.split_stats(st.cpu().numpy(), c)
+    assert H.rel(G, Go) <= TOL_GRAM and H.rel(r, ro) <= TOL_GRAM and abs(s - s_o) <= TOL_GRAM * s_o and n == n_o == 18 * N
+    assert np.array_equal(G, G.T) and torch.equal(dm.gram_accumulate(*dev), st)       # symmetric, bit-reproducible
+    # host-array entry (what read_data returns: float32 q / contact, float64 dq / ddq / tau) == device-resident entry
+    sh = dm.gram_accumulate_host(q.astype(np.float32), dq, ddq, tau, cnt.astype(np.float32), chunk=8192)
+    torch.cuda.synchronize()
+    assert H.rel(sh.cpu().numpy(), st.cpu().numpy()) <= 1e-13
+    # stage 3 on the ORACLE's statistics, two independent solves
+    prob = osdp.build_problem(Go, ro, s_o, n_o, 13, flat.phi_prior, flat.robot_mass, flat.ellipsoids, 12)
+    xa, _ = osdp.solve_alm(prob)
+    xb, _ = osdp.solve_barrier(prob)
+    phi, bv, bc, info = si.identify(*dev, return_info=True)
+    x = np.concatenate([phi, bv, bc])
+    for xo in (xa, xb):
+        assert H.rel(x, xo) <= TOL_PHI and H.rel(phi, xo[:130]) <= TOL_PHI
+        for i in range(13):
+            assert H.rel(phi[10 * i:10 * i + 10], xo[10 * i:10 * i + 10]) <= TOL_PHI
+    assert info["status"] in (0, 1)
+    # evaluation pass (reference print_tau_prediction_rmse) at full size, prior and identified parameters
+    for p in (flat.phi_prior.astype(np.float64), phi):
+        tot, pj = si.tau_prediction_rmse(*dev, p)
+        tot_o, pj_o = co.tau_rmse(*data, p)
+        assert abs(tot - tot_o) <= TOL_RMSE_FULL * tot_o and np.abs(pj - pj_o).max() <= TOL_RMSE_FULL * pj_o.max()
+    out1 = dm.predict_rmse(*dev, torch.from_numpy(phi))
+    assert torch.equal(out1, dm.predict_rmse(*dev, torch.from_numpy(phi)))            # no atomics: bit-reproducible
+    # checksum of checksums: x^T G x - 2 x^T r + s is the stack's squared residual; its joint rows are what the
+    # evaluation pass sums when friction is left out (quirk Q7), so that part is bounded by the whole
+    x0 = np.concatenate([phi, np.zeros(24)])
+    ssr = float(x0 @ G @ x0 - 2 * x0 @ r + s)
+    tot, _ = si.tau_prediction_rmse(*dev, phi)
+    assert 0 < tot * N <= ssr * (1 + 1e-9)
+
+
+def test_full_size_1m_g1_vs_oracle():
+    """BASELINE configs[3], the headline configuration: the 1 000 000-sample G1-12dof log of bench.py.  The fused Gram of
+    the whole log against the oracle's C twin (all host cores, a few seconds) at 1e-12; additivity over the 8-rank shard
+    boundaries; and the evaluation pass of the first 150 000 samples against the oracle's at 1e-9."""
+    from oracle.cbuild import COracle
+    N, c = 1_000_000, 154
+    flat = H.flat_model("g1_12dof")
+    q, dq, ddq, cnt = H.synth.make_trajectory(flat, N, H.synth.SEEDS["g1_1m"])
+    tau = H.synth.synth_tau(flat, N, 11, scale=10.0)
+    data = (q, dq, ddq, tau, cnt)
+    dm = _dev(flat)
+    dev = _up(data)
+    co = COracle(H.oracle_tree(flat), flat.ee_names)
+    so, _ = co.gram(*data)
+    st = dm.gram_accumulate(*dev)
+    G, r, s, n = H.split_stats(st.cpu().numpy(), c)
+    Go, ro, s_o, n_o = H.split_stats(so, c)
+    assert H.rel(G, Go) <= TOL_GRAM and H.rel(r, ro) <= TOL_GRAM and abs(s - s_o) <= TOL_GRAM * s_o and n == n_o == 18 * N
+    from system_identification_b200.distributed import shard_bounds
+    acc = torch.zeros_like(st)
+    for rk in range(8):
+        lo, hi = shard_bounds(N, rk, 8)
+        dm.gram_accumulate(*(a[:, lo:hi] for a in dev), stats=acc)
+    assert H.rel(acc.cpu().numpy(), so) <= TOL_GRAM
+    M = 150_000
+    phi = flat.phi_prior.astype(np.float64)
+    out = dm.predict_rmse(*(a[:, :M] for a in dev), torch.from_numpy(phi)).cpu().numpy()
+    tot_o, pj_o = co.tau_rmse(*(a[:, :M] for a in data), phi)
+    assert abs(out[0] - tot_o) <= TOL_RMSE_FULL * tot_o and np.abs(out[1:] - pj_o).max() <= TOL_RMSE_FULL * pj_o.max()
+
+
 def test_full_size_properties_20k():
-    """BASELINE configs at N = 20 000: properties that do not need the oracle at that size."""
+    """Size-independent properties at N = 20 000 (additivity over shards, linearity in tau)."""
     flat, data = H.small_log("spot", 20000)
     dm = _dev(flat)
     dev = _up(data)
@@ -324,25 +418,16 @@ def test_full_size_properties_20k():
     st = dm.gram_accumulate(*dev)
     G, r, s, n = H.split_stats(st.cpu().numpy(), c)
     assert n == 18 * 20000 and np.array_equal(G, G.T) and np.linalg.eigvalsh(G).min() >= -1e-9 * np.abs(G).max()
-    # additivity over shards (the multi-GPU reduction in miniature) and determinism
+    # additivity over shards (the multi-GPU reduction in miniature)
     halves = dm.gram_accumulate(*(a[:, :9000] for a in dev))
     dm.gram_accumulate(*(a[:, 9000:] for a in dev), stats=halves)
     assert H.rel(halves.cpu().numpy(), st.cpu().numpy()) <= 1e-13
-    assert torch.equal(dm.gram_accumulate(*dev), st)
     # linearity in tau: r(tau1 + tau2) = r(tau1) + r(tau2); G does not depend on tau
     tau2 = torch.roll(dev[3], 7, dims=1)
     r1 = dm.gram_accumulate(*dev)[c * c:c * c + c]
     r2 = dm.gram_accumulate(dev[0], dev[1], dev[2], tau2, dev[4])[c * c:c * c + c]
     r12 = dm.gram_accumulate(dev[0], dev[1], dev[2], (dev[3] + tau2).contiguous(), dev[4])[c * c:c * c + c]
     assert H.rel((r1 + r2).cpu().numpy(), r12.cpu().numpy()) <= 1e-12
-    # phi^T G phi - 2 phi^T r + s == N * 18/... == sum of squared residuals == rmse pass (checksum of checksums)
-    phi = torch.from_numpy(flat.phi_prior.astype(np.float64)).cuda()
-    x = torch.cat([phi, torch.zeros(24, dtype=torch.float64, device="cuda")])
-    Gt = st[:c * c].view(c, c)
-    ssr = float(x @ Gt @ x - 2 * x @ st[c * c:c * c + c] + st[c * c + c])
-    out = dm.predict_rmse(*dev, phi).cpu().numpy()
-    # the rmse pass only sees joint rows; the Gram sees all 18: compare through a second Gram restricted check instead
-    assert ssr > 0 and out[0] > 0 and out[0] * 20000 <= ssr * (1 + 1e-9)
 
 
 TOL_FILT = 1e-10       # relative to the max-abs of the scipy result (fp64 recursions / fits in a different summation order)

@@ -177,3 +177,18 @@ def test_rmse_formulas_quirk_q7():
     err = (A[:, :130] @ phi - b).reshape(6, t.nv)[:, 6:]
     assert abs(tot - np.mean(np.sum(err ** 2, axis=1))) <= 1e-12 * tot          # mean squared norm, no root
     assert np.abs(pj - np.sqrt(np.mean(err ** 2, axis=0))).max() <= 1e-12 * pj.max()
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_c_twin_rmse_matches_numpy_oracle(name):
+    """oracle_tau_rmse (the C twin the full-size GPU tests compare against) == dy.tau_prediction_rmse, the numpy
+    restatement of reference src/sys_identification.py:421-437."""
+    from oracle.cbuild import COracle
+    flat, data = H.small_log(name, 40, seed=13)
+    t = H.oracle_tree(flat)
+    co = COracle(t, flat.ee_names)
+    rng = np.random.default_rng(5)
+    for phi in (flat.phi_prior.astype(float), flat.phi_prior.astype(float) * (1 + 0.1 * rng.standard_normal(130))):
+        tot, pj = dy.tau_prediction_rmse(t, *data, phi, flat.ee_names)
+        tot_c, pj_c = co.tau_rmse(*data, phi, nthreads=2)
+        assert abs(tot_c - tot) <= 1e-12 * tot and np.abs(pj_c - pj).max() <= 1e-12 * pj.max()
