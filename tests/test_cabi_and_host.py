@@ -193,3 +193,23 @@ def test_ingest_column_lists_match_the_reference_scripts():
                      lambda: ingest.fd_rate(np.arange(4.0), np.zeros((2, 4))), lambda: ingest.round_dat(np.zeros(3))):
             with pytest.raises(RuntimeError, match="no CPU fallback"):
                 call()
+
+
+@pytest.mark.parametrize("name", H.ROBOTS)
+def test_host_consistency_mirror_equals_oracle(name):
+    """SystemIdentification.get_physical_consistency (host, no GPU) == oracle/consistency.py, the restatement of reference
+    src/sys_identification.py:324-389, on the prior and on perturbed (partly inconsistent) parameter vectors."""
+    from oracle import consistency as oc
+    from system_identification_b200.sys_identification import SystemIdentification
+    flat = H.flat_model(name)
+    si = SystemIdentification.from_flat_model(flat)
+    rng = np.random.default_rng(7)
+    prior = np.asarray(si.get_phi_prior(), dtype=np.float64)
+    for phi in (prior, prior * (1 + 0.5 * rng.standard_normal(prior.size))):
+        got = si.get_physical_consistency(phi)
+        ref = oc.physical_consistency(phi, flat.ellipsoids)
+        for a, b in zip(got, ref):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+    # a consistent prior has non-negative margins everywhere (the reference's acceptance rule, :325-326)
+    ref = oc.physical_consistency(prior, flat.ellipsoids)
+    assert min(np.min(np.real(v)) for v in ref[:3]) > -1e-6

@@ -69,7 +69,11 @@ def test_solve_llsq_svd_on_the_projected_regressor(name):
 
 
 @pytest.mark.parametrize("name", H.ROBOTS)
-def test_physical_consistency_batch_vs_host_mirror(name):
+def test_physical_consistency_batch_vs_oracle(name):
+    """consistency_kernel (sysid_physical_consistency) against oracle/consistency.py, the restatement of reference
+    src/sys_identification.py:324-389 -- and the host mirror (SystemIdentification.get_physical_consistency) against the
+    same oracle (bit for bit: both run numpy's float32 eigvals on the same float32 matrices)."""
+    from oracle import consistency as oc
     from system_identification_b200.sys_identification import SystemIdentification
     flat = H.flat_model(name)
     si = SystemIdentification.from_flat_model(flat)
@@ -79,7 +83,9 @@ def test_physical_consistency_batch_vs_host_mirror(name):
     out = si.get_physical_consistency_batch(phis)
     assert out.shape == (41, 5, 13)
     for i in (0, 1, 17, 40):
-        ref = np.array([np.real(np.asarray(v, dtype=np.complex128)) for v in si.get_physical_consistency(phis[i])])   # (5, L)
+        ref = np.array([np.real(np.asarray(v, dtype=np.complex128)) for v in oc.physical_consistency(phis[i], flat.ellipsoids)])   # (5, L)
+        host = np.array([np.real(np.asarray(v, dtype=np.complex128)) for v in si.get_physical_consistency(phis[i])])
+        assert np.array_equal(host, ref), (name, i)
         for k in range(5):
             scale = max(np.abs(phis[i]).max(), np.abs(ref[k]).max(), 1.0) if k < 4 else np.abs(ref[k]).max()
             # the reference's eigvals run in float32 (its matrices are np.float32): float32 agreement is all there is
