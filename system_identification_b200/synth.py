@@ -183,7 +183,9 @@ def identifiable_tau_device(flat: FlatModel, dm, dev, seed, perturb=0.05, bv_max
         F = torch.einsum("nrc,c->nr", Y, phi_true)
         rhs = torch.einsum("nrk,nk->nr", P, F)
         PS = P[:, :, 6:]
-        sol = torch.einsum("ndk,nk->nd", torch.linalg.pinv(PS), rhs)                     # (n, d) minimum-norm least squares
+        # minimum-norm least squares; P S^T has rank 18 - rank(J_c) - (0..6) only, so the cutoff must sit well above the
+        # rounding noise of its zero singular values (1e-15 would let them through and produce torques of 1e8 N m)
+        sol = torch.einsum("ndk,nk->nd", torch.linalg.pinv(PS, rtol=1e-9), rhs)
         dqj = sl[1][6:, :].T
         t = sol + bv * dqj + bc * torch.sign(dqj) + noise * torch.randn(sol.shape, generator=gen, device="cuda", dtype=torch.float64)
         out[:, lo:hi] = t.T

@@ -74,6 +74,7 @@ class SystemIdentification(object):
         self._last_key = None
         self._last_tau_key = None
         self._last_out = None
+        self._block = None
 
     # ------------------------------------------------------------------ device plumbing
     @property
@@ -87,14 +88,70 @@ class SystemIdentification(object):
             self._device_model = DeviceModel(self._flat)
         return self._device_model
 
+    # The reference demos call the two per-sample producers inside Python loops over q[:, i] (demo/solo_identification.py:36-55):
+    # N launches of one sample each would be all latency.  When the five vectors are column views of 2-D arrays (which is what
+    # q[:, i] is), the whole block of COMPAT_CHUNK columns around i is computed in ONE sysid_projected_batch launch on the
+    # parent arrays and the following calls are served from it -- after checking that the bytes handed in are the bytes the
+    # block was computed from.  Anything else (plain vectors, lists) takes the single-sample launch.
+    COMPAT_CHUNK = 4096
+
+    @staticmethod
+    def _column_of(v):
+        """(parent 2-D array, column index) when v is a column view parent[:, i]; None otherwise."""
+        if not isinstance(v, np.ndarray) or v.ndim != 1:
+            return None
+        b = v.base
+        if not isinstance(b, np.ndarray) or b.ndim != 2 or b.shape[0] != v.shape[0] or b.shape[1] == 0:
+            return None
+        if v.shape[0] > 1 and v.strides[0] != b.strides[0]:
+            return None
+        off = v.__array_interface__["data"][0] - b.__array_interface__["data"][0]
+        if b.strides[1] <= 0 or off < 0 or off % b.strides[1] != 0:
+            return None
+        i = off // b.strides[1]
+        return (b, int(i)) if i < b.shape[1] else None
+
+    def _block_for(self, vecs):
+        """vecs = (q, dq, ddq, tau or None, cnt) column views -> (block dict, local index) or None."""
+        loc = [None if v is None else self._column_of(v) for v in vecs]
+        if any(l is None for l, v in zip(loc, vecs) if v is not None):
+            return None
+        idx = {l[1] for l in loc if l is not None}
+        N = {l[0].shape[1] for l in loc if l is not None}
+        if len(idx) != 1 or len(N) != 1:
+            return None
+        i, N = idx.pop(), N.pop()
+        ids = tuple(None if l is None else (id(l[0]), l[0].__array_interface__["data"][0], l[0].shape, l[0].dtype.str) for l in loc)
+        blk = self._block
+        lo = (i // self.COMPAT_CHUNK) * self.COMPAT_CHUNK
+        # the friction blocks do not depend on tau: a block computed with torques serves a call without them
+        same = blk is not None and blk["lo"] == lo and all(a == b_ for k, (a, b_) in enumerate(zip(blk["ids"], ids)) if not (k == 3 and b_ is None))
+        if not same:
+            from .ops import to_device
+            hi = min(N, lo + self.COMPAT_CHUNK)
+            host = [np.zeros((self.joints_dof, hi - lo)) if l is None else np.ascontiguousarray(l[0][:, lo:hi], dtype=np.float64) for l in loc]
+            A, b = self.device_model.projected_batch(*(to_device(a) for a in host), friction=True)
+            blk = {"ids": ids, "lo": lo, "host": host, "A": A.cpu().numpy(), "b": b.cpu().numpy()}
+            self._block = blk
+        k = i - lo
+        # the served bytes must be the bytes that were asked for (a parent array modified in place invalidates the block)
+        for v, h in zip(vecs, blk["host"]):
+            if v is not None and not np.array_equal(np.asarray(v, dtype=np.float64), h[:, k], equal_nan=True):
+                self._block = None
+                return None
+        return blk, k
+
     def _one_sample(self, q, dq, ddq, tau, cnt):
-        """Per-sample compat path: one launch of the projected-batch kernel with N = 1.  The demos call
-        get_proj_regressor_torque and get_proj_friction_regressors with the same sample back to back;
-        the second call is served from the first one's result."""
-        import torch
+        """Per-sample compat path: (A (nv, c), b (nv)) of one sample; served from a block launch when the arguments are
+        column views of the log (see above), else one launch of the projected-batch kernel with N = 1."""
         from .ops import to_device
         q = np.asarray(q); dq = np.asarray(dq); ddq = np.asarray(ddq); cnt = np.asarray(cnt)
-        tau = np.zeros(self.joints_dof) if tau is None else np.asarray(tau)
+        tau_in = None if tau is None else np.asarray(tau)
+        hit = self._block_for((q, dq, ddq, tau_in, cnt))
+        if hit is not None:
+            blk, k = hit
+            return blk["A"][k], blk["b"][k]
+        tau = np.zeros(self.joints_dof) if tau_in is None else tau_in
         key = (q.tobytes(), dq.tobytes(), ddq.tobytes(), cnt.tobytes())
         if self._last_key == key and self._last_tau_key == tau.tobytes():
             return self._last_out
@@ -106,8 +163,8 @@ class SystemIdentification(object):
         parts = []
         for n in (self.nq, self.nv, self.nv, self.joints_dof, self._nb_ee):
             parts.append(dev[o:o + n]); o += n
-        A, b, P = dm.projected_batch(*parts, friction=True, want_P=True)
-        out = (A[0].cpu().numpy(), b[0].cpu().numpy(), P[0].cpu().numpy())
+        A, b = dm.projected_batch(*parts, friction=True)
+        out = (A[0].cpu().numpy(), b[0].cpu().numpy())
         self._last_key, self._last_tau_key, self._last_out = key, tau.tobytes(), out
         return out
 
@@ -169,13 +226,16 @@ class SystemIdentification(object):
 
     # ------------------------------------------------------------------ per-sample producers (reference :401-418)
     def get_proj_regressor_torque(self, q, dq, ddq, tau, cnt):
-        A, b, _ = self._one_sample(q, dq, ddq, tau, cnt)
+        A, b = self._one_sample(q, dq, ddq, tau, cnt)
         return A[:, :self._num_inertial_params * self._num_links].copy(), b.copy()
 
     def get_proj_friction_regressors(self, q, dq, ddq, cnt):
         # the friction blocks do not depend on tau: reuse the launch of the matching regressor call if there was one
         key = (np.asarray(q).tobytes(), np.asarray(dq).tobytes(), np.asarray(ddq).tobytes(), np.asarray(cnt).tobytes())
-        A = self._last_out[0] if key == self._last_key else self._one_sample(q, dq, ddq, None, cnt)[0]
+        if self._block is None and self._last_out is not None and key == self._last_key:
+            A = self._last_out[0]
+        else:
+            A = self._one_sample(q, dq, ddq, None, cnt)[0]
         p, d = self._num_inertial_params * self._num_links, self.joints_dof
         return A[:, p:p + d].copy(), A[:, p + d:p + 2 * d].copy()
 

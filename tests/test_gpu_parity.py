@@ -339,6 +339,7 @@ def test_full_size_20k_vs_oracle(name):
     dev = list(_up((q, dq, ddq, np.zeros((12, N)), cnt)))
     dev[3] = _device_identifiable_tau(flat, dm, dev, seed=23)
     tau = dev[3].cpu().numpy()
+    assert np.isfinite(tau).all() and np.abs(tau).max() < 1e4            # a well-posed log: no blown-up least-squares torques
     data = (q, dq, ddq, tau, cnt)
     co = COracle(H.oracle_tree(flat), flat.ee_names)
     so, _ = co.gram(*data)
