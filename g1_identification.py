@@ -34,7 +34,7 @@ def read_csv_log(csv_path, q_name, filter_type):
         b, a = filters.butter_lowpass(5, 0.15)
         dq, ddq, tau = (filters.filtfilt(b, a, v, float32_input=True) for v in (dq, ddq, tau))
     elif filter_type == "savitzky":
-        dq, ddq, tau = (filters.savgol_filter(v, 21, 5) for v in (dq, ddq, tau))
+        dq, ddq, tau = (filters.savgol_filter(v, 21, 5, float32_input=True) for v in (dq, ddq, tau))
     return q, dq, ddq, tau, cnt
 
 

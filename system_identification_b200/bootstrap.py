@@ -55,18 +55,26 @@ def bootstrap_identify(sysid, q, dq, ddq, tau, cnt, B=1024, block=1, seed=1005, 
             dm.gram_accumulate(*sl, friction=friction, stats=per_block[k])
         stats = Wl @ per_block                              # (nb, slen): every statistic is additive over blocks
     x = torch.empty((nb, c), dtype=torch.float64, device=dev[0].device)
-    info = None
-    if nb > 0:
-        x, info = sdp_solve(stats, L, nd, sysid.get_phi_prior(), sysid.get_bounding_ellipsoids(), sysid.get_robot_mass(),
-                            lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER, reg_type=reg_type,
-                            batch=nb)
+    info, err = None, None
+    try:
+        if nb > 0:
+            x, info = sdp_solve(stats, L, nd, sysid.get_phi_prior(), sysid.get_bounding_ellipsoids(), sysid.get_robot_mass(),
+                                lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER, reg_type=reg_type,
+                                batch=nb)
+    except Exception as e:                                  # noqa: BLE001 -- every rank must still reach the collective below
+        err = e
     if ws > 1:
         import torch.distributed as dist
-        sizes = [D.shard_bounds(B, r, ws) for r in range(ws)]
-        full = torch.zeros((B, c), dtype=torch.float64, device=dev[0].device)
-        full[lo:hi] = x
+        full = torch.zeros((B + 1, c), dtype=torch.float64, device=dev[0].device)
+        if err is None:
+            full[lo:hi] = x
+        else:
+            full[B, 0] = 1.0                                # failure flag, summed over ranks
         dist.all_reduce(full, op=dist.ReduceOp.SUM)         # disjoint row ranges: a gather
-        x = full
-        del sizes
+        if err is None and float(full[B, 0].item()) != 0.0:
+            err = RuntimeError("bootstrap_identify(): the batched LMI solve failed on another rank")
+        x = full[:B]
+    if err is not None:
+        raise err
     out = (x.cpu().numpy(), info)
     return out + (stats,) if return_stats else out

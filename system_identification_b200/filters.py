@@ -72,8 +72,11 @@ def filtfilt(b, a, x, out=None, float32_input=False):
     return out
 
 
-def savgol_filter(x, window_length, polyorder):
-    """scipy.signal.savgol_filter(x, window_length, polyorder) with its defaults (deriv=0, mode='interp'), along axis 1."""
+def savgol_filter(x, window_length, polyorder, float32_input=False):
+    """scipy.signal.savgol_filter(x, window_length, polyorder) with its defaults (deriv=0, mode='interp'), along axis 1.
+    float32_input=True reproduces what scipy returns for a float32 log (the reference's np.loadtxt(dtype=float32) arrays,
+    demo/solo_identification.py:26-32): ndimage's convolve1d accumulates in double and stores float32, and the polynomial
+    edge fit is evaluated in double and assigned into the float32 result -- i.e. the fp64 result rounded through float32."""
     _require_cuda()
     lib = _lib.load()
     x = _check(x, "x")
@@ -86,7 +89,7 @@ def savgol_filter(x, window_length, polyorder):
     out = torch.empty((ch, N), dtype=torch.float64, device=x.device)
     ws = torch.empty(lib.sysid_savgol_workspace_bytes(int(window_length)), dtype=torch.uint8, device=x.device)
     _lib.check(lib.sysid_savgol(int(window_length), int(polyorder), _ptr(x), _ptr(out), ch, N, x.stride(0), _ptr(ws), ws.numel(), _stream()))
-    return out
+    return out.to(torch.float32).to(torch.float64) if float32_input else out
 
 
 def preprocess(robot_q, robot_dq, robot_ddq, robot_tau, robot_contact, filter_type):
@@ -100,5 +103,6 @@ def preprocess(robot_q, robot_dq, robot_ddq, robot_tau, robot_contact, filter_ty
         f32 = all(np.asarray(v).dtype == np.float32 for v in (robot_dq, robot_ddq, robot_tau))
         dq, ddq, tau = (filtfilt(b, a, v, float32_input=f32) for v in (dq, ddq, tau))
     elif filter_type == "savitzky":
-        dq, ddq, tau = savgol_filter(dq, 21, 5), savgol_filter(ddq, 21, 5), savgol_filter(tau, 21, 5)
+        f32 = all(np.asarray(v).dtype == np.float32 for v in (robot_dq, robot_ddq, robot_tau))
+        dq, ddq, tau = (savgol_filter(v, 21, 5, float32_input=f32) for v in (dq, ddq, tau))
     return q, dq, ddq, tau, cnt

@@ -38,7 +38,14 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
              friction=True, return_info=False, sharded=False, weights=None):
     """sysid: SystemIdentification.  Arrays: (channels x N) numpy or torch (host or device).
     With torch.distributed initialised and sharded=False every rank passes the FULL log and takes its own
-    contiguous shard; with sharded=True each rank passes only its shard.  Returns phi (10 L,) [, b_v, b_c, info]."""
+    contiguous shard; with sharded=True each rank passes only its shard.  Returns phi (10 L,) [, b_v, b_c, info].
+
+    Deviations from the reference that are REPORTED, never silent (a RuntimeWarning each, counts in info):
+      * samples with a non-finite input are skipped (the reference would propagate NaN into the whole stack);
+      * a contact Jacobian that loses row rank has the dependent row dropped at 1e-13 of the largest row norm squared
+        (numpy's pinv cuts singular values at 1e-15 sigma_max; the two differ only where cond(J_c) > 3e6).
+    A log in which EVERY sample is skipped raises ValueError."""
+    import warnings
     from .solver import NEWTON_STEPS_PER_IPM_ITER
     dm = sysid.device_model
     rank, ws = D.world()
@@ -49,9 +56,16 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         if weights is not None:
             weights = weights[lo:hi]
     arrays = (q, dq, ddq, tau, cnt)
+    device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+    L, nd = sysid.get_num_links(), (sysid.joints_dof if friction else 0)
+    c = 10 * L + 2 * nd
+    # [stats (c*c + c + 2) | rank-loss count, skipped count] in ONE buffer so that a single all-reduce merges both
+    buf = torch.zeros(c * c + c + 2 + 2, dtype=torch.float64, device=device)
+    stats = buf[:c * c + c + 2]
+    counts = torch.zeros(2, dtype=torch.int64, device=device)
     if _host_streamable(arrays, weights):
-        # host float64 arrays: chunked upload overlapped with the kernel inside the library
-        stats = dm.gram_accumulate_host(*arrays, friction=friction, weights=weights)
+        # host float64 / float32 arrays: chunked upload overlapped with the kernel inside the library
+        dm.gram_accumulate_host(*arrays, friction=friction, weights=weights, stats=stats, info=counts)
     else:
         dev = [a if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64) else to_device(a) for a in arrays]
         dev = [a if a.stride(1) == 1 else a.contiguous() for a in dev]
@@ -59,29 +73,46 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
             dev = [a.contiguous() for a in dev]
         if weights is not None and not (isinstance(weights, torch.Tensor) and weights.is_cuda):
             weights = torch.as_tensor(np.asarray(weights, dtype=np.float64)).cuda()
-        stats = dm.gram_accumulate(*dev, friction=friction, weights=weights)
-    D.allreduce_stats(stats)
-    L, nd = sysid.get_num_links(), (sysid.joints_dof if friction else 0)
-    c = 10 * L + 2 * nd
+        dm.gram_accumulate(*dev, friction=friction, weights=weights, stats=stats, info=counts)
+    buf[c * c + c + 2:] = counts.to(torch.float64)
+    D.allreduce_stats(buf)
+    # rank 0 solves; its outcome (status and solution, or the fact that it raised) reaches every rank through ONE
+    # broadcast, so that no rank is left waiting in a collective when the solve fails on the host
+    out = torch.zeros(c + 4, dtype=torch.float64, device=device)      # [x (c) | status | failed | rank-loss | skipped]
+    info, err = None, None
     if rank == 0:
-        x, info = sdp_solve(stats, L, nd, sysid.get_phi_prior(), sysid.get_bounding_ellipsoids(), sysid.get_robot_mass(),
-                            lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER, reg_type=reg_type)
-        status = int(info[0]["status"])
-        x = x[0]
-    else:
-        x = torch.empty(c, dtype=torch.float64, device=stats.device)
-        info, status = None, 0
+        try:
+            n_rows = float(buf[c * c + c + 1].item())
+            if not n_rows > 0.0:
+                raise ValueError("identify(): no usable sample (every sample of the log has a non-finite input or zero weight)")
+            x, info = sdp_solve(stats, L, nd, sysid.get_phi_prior(), sysid.get_bounding_ellipsoids(), sysid.get_robot_mass(),
+                                lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER, reg_type=reg_type)
+            out[:c] = x[0]
+            out[c] = float(int(info[0]["status"]))
+        except Exception as e:                                           # noqa: BLE001 -- re-raised below, on every rank
+            err = e
+            out[c + 1] = 1.0
+        out[c + 2:] = buf[c * c + c + 2:]
     if ws > 1:
-        st = torch.tensor([status], dtype=torch.int32, device=stats.device)
-        D.broadcast_solution(st)
-        status = int(st.item())
-        D.broadcast_solution(x)
+        D.broadcast_solution(out)
+    outh = out.cpu().numpy()
+    status, failed, n_rankloss, n_skipped = int(outh[c]), outh[c + 1] != 0.0, int(outh[c + 2]), int(outh[c + 3])
+    if failed:
+        if err is not None:
+            raise err
+        raise RuntimeError("identify(): the LMI solve failed on rank 0 (see that rank's exception)")
+    if n_skipped:
+        warnings.warn(f"identify(): {n_skipped} sample(s) with a non-finite input were skipped (the reference would propagate NaN)", RuntimeWarning, stacklevel=2)
+    if n_rankloss:
+        warnings.warn(f"identify(): the contact Jacobian lost row rank in {n_rankloss} sample(s); dependent rows were dropped "
+                      "(pinv semantics, cutoff 1e-13 of the largest squared row norm)", RuntimeWarning, stacklevel=2)
     if status not in (0, 1):   # 1 = optimal_inaccurate, accepted like the reference accepts cp.OPTIMAL_INACCURATE
         print("The problem did not solve to optimality. Status:", status)
         raise ValueError("The problem did not solve to optimality.")
-    xh = x.cpu().numpy()
+    xh = outh[:c]
     phi = xh[:10 * L].copy()
     if not return_info:
         return phi
-    info_d = None if info is None else {k: info[0][k].item() for k in info.dtype.names}
+    info_d = {} if info is None else {k: info[0][k].item() for k in info.dtype.names}
+    info_d.update(status=status, rank_deficient_samples=n_rankloss, skipped_samples=n_skipped)
     return phi, xh[10 * L:10 * L + nd].copy(), xh[10 * L + nd:].copy(), info_d

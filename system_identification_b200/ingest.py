@@ -53,6 +53,36 @@ def _as_dev2d(x, device=None):
     return t if t.stride(1) == 1 else t.contiguous()
 
 
+def _patch_unconverted(out, raw, delim, rows, cols, transposed, f32, empty_nan, where=""):
+    """The device converts a field only when it can do so EXACTLY (Clinger's fast path and a 128-bit integer division:
+    every '%.6f' / '%.17g' / '%.18e' field of ordinary magnitude).  Fields outside that domain -- e.g. floating-point
+    residue such as -2.7755575615628914e-17 in a logger CSV -- are flagged by the kernel (written as NaN and counted) and
+    converted here, on the host, by Python's correctly rounded float(), which is what np.loadtxt / pandas would have used:
+    only those few fields, patched into the device array.  A field that is not a number raises ValueError, like np.loadtxt."""
+    cand = torch.isnan(out).nonzero().cpu().numpy()                   # flagged fields (and literal nan fields: re-read, unchanged)
+    cuts = np.flatnonzero((raw == delim) | (raw == 0x0A))
+    vals = np.empty(len(cand), dtype=np.float64)
+    for n_, (a, b) in enumerate(cand):
+        row, col = (int(b), int(a)) if transposed else (int(a), int(b))
+        k = row * cols + col
+        lo = int(cuts[k - 1]) + 1 if k > 0 else 0
+        hi = int(cuts[k]) if k < cuts.size else raw.size
+        tok = bytes(raw[lo:hi]).strip()
+        if tok == b"" and empty_nan:
+            vals[n_] = np.nan
+            continue
+        try:
+            vals[n_] = float(tok)
+        except ValueError:
+            raise ValueError(f"could not convert string {tok!r} to float at row {row}, column {col}{where}") from None
+    if f32:
+        vals = vals.astype(np.float32).astype(np.float64)
+    if len(cand):
+        ij = torch.from_numpy(cand).to(out.device)
+        out[ij[:, 0], ij[:, 1]] = torch.from_numpy(vals).to(out.device)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ .dat text
 def load_dat(source, delimiter="\t", dtype=np.float32, device=None):
     """np.loadtxt(source, delimiter=delimiter, dtype=dtype) for the text np.savetxt(fmt='%.6f') writes, parsed on the
@@ -90,15 +120,12 @@ def load_dat(source, delimiter="\t", dtype=np.float32, device=None):
     info = (C.c_int64 * 4)()
     rc = lib.sysid_dat_parse(_ptr(text), n, ord(delimiter), _ptr(ws), ws.numel(), rows, cols, _ptr(out), cols, 1 if f32 else 0,
                              info, _stream())
+    if rc == -1 and info[0] > 0 and info[2] == 0:
+        # fields outside the device's exact-conversion domain: converted on the host, only those (see _patch_unconverted)
+        where = "" if isinstance(source, (bytes, bytearray, memoryview)) else f" in {os.fspath(source)}"
+        return _patch_unconverted(out, raw[:n], ord(delimiter), rows, cols, False, f32, False, where)
     if rc == -1:
-        msg = lib.sysid_last_error().decode()
-        if info[0] > 0:                              # name the offending text, as np.loadtxt does (error path only)
-            cuts = np.flatnonzero((raw[:n] == ord(delimiter)) | (raw[:n] == 0x0A))
-            k = int(info[1])
-            lo = int(cuts[k - 1]) + 1 if k > 0 else 0
-            hi = int(cuts[k]) if k < cuts.size else n
-            msg += f": {bytes(raw[lo:hi])!r}" + ("" if isinstance(source, (bytes, bytearray, memoryview)) else f" in {os.fspath(source)}")
-        raise ValueError(msg)
+        raise ValueError(lib.sysid_last_error().decode())
     _lib.check(rc)
     return out
 
@@ -143,15 +170,11 @@ def load_csv(source, device=None):
     out = torch.empty((cols, rows), dtype=torch.float64, device=dev)
     info = (C.c_int64 * 4)()
     rc = lib.sysid_dat_parse_ex(_ptr(text), n, ord(","), _ptr(ws), ws.numel(), rows, cols, _ptr(out), rows, 2 | 4, info, _stream())
+    if rc == -1 and info[0] > 0 and info[2] == 0:
+        _patch_unconverted(out, body[:n], ord(","), rows, cols, True, False, True)
+        return {name: out[i] for i, name in enumerate(names)}
     if rc == -1:
-        msg = lib.sysid_last_error().decode()
-        if info[0] > 0:
-            cuts = np.flatnonzero((body[:n] == ord(",")) | (body[:n] == 0x0A))
-            k = int(info[1])
-            lo = int(cuts[k - 1]) + 1 if k > 0 else 0
-            hi = int(cuts[k]) if k < cuts.size else n
-            msg += f": {bytes(body[lo:hi])!r} (column {names[k % cols]!r})"
-        raise ValueError(msg)
+        raise ValueError(lib.sysid_last_error().decode())
     _lib.check(rc)
     return {name: out[i] for i, name in enumerate(names)}
 
@@ -167,7 +190,7 @@ def read_data(path, robot_name, filter_type, q_name="q"):
         b, a = filters.butter_lowpass(5, 0.15)
         dq, ddq, tau = (filters.filtfilt(b, a, v, float32_input=True) for v in (dq, ddq, tau))
     elif filter_type == "savitzky":
-        dq, ddq, tau = (filters.savgol_filter(v, 21, 5) for v in (dq, ddq, tau))
+        dq, ddq, tau = (filters.savgol_filter(v, 21, 5, float32_input=True) for v in (dq, ddq, tau))
     return q, dq, ddq, tau, cnt
 
 

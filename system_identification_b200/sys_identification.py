@@ -30,6 +30,11 @@ class SystemIdentification(object):
     def __init__(self, urdf_file, config_file, floating_base):
         self._urdf_path = urdf_file
         self._floating_base = floating_base
+        if not floating_base:
+            # reference src/sys_identification.py:15-18,29-37 (pin.buildModelFromUrdf(path), _base_dof = 0, S = I): no demo
+            # uses it and the kernels' tree layout assumes the free-flyer root
+            raise NotImplementedError("floating_base=False (fixed-base models) is not supported by the B200 path: the kernels "
+                                      "assume a free-flyer root joint, as every reference driver script uses")
         with open(config_file, "r") as file:
             config = yaml.safe_load(file)
         robot_config = config.get("robot", {})
@@ -75,6 +80,7 @@ class SystemIdentification(object):
         self._last_tau_key = None
         self._last_out = None
         self._block = None
+        self._prev_sig = {True: None, False: None}
 
     # ------------------------------------------------------------------ device plumbing
     @property
@@ -89,57 +95,113 @@ class SystemIdentification(object):
         return self._device_model
 
     # The reference demos call the two per-sample producers inside Python loops over q[:, i] (demo/solo_identification.py:36-55):
-    # N launches of one sample each would be all latency.  When the five vectors are column views of 2-D arrays (which is what
-    # q[:, i] is), the whole block of COMPAT_CHUNK columns around i is computed in ONE sysid_projected_batch launch on the
-    # parent arrays and the following calls are served from it -- after checking that the bytes handed in are the bytes the
-    # block was computed from.  Anything else (plain vectors, lists) takes the single-sample launch.
+    # N launches of one sample each would be all latency.  The arguments of consecutive calls are 1-D views whose data
+    # pointers advance by exactly one element (np.loadtxt arrays: +4 bytes; scipy filtfilt output, a reversed-and-sliced
+    # view: -8 bytes).  When a call's pointers sit one element after the previous call's, the columns that FOLLOW are read
+    # speculatively through strided views (bounded by the memory of the arrays that own the data), the whole block of up to
+    # COMPAT_CHUNK samples is computed in ONE sysid_projected_batch launch, and later calls are served from it -- after
+    # checking that the bytes handed in are the bytes the block was computed from.  Everything else (plain vectors, lists,
+    # random access) takes the single-sample launch.
     COMPAT_CHUNK = 4096
 
     @staticmethod
-    def _column_of(v):
-        """(parent 2-D array, column index) when v is a column view parent[:, i]; None otherwise."""
-        if not isinstance(v, np.ndarray) or v.ndim != 1:
-            return None
+    def _owner_bounds(v):
+        """[lo, hi) byte range of the array that owns v's memory; None when v owns its data (then it is no column view)."""
         b = v.base
-        if not isinstance(b, np.ndarray) or b.ndim != 2 or b.shape[0] != v.shape[0] or b.shape[1] == 0:
+        if not isinstance(b, np.ndarray):
             return None
-        if v.shape[0] > 1 and v.strides[0] != b.strides[0]:
+        while isinstance(b.base, np.ndarray):
+            b = b.base
+        if b.ndim == 0 or b.size == 0:
             return None
-        off = v.__array_interface__["data"][0] - b.__array_interface__["data"][0]
-        if b.strides[1] <= 0 or off < 0 or off % b.strides[1] != 0:
-            return None
-        i = off // b.strides[1]
-        return (b, int(i)) if i < b.shape[1] else None
+        lo = b.__array_interface__["data"][0]
+        ext = [(n - 1) * st for n, st in zip(b.shape, b.strides)]
+        return lo + sum(e for e in ext if e < 0), lo + sum(e for e in ext if e > 0) + b.itemsize
 
-    def _block_for(self, vecs):
-        """vecs = (q, dq, ddq, tau or None, cnt) column views -> (block dict, local index) or None."""
-        loc = [None if v is None else self._column_of(v) for v in vecs]
-        if any(l is None for l, v in zip(loc, vecs) if v is not None):
+    def _sig(self, vecs):
+        """(pointer, row stride, itemsize, rows, dtype) per argument, or None when an argument cannot be a column view."""
+        out = []
+        for v in vecs:
+            if v is None:
+                out.append(None)
+                continue
+            if not isinstance(v, np.ndarray) or v.ndim != 1 or v.dtype not in (np.float32, np.float64) or v.shape[0] == 0:
+                return None
+            out.append((v.__array_interface__["data"][0], v.strides[0], v.itemsize, v.shape[0], v.dtype.str))
+        return out
+
+    def _open_block(self, vecs, sig, prev):
+        """Called when `sig` is one element after `prev` in every argument: speculative block starting at this call's column."""
+        from numpy.lib.stride_tricks import as_strided
+        from .ops import to_device
+        steps, n = [], self.COMPAT_CHUNK
+        for v, a, b in zip(vecs, sig, prev):
+            if a is None:
+                steps.append(None)
+                continue
+            if b is None or a[1:] != b[1:] or abs(a[0] - b[0]) != a[2]:
+                return None
+            e = a[0] - b[0]
+            own = self._owner_bounds(v)
+            if own is None:
+                return None
+            ptr, S, item, rows = a[0], a[1], a[2], a[3]
+            # columns j = 0 .. n-1 of rows 0 .. rows-1 live at ptr + r S + j e: keep them inside the owner and inside one row
+            lo_r, hi_r = min(0, (rows - 1) * S), max(0, (rows - 1) * S)
+            if e > 0:
+                n = min(n, (own[1] - item - ptr - hi_r) // e + 1)
+            else:
+                n = min(n, (ptr + lo_r - own[0]) // (-e) + 1)
+            if rows > 1:
+                n = min(n, abs(S) // item)
+            steps.append(e)
+        if n < 2:
             return None
-        idx = {l[1] for l in loc if l is not None}
-        N = {l[0].shape[1] for l in loc if l is not None}
-        if len(idx) != 1 or len(N) != 1:
-            return None
-        i, N = idx.pop(), N.pop()
-        ids = tuple(None if l is None else (id(l[0]), l[0].__array_interface__["data"][0], l[0].shape, l[0].dtype.str) for l in loc)
+        host = []
+        for v, a, e in zip(vecs, sig, steps):
+            if a is None:
+                host.append(np.zeros((self.joints_dof, n)))
+            else:
+                host.append(np.array(as_strided(v, shape=(a[3], n), strides=(a[1], e), writeable=False), dtype=np.float64, order="C"))
+        A, b = self.device_model.projected_batch(*(to_device(h) for h in host), friction=True)
+        return {"sig": sig, "steps": steps, "n": n, "host": host, "A": A.cpu().numpy(), "b": b.cpu().numpy()}
+
+    def _block_lookup(self, vecs, sig):
+        """(block, k) when every argument is column k of the current block and carries the bytes the block was computed from."""
         blk = self._block
-        lo = (i // self.COMPAT_CHUNK) * self.COMPAT_CHUNK
-        # the friction blocks do not depend on tau: a block computed with torques serves a call without them
-        same = blk is not None and blk["lo"] == lo and all(a == b_ for k, (a, b_) in enumerate(zip(blk["ids"], ids)) if not (k == 3 and b_ is None))
-        if not same:
-            from .ops import to_device
-            hi = min(N, lo + self.COMPAT_CHUNK)
-            host = [np.zeros((self.joints_dof, hi - lo)) if l is None else np.ascontiguousarray(l[0][:, lo:hi], dtype=np.float64) for l in loc]
-            A, b = self.device_model.projected_batch(*(to_device(a) for a in host), friction=True)
-            blk = {"ids": ids, "lo": lo, "host": host, "A": A.cpu().numpy(), "b": b.cpu().numpy()}
-            self._block = blk
-        k = i - lo
-        # the served bytes must be the bytes that were asked for (a parent array modified in place invalidates the block)
+        if blk is None:
+            return None
+        k = None
+        for a, b0, e in zip(sig, blk["sig"], blk["steps"]):
+            if a is None:
+                continue                        # a call without torques is served by a block computed with them (friction blocks)
+            if b0 is None or a[1:] != b0[1:] or (a[0] - b0[0]) % e != 0:
+                return None
+            kk = (a[0] - b0[0]) // e
+            if k is None:
+                k = kk
+            if kk != k or not (0 <= kk < blk["n"]):
+                return None
         for v, h in zip(vecs, blk["host"]):
             if v is not None and not np.array_equal(np.asarray(v, dtype=np.float64), h[:, k], equal_nan=True):
-                self._block = None
+                self._block = None              # the log was modified in place after the block was computed
                 return None
-        return blk, k
+        return blk, int(k)
+
+    def _block_for(self, vecs):
+        sig = self._sig(vecs)
+        kind = vecs[3] is None                  # the friction loop passes no torques: each kind of call has its own history
+        if sig is None:
+            self._prev_sig[kind] = None
+            return None
+        hit = self._block_lookup(vecs, sig)
+        if hit is None and self._prev_sig[kind] is not None:
+            blk = self._open_block(vecs, sig, self._prev_sig[kind])
+            if blk is not None:
+                self._block = blk
+                hit = self._block_lookup(vecs, sig)
+        self._prev_sig[kind] = sig
+        return hit
 
     def _one_sample(self, q, dq, ddq, tau, cnt):
         """Per-sample compat path: (A (nv, c), b (nv)) of one sample; served from a block launch when the arguments are

@@ -74,7 +74,7 @@ def _check(which, N, tmp_path, robot):
     g, rec, text, wall, nlaunch, flat, script = _run(which, N, tmp_path)
     assert g["SystemIdentification"] is SystemIdentification          # the script imported THIS repository's src
     assert rec["rows"] == (18 * N, 130) and rec["phi"].shape == (130,)
-    assert nlaunch <= 2 * ((N + 4095) // 4096) + 2                     # block launches, not one launch per sample
+    assert nlaunch <= 2 * ((N + 4095) // 4096 + 2)                     # block launches (+ the two calls that open a pass), not one per sample
     assert "Inertial Parameters of" in text and "RMSE for joint torques prediction using Identified parameters" in text
     # the same identification through the fused path, on the arrays the script's OWN read_data returns
     ws = os.path.dirname(os.path.dirname(script))
@@ -116,22 +116,31 @@ def test_root_spot_identification_unmodified(tmp_path):
 
 
 def test_per_sample_api_served_from_blocks_equals_single_launches():
-    """Column views are served from one block launch; plain vectors take the single-sample launch; both agree bit for bit,
-    and a parent array modified in place is noticed."""
+    """Consecutive column views (any kind: plain slices, float32, the reversed-and-sliced views scipy's filtfilt returns)
+    are served from one block launch; plain vectors and random access take the single-sample launch; both agree bit for
+    bit, and a parent array modified in place after the block was computed is noticed."""
     from system_identification_b200.sys_identification import SystemIdentification
     flat, data = H.small_log("g1_12dof", 70, seed=3)
-    si = SystemIdentification.from_flat_model(flat)
     q, dq, ddq, tau, cnt = data
     q32 = q.astype(np.float32)
+    pad = np.concatenate([np.zeros((18, 5)), dq[:, ::-1], np.zeros((18, 7))], axis=1)
+    dq_view = pad[:, ::-1][:, 7:-5]                                      # negative column stride, offset, foreign owner
+    assert np.array_equal(dq_view, dq) and dq_view.strides[1] == -8
+    si = SystemIdentification.from_flat_model(flat)
+    ref = SystemIdentification.from_flat_model(flat)
+    outs = []
+    for i in range(70):                                                  # the demo's access pattern
+        y, t = si.get_proj_regressor_torque(q32[:, i], dq_view[:, i], ddq[:, i], tau[:, i], cnt[:, i])
+        bv, bc = si.get_proj_friction_regressors(q32[:, i], dq_view[:, i], ddq[:, i], cnt[:, i])
+        outs.append((y, t, bv, bc))
+        if i >= 1:
+            assert si._block is not None and si._block["n"] == 69          # opened at the second call, bounded by the owners
     for i in (0, 1, 69, 33):
-        y, t = si.get_proj_regressor_torque(q32[:, i], dq[:, i], ddq[:, i], tau[:, i], cnt[:, i])
-        bv, bc = si.get_proj_friction_regressors(q32[:, i], dq[:, i], ddq[:, i], cnt[:, i])
-        assert si._block is not None
-        si2 = SystemIdentification.from_flat_model(flat)
-        y2, t2 = si2.get_proj_regressor_torque(q32[:, i].copy(), dq[:, i].copy(), ddq[:, i].copy(), tau[:, i].copy(), cnt[:, i].copy())
-        bv2, bc2 = si2.get_proj_friction_regressors(q32[:, i].copy(), dq[:, i].copy(), ddq[:, i].copy(), cnt[:, i].copy())
-        assert si2._block is None
+        y2, t2 = ref.get_proj_regressor_torque(q32[:, i].copy(), dq[:, i].copy(), ddq[:, i].copy(), tau[:, i].copy(), cnt[:, i].copy())
+        bv2, bc2 = ref.get_proj_friction_regressors(q32[:, i].copy(), dq[:, i].copy(), ddq[:, i].copy(), cnt[:, i].copy())
+        assert ref._block is None
+        y, t, bv, bc = outs[i]
         assert np.array_equal(y, y2) and np.array_equal(t, t2) and np.array_equal(bv, bv2) and np.array_equal(bc, bc2)
-    dq[3, 33] += 1.0                                                   # in-place edit of the parent after the block was computed
-    y3, _ = si.get_proj_regressor_torque(q32[:, 33], dq[:, 33], ddq[:, 33], tau[:, 33], cnt[:, 33])
-    assert not np.array_equal(y3, y)
+    ddq[3, 33] += 1.0                                                    # in-place edit of a parent after the block was computed
+    y3, _ = si.get_proj_regressor_torque(q32[:, 33], dq_view[:, 33], ddq[:, 33], tau[:, 33], cnt[:, 33])
+    assert not np.array_equal(y3, outs[33][0]) and si._block is None

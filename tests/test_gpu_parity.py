@@ -455,6 +455,11 @@ def test_filters_vs_scipy_fixture_and_live():
     assert g["savgol"].dtype == np.float32
     y = F.savgol_filter(up(g["x"]), 21, 5).cpu().numpy()
     assert np.abs(y - g["savgol"]).max() <= 3e-5 * np.abs(g["savgol"]).max()
+    # float32_input=True reproduces that rounding: equal to scipy's float32 result except where the fp64 value sits within
+    # a summation-order ulp of a float32 rounding boundary (then one float32 ulp apart)
+    y32 = F.savgol_filter(up(g["x"]), 21, 5, float32_input=True).cpu().numpy()
+    ref32 = g["savgol"].astype(np.float64)
+    assert np.abs(y32 - ref32).max() <= 1.3e-7 * np.abs(ref32).max() and np.mean(y32 == ref32) >= 0.999
     assert _loaded_native()
     # reference error behaviour
     with pytest.raises(ValueError):
