@@ -32,7 +32,8 @@ N_SAMPLES = int(os.environ.get("SYSID_BENCH_SAMPLES", 1_000_000))
 FLOP_PER_SAMPLE = 18 * 154 * 155 + 2 * 18 * 154          # 435 204: lower-triangle Gram + A^T b
 BYTES_PER_SAMPLE = 8 * (19 + 18 + 18 + 12 + 2)            # 552 B of fp64 input per G1-12 sample
 FP64_PEAK_FALLBACK_TFLOPS = 35.77                         # profiles/fp64_peak_r01.json: cuBLAS DGEMM 8192^3 on this pool
-CPU_SAMPLE = int(os.environ.get("SYSID_BENCH_CPU_SAMPLES", 150_000))
+CPU_SAMPLE = int(os.environ.get("SYSID_BENCH_CPU_SAMPLES", 150_000))      # cpu_baseline leg of OUR arm (bounded, ~10 s); the reference
+REF_FULL = os.environ.get("SYSID_BENCH_REF_FULL", "1") == "1"                # arm times the WHOLE log per step (same config as ours)
 WORKLOAD = f"{ROBOT} {N_SAMPLES}-sample log (BASELINE configs[3]), regressor+projector+Gram with friction columns, c=154"
 
 
@@ -45,15 +46,35 @@ def parse():
     return ap.parse_args()
 
 
+KERNEL_SOURCES = ("gram_kernels.cuh", "phases.cuh", "tmem_park.cuh", "gram_tiles.inc")
+
+
+def kernel_source_stamp():
+    """sha256 of the fused kernel's sources as they are in this tree (.git does not travel to the GPU box)."""
+    import hashlib
+    h = {}
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "system_identification_b200", "csrc", f), "rb") as fh:
+            h[f] = hashlib.sha256(fh.read()).hexdigest()[:16]
+    return h
+
+
 def ncu_traffic(n_loc):
-    """DRAM bytes of one fused-kernel launch from the committed ncu capture (scaled linearly when a rank's launch covers
-    fewer samples than the captured one); None when the capture is missing."""
+    """DRAM bytes of one fused-kernel launch from the committed ncu capture (profiles/gram_fused_traffic.json, written by
+    tools/update_traffic.py from an `ncu --set full` report).  Returned only when the capture was taken from the kernel
+    sources that are being benchmarked (content stamp) and, at N = 1, from a launch of the same size; otherwise None plus the
+    reason -- a stale constant is not a measurement."""
     try:
         with open(os.path.join(ROOT, "profiles", "gram_fused_traffic.json")) as f:
             t = json.load(f)
-        return (t["dram_bytes_read"] + t["dram_bytes_write"]) * n_loc / t["samples_per_launch"]
     except Exception:
-        return None
+        return None, "no capture under profiles/"
+    if t.get("source_stamp") != kernel_source_stamp():
+        return None, "the committed capture predates the current kernel sources (stamp mismatch): re-capture with tools/update_traffic.py"
+    per_launch = t["dram_bytes_read"] + t["dram_bytes_write"]
+    if n_loc != t["samples_per_launch"]:
+        return per_launch * n_loc / t["samples_per_launch"], f"scaled linearly from a {t['samples_per_launch']}-sample capture ({t.get('git_sha', '?')})"
+    return per_launch, f"ncu --set full capture of the same launch ({t.get('git_sha', '?')})"
 
 
 def load_flat():
@@ -91,32 +112,70 @@ def cpu_port_throughput(flat, data, n_samples, threads=0, repeats=1):
     return n_samples / best, used, best
 
 
+def oracle_sdp_seconds(flat, stats, c=154):
+    """B3: the oracle's stage-3 solve (semismooth-Newton ALM in numpy, oracle/sdp.py) of the given statistics, one core."""
+    import numpy as np
+    from oracle import sdp as osdp
+    G = stats[:c * c].reshape(c, c); r = stats[c * c:c * c + c]; s_, n_ = float(stats[c * c + c]), float(stats[c * c + c + 1])
+    t0 = time.perf_counter()
+    prob = osdp.build_problem(G, r, s_, n_, flat.nbodies, flat.phi_prior, flat.robot_mass, flat.ellipsoids, flat.joints_dof)
+    x, info = osdp.solve_alm(prob)
+    return time.perf_counter() - t0, x
+
+
+def reference_shaped_seconds_per_sample(flat, data, n=1500):
+    """B1: the path the way the reference executes it -- a Python loop over samples, numpy pinv, per-sample blocks stacked,
+    one core (oracle/dynamics.py::stacked_system restates demo/solo_identification.py:36-55,79-84) -- on a bounded sample."""
+    from oracle import dynamics as dy
+    from oracle import urdf_tree as ut
+    t = ut.tree_from_flat(flat)
+    sub = tuple(a[:, :n] for a in data)
+    t0 = time.perf_counter()
+    A, b = dy.stacked_system(t, *sub, flat.ee_names)
+    G = A.T @ A
+    return (time.perf_counter() - t0) / n, n
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import numpy as np
     flat = load_flat()
-    n = min(CPU_SAMPLE, N_SAMPLES)
+    n = N_SAMPLES if REF_FULL else min(CPU_SAMPLE, N_SAMPLES)
     data = host_log(flat, n)
     for _ in range(max(args.warmup, 0)):
         cpu_port_throughput(flat, data, min(n, 20000))
-    times = []
+    from oracle import urdf_tree as ut
+    from oracle.cbuild import COracle
+    co = COracle(ut.tree_from_flat(flat), flat.ee_names)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    times, solve_times = [], []
     used = 1
     for _ in range(max(args.steps, 1)):
-        thr, used, dt = cpu_port_throughput(flat, data, n)
-        times.append(dt)
+        t0 = time.perf_counter()
+        stats, used = co.gram(*data, nthreads=threads)
+        times.append(time.perf_counter() - t0)
+        st, _ = oracle_sdp_seconds(flat, stats)              # B3: the stage-3 solve belongs to the end-to-end figure
+        solve_times.append(st)
     T = sum(times)
     value = n * len(times) / T
-    sample = f"first {n} samples of the {N_SAMPLES}-sample G1-12dof log per step (regressor+projector+Gram, OpenMP)"
+    e2e_value = n * len(times) / (T + sum(solve_times))
+    b1_s, b1_n = reference_shaped_seconds_per_sample(flat, data)
+    sample = (f"the whole {n}-sample G1-12dof log per step" if n == N_SAMPLES else f"first {n} samples of the {N_SAMPLES}-sample G1-12dof log per step") + \
+             " (regressor+projector+Gram: oracle/sysid_oracle.c, OpenMP; stage 3: oracle/sdp.py solve_alm, numpy)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "samples_per_step": n,
-                   "note": "the CPU arm times a bounded sample of the same log per step (samples/s is size-independent: the work is linear in N)"},
+        "config": {"workload": WORKLOAD, "samples_per_step": n},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample,
+                         "b1_reference_shaped": {"value": 1.0 / b1_s, "unit": UNIT, "cores": 1, "sample": f"first {b1_n} samples; per-sample Python loop, numpy pinv, stacked A (oracle/dynamics.py::stacked_system)"},
+                         "b3_sdp_solve_seconds": sum(solve_times) / len(solve_times),
                          "note": "pinocchio/cvxpy/MOSEK are not installable in this image; oracle/sysid_oracle.c restates the reference's per-sample arithmetic"},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "identify_seconds": (T + sum(solve_times)) / len(times),
+                "note": "statistics (C/OpenMP, all cores) + LMI solve (numpy oracle, one core) per step: the same work as the GPU arm's identify()"},
         "gpu_launches": 0,
     }
     emit(line)
@@ -178,7 +237,6 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     flat = load_flat()
     si = SystemIdentification.from_flat_model(flat)
@@ -212,7 +270,9 @@ def run_ours(args):
     # fp64 roofline denominator, measured live (cuBLAS DGEMM through torch), rank 0's GPU
     peak_tflops, peak_how = measure_fp64_peak(torch)
 
-    for _ in range(max(args.warmup, 3)):
+    if args.warmup < 3:
+        print(f"bench.py: --warmup {args.warmup} is below the contract's minimum of 3; running exactly {args.warmup} as asked", file=sys.stderr)
+    for _ in range(args.warmup):
         step()
     barrier()
     sampler = ClockSampler(local)
@@ -263,22 +323,39 @@ def run_ours(args):
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms = float(te[0])
     clocks = sampler.stop() if rank == 0 else None
+    stats_e2e = dm.gram_accumulate(*dev) if world == 1 else None     # the statistics the e2e solve saw (B3 solves the same problem on the CPU)
 
     if rank == 0:
         value = N_SAMPLES * args.steps / (t_ms * 1e-3)
         kernel_s = (k_ms / args.steps) * 1e-3
         achieved = FLOP_PER_SAMPLE * n_loc / kernel_s * 1e-12
         info = last[3] or {}
-        cpu_thr, cpu_cores, cpu_dt = cpu_port_throughput(flat, (q, dq, ddq, tau, cnt), min(CPU_SAMPLE, N_SAMPLES)) if world == 1 else (None, None, None)
+        cpu = None
+        if world == 1:
+            # cpu_baseline leg (rank 0, N = 1 only): B2 = the oracle's C/OpenMP twin on a bounded sample of the same log, B1 = the
+            # reference-shaped numpy loop on one core, B3 = the oracle's stage-3 solve of THIS log's statistics
+            ncpu = min(CPU_SAMPLE, N_SAMPLES)
+            cpu_thr, cpu_cores, cpu_dt = cpu_port_throughput(flat, (q, dq, ddq, tau, cnt), ncpu)
+            b1_s, b1_n = reference_shaped_seconds_per_sample(flat, (q, dq, ddq, tau, cnt))
+            b3_s, x_cpu = oracle_sdp_seconds(flat, stats_e2e.cpu().numpy())
+            x_gpu = __import__("numpy").concatenate([last[0], last[1], last[2]])
+            cpu = {"value": cpu_thr, "unit": UNIT, "cores": cpu_cores, "kind": "port",
+                   "sample": f"first {ncpu} samples of the same log, oracle/sysid_oracle.c with OpenMP ({cpu_dt:.1f} s)",
+                   "b1_reference_shaped": {"value": 1.0 / b1_s, "unit": UNIT, "cores": 1,
+                                           "sample": f"first {b1_n} samples; per-sample Python loop, numpy pinv, stacked A (oracle/dynamics.py::stacked_system)"},
+                   "b3_sdp_solve_seconds": b3_s,
+                   "b3_phi_rel_diff_vs_gpu": float(__import__("numpy").linalg.norm(x_gpu - x_cpu) / __import__("numpy").linalg.norm(x_cpu))}
+        traffic, traffic_how = ncu_traffic(n_loc)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD,
                        "samples_per_rank": n_loc, "sharding": f"contiguous time shards over {world} rank(s), one NCCL all-reduce of {c * c + c + 2} fp64",
                        "l2": "256 MiB buffer rewritten between timed iterations (inputs per rank: %.0f MB)" % (BYTES_PER_SAMPLE * n_loc / 1e6)},
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": ncu_traffic(n_loc), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/gram_fused_traffic.json)",
+                         "traffic": traffic, "traffic_source": traffic_how,
+                         "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum, profiles/gram_fused_traffic.json)",
                          "algorithmic_bytes": BYTES_PER_SAMPLE * n_loc, "peak_source": peak_how,
                          "note": "fp64 DMMA contraction; achieved = 435204 algorithmic FLOP/sample x samples per launch / CUDA-event time of the fused kernel (+ its 10-us reduction kernel)",
                          "hbm_stream_gbs": BYTES_PER_SAMPLE * n_loc / kernel_s * 1e-9},
@@ -288,9 +365,8 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "clocks": clocks,
         }
-        if cpu_thr is not None:
-            line["cpu_baseline"] = {"value": cpu_thr, "unit": UNIT, "cores": cpu_cores, "kind": "port",
-                                    "sample": f"first {min(CPU_SAMPLE, N_SAMPLES)} samples of the same log, oracle/sysid_oracle.c with OpenMP ({cpu_dt:.1f} s)"}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         emit(line)
     if world > 1:
         dist.barrier()

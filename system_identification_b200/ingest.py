@@ -53,7 +53,7 @@ def _as_dev2d(x, device=None):
     return t if t.stride(1) == 1 else t.contiguous()
 
 
-def _patch_unconverted(out, raw, delim, rows, cols, transposed, f32, empty_nan, where=""):
+def _patch_unconverted(out, raw, delim, rows, cols, transposed, f32, empty_nan, where="", names=None):
     """The device converts a field only when it can do so EXACTLY (Clinger's fast path and a 128-bit integer division:
     every '%.6f' / '%.17g' / '%.18e' field of ordinary magnitude).  Fields outside that domain -- e.g. floating-point
     residue such as -2.7755575615628914e-17 in a logger CSV -- are flagged by the kernel (written as NaN and counted) and
@@ -74,7 +74,8 @@ def _patch_unconverted(out, raw, delim, rows, cols, transposed, f32, empty_nan, 
         try:
             vals[n_] = float(tok)
         except ValueError:
-            raise ValueError(f"could not convert string {tok!r} to float at row {row}, column {col}{where}") from None
+            cname = f" (column {names[col]!r})" if names is not None else ""
+            raise ValueError(f"could not convert string {tok!r} to float at row {row}, column {col}{cname}{where}") from None
     if f32:
         vals = vals.astype(np.float32).astype(np.float64)
     if len(cand):
@@ -171,7 +172,7 @@ def load_csv(source, device=None):
     info = (C.c_int64 * 4)()
     rc = lib.sysid_dat_parse_ex(_ptr(text), n, ord(","), _ptr(ws), ws.numel(), rows, cols, _ptr(out), rows, 2 | 4, info, _stream())
     if rc == -1 and info[0] > 0 and info[2] == 0:
-        _patch_unconverted(out, body[:n], ord(","), rows, cols, True, False, True)
+        _patch_unconverted(out, body[:n], ord(","), rows, cols, True, False, True, names=names)
         return {name: out[i] for i, name in enumerate(names)}
     if rc == -1:
         raise ValueError(lib.sysid_last_error().decode())
