@@ -113,13 +113,14 @@ def cpu_port_throughput(flat, data, n_samples, threads=0, repeats=1):
 
 
 def oracle_sdp_seconds(flat, stats, c=154):
-    """B3: the oracle's stage-3 solve (semismooth-Newton ALM in numpy, oracle/sdp.py) of the given statistics, one core."""
+    """B3: the oracle's stage-3 solve of the given statistics (log-barrier Newton in numpy, oracle/sdp.py::solve_barrier:
+    the oracle's STATED CPU reference solve and the faster of its two methods), one core."""
     import numpy as np
     from oracle import sdp as osdp
     G = stats[:c * c].reshape(c, c); r = stats[c * c:c * c + c]; s_, n_ = float(stats[c * c + c]), float(stats[c * c + c + 1])
     t0 = time.perf_counter()
     prob = osdp.build_problem(G, r, s_, n_, flat.nbodies, flat.phi_prior, flat.robot_mass, flat.ellipsoids, flat.joints_dof)
-    x, info = osdp.solve_alm(prob)
+    x, info = osdp.solve_barrier(prob)
     return time.perf_counter() - t0, x
 
 
@@ -163,7 +164,7 @@ def run_reference(args):
     e2e_value = n * len(times) / (T + sum(solve_times))
     b1_s, b1_n = reference_shaped_seconds_per_sample(flat, data)
     sample = (f"the whole {n}-sample G1-12dof log per step" if n == N_SAMPLES else f"first {n} samples of the {N_SAMPLES}-sample G1-12dof log per step") + \
-             " (regressor+projector+Gram: oracle/sysid_oracle.c, OpenMP; stage 3: oracle/sdp.py solve_alm, numpy)"
+             " (regressor+projector+Gram: oracle/sysid_oracle.c, OpenMP; stage 3: oracle/sdp.py solve_barrier, numpy)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
         "warmup": args.warmup, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "strong",
