@@ -39,15 +39,21 @@ constexpr int GRAM_WARPS = GRAM_THREADS / 32;
 #define SYSID_FSB 24
 #endif
 constexpr int MMA_UNROLL = SYSID_MMA_UNROLL;
-constexpr int FTS = SYSID_FTS;                 // samples per tile round
+constexpr int FTS = SYSID_FTS;                 // samples per tile round (at most: a round also stops at FROWS rows)
 constexpr int FSB = SYSID_FSB;                 // samples per super-batch (F phases)
-constexpr int FROWS = FTS * MAXV;
+#ifndef SYSID_FILL_DMMA
+constexpr int FROWS = FTS * MAXV;              // default: the scalar fill (phase_fill_q), every round takes FTS samples
+constexpr int FUSED_W = 0;
+#else
+constexpr int FROWS = 64;                      // rows of the tile: four stance samples (<= 15 rows each) or three in flight (18)
+constexpr int FUSED_W = FTS * MAXB * 44 + MAXV * MAXV;   // base-frame wrench matrices of the round's samples + an identity (proj_phase.cuh)
+#endif
 constexpr int FTILE = FROWS * TILE_LD;
-static_assert(FROWS % 4 == 0 && FSB % FTS == 0, "k-steps of 4 rows");
+static_assert(FROWS % 4 == 0 && FSB % FTS == 0 && FROWS >= MAXV, "k-steps of 4 rows; a round holds at least one sample");
 // the F-phase scratch aliases the tile (never live together)
 constexpr int FUSED_FSCR = FSB * (SC_STRIDE + IN_CHANNELS);     // scratch, then the staged inputs
 constexpr int FUSED_FRONT = (FTILE > FUSED_FSCR) ? FTILE : FUSED_FSCR;
-constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * (FUSED_FRONT + FSB * CX_STRIDE);
+constexpr size_t GRAM_SMEM_BYTES = sizeof(double) * (FUSED_FRONT + FUSED_W + FSB * CX_STRIDE);
 static_assert(GRAM_SMEM_BYTES + 1024 <= 232448, "shared memory budget");
 
 // stacked-matrix / rmse kernels: 72-row tile
@@ -60,6 +66,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
+
+}  // namespace sysid
+#include "proj_phase.cuh"
+namespace sysid {
+static_assert(WB == 44, "FUSED_W");
 
 // rank-(4*ksteps) update of this warp's tiles from `tile` (rows x TILE_LD doubles in shared memory)
 template <int NW, int W, int MAXNT>
@@ -172,6 +183,11 @@ struct GramArgs {
 #define F_TICK(k)
 #endif
 
+// Tile fill policy: default = the scalar fill (phase_fill_q).  -DSYSID_FILL_DMMA builds the tensor-pipe fill of
+// proj_phase.cuh (wbuild + proj): parity-green and a third of the scalar warp instructions per row, but measured SLOWER inside
+// this phased kernel (47.7 vs 52.7 Msamples/s on 262 144 G1 samples, profiles/gram_fused_r02_dmma_fill.txt): every phase between
+// two CTA barriers is latency-bound at 16 warps per SM, and the M phase already runs at 98 % of the DMMA pipe, so trading scalar
+// work for DMMA work only pays once the fill OVERLAPS the contraction.
 // Accumulator parking policy: default = the accumulators live in tensor memory and visit registers only for the M phases
 // (every other phase gets the whole register file: zero spills).  -DSYSID_PARK_F_ONLY: parked only across the F phases;
 // -DSYSID_PARK_L2: the pre-TMEM path through the partial-Gram slot in L2.  Measured on the 1M-sample G1 log:
@@ -186,12 +202,17 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     double* tile = smem;
     double* scr = smem;                        // aliases the tile: only live during the F phases
     double* inp = smem + FSB * SC_STRIDE;
-    double* ctx = smem + FUSED_FRONT;
+    double* Wsm = smem + FUSED_FRONT;          // wrench matrices of the current round (empty in the scalar-fill build)
+    double* ctx = smem + FUSED_FRONT + FUSED_W;
     __shared__ double s_stat[3];               // sum of weights, rank-loss count, skipped count
     __shared__ int s_bad[FSB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
     if (tid < 3) s_stat[tid] = 0.0;
     if (tid < FSB) s_bad[tid] = 0;
+#ifdef SYSID_FILL_DMMA
+    double* ident18 = Wsm + FTS * MAXB * 44;   // basis of a sample in flight (Q = I is not stored per sample)
+    for (int e = tid; e < MAXV * MAXV; e += GRAM_THREADS) ident18[e] = (e / MAXV == e % MAXV) ? 1.0 : 0.0;
+#endif
 #ifndef SYSID_PARK_L2
     __shared__ uint32_t s_tmem;
     if (warp == 0) tmem_alloc(&s_tmem, TMEM_PARK_COLS);
@@ -246,6 +267,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         if (t < FSB) s_bad[t] = 0;
         PHASE_TICK(clkF)
         prefetch_inputs<FSB, GRAM_THREADS>(M, args.io, (sb + gridDim.x) * FSB, args.N, t);     // lands in L2 during the rounds below
+#ifndef SYSID_FILL_DMMA
         const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
         for (int sub = 0; sub < nsub; ++sub) {
             const int ksteps = phase_fill_q<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
@@ -261,6 +283,48 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
             __syncthreads();
             PHASE_TICK(clkM)
         }
+#else
+        const int nsamp = (int)min((long long)FSB, args.N - base);
+        for (int s0 = 0; s0 < nsamp;) {
+            // the round: up to FTS samples, as long as their rows (18 - rank J_c each, 0 for a skipped sample) fit the tile
+            int off[FTS + 1], cnt = 0;
+            off[0] = 0;
+#pragma unroll
+            for (int u = 0; u < FTS; ++u) {
+                int nq = 0;
+                bool fits = false;
+                if (cnt == u && s0 + u < FSB) {
+                    const double* cu = ctx + (s0 + u) * CX_STRIDE;
+                    nq = (cu[CX_W] == 0.0) ? 0 : (int)cu[CX_NQ];
+                    fits = off[u] + nq <= FROWS;
+                }
+                if (fits) { off[u + 1] = off[u] + nq; cnt = u + 1; } else off[u + 1] = off[u];
+            }
+            const int rows = off[FTS], ksteps = (rows + 3) >> 2;
+#ifdef SYSID_PHASE_CLOCKS
+            clkSub[4] += 1000000LL + ksteps;         // diagnostic: rounds (x 1e6) and k-steps of this CTA
+#endif
+            for (int e = t; e < (4 * ksteps - rows) * CW; e += GRAM_THREADS) tile[(rows + e / CW) * TILE_LD + (e % CW)] = 0.0;   // pad rows of the last k-step
+            phase_wbuild<FTS>(M, ctx, Wsm, s0, cnt, warp, lane);
+            __syncthreads();
+            PHASE_TICK(clkSub[5])
+            phase_proj_mma<FTS, TILE_LD>(M, ctx, Wsm, ident18, tile, s0, cnt, off, args.friction, warp, lane);
+            __syncthreads();
+            PHASE_TICK(clkC)
+            if (ksteps > 0) {
+#if defined(SYSID_PARK_FILL)
+                tmem_unpark<GRAM_MAXNT>(tpark, acc);
+#endif
+                mma_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, tile, ksteps, lane, acc);
+#if defined(SYSID_PARK_FILL)
+                tmem_park<GRAM_MAXNT>(tpark, acc);
+#endif
+            }
+            __syncthreads();
+            PHASE_TICK(clkM)
+            s0 += cnt;
+        }
+#endif
     }
 #if defined(SYSID_PARK_FILL)
     if ((long long)blockIdx.x < nsb) tmem_unpark<GRAM_MAXNT>(tpark, acc);

@@ -11,6 +11,8 @@ constexpr int MAXD = 12;     // actuated joints
 constexpr int MAXEE = 4;     // contact frames
 constexpr int MAXCH = 6;     // longest foot chain (joints between the foot and the root, root excluded)
 constexpr int CW = 160;      // padded width of one stacked row: 10*nb + 2*d + 1 (tau column) <= 155 -> 160
+constexpr int PROJ_PARTS = 4;      // the projection phase of the fused kernel deals every sample's bodies to this many warps
+constexpr int PROJ_MAXITEMS = 12;  // chain-walk steps of one part (prefix joints it only accumulates + joints whose body it emits)
 
 enum { JT_FF = 0, JT_RX = 1, JT_RY = 2, JT_RZ = 3, JT_RU = 4 };
 
@@ -40,6 +42,14 @@ struct DevModel {
     int32_t fch[MAXD][MAXCH];
     int32_t fill_split;              // bodies of a chain are dealt round-robin to this many lane groups of the tile fill
     uint32_t submask[MAXJ];          // bit i set: body (joint) i lies in the subtree of joint j, j itself included (evaluation pass)
+    // projection phase (phase_proj_mma): part p walks the joints proj_item[p][0 .. proj_n[p]); flag bit 0 = emit the body's ten columns,
+    // bit 1 = first joint of a walk (restart from the base rows); proj_root[p]: the part emits the root body; proj_tail[p]:
+    // mask of the friction / torque / padding 8-column groups (from column nparams on) the part emits
+    int8_t proj_n[PROJ_PARTS];
+    uint32_t proj_item[PROJ_PARTS][PROJ_MAXITEMS];  // joint | flags << 8 (flag bit 0: emit, bit 1: restart)
+    uint8_t proj_root[PROJ_PARTS];
+    uint32_t proj_tail[PROJ_PARTS];
+    uint8_t proj_tailks[2][32];      // [friction][column group]: which 4-joint k-steps of the group are structurally non-zero
 };
 
 }  // namespace sysid

@@ -171,6 +171,56 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
     M.fill_split = ((M.nfch * 2 + 1) * 96 <= GRAM_THREADS) ? 2 : 1;
     for (int i = 1; i < d->njoints; ++i)
         for (int k = i; k >= 1; k = M.parent[k]) M.submask[k] |= 1u << i;       // i is in the subtree of each of its ancestors
+    // projection phase: the bodies [root, owned joints of chain 0, of chain 1, ...] are cut into PROJ_PARTS contiguous runs of
+    // (almost) equal length; a run that starts inside a chain first walks the chain's earlier joints without emitting them
+    {
+        int seq_joint[MAXB], seq_chain[MAXB], seq_pos[MAXB], nseq = 0;
+        seq_joint[nseq] = 1; seq_chain[nseq] = -1; seq_pos[nseq] = 0; ++nseq;      // the root body
+        for (int c = 0; c < M.nfch; ++c)
+            for (int e = M.fch_own[c]; e < M.fch_len[c]; ++e) { seq_joint[nseq] = M.fch[c][e]; seq_chain[nseq] = c; seq_pos[nseq] = e; ++nseq; }
+        int cost[PROJ_PARTS] = {0, 0, 0, 0};
+        int lo = 0;
+        for (int p = 0; p < PROJ_PARTS; ++p) {
+            const int hi = lo + nseq / PROJ_PARTS + (p < nseq % PROJ_PARTS ? 1 : 0);
+            int n = 0, cur_chain = -2;
+            bool ok = true;
+            for (int u = lo; u < hi && ok; ++u) {
+                if (seq_chain[u] < 0) { M.proj_root[p] = 1; cost[p] += 4; continue; }
+                const int c = seq_chain[u];
+                if (c != cur_chain) {                     // a new walk: the chain's joints before this one are accumulated only
+                    for (int e = 0; e < seq_pos[u] && ok; ++e) {
+                        if (n >= PROJ_MAXITEMS) { ok = false; break; }
+                        M.proj_item[p][n] = (uint32_t)M.fch[c][e] | ((e == 0 ? 2u : 0u) << 8); ++n; cost[p] += 1;
+                    }
+                    cur_chain = c;
+                }
+                if (n >= PROJ_MAXITEMS) { ok = false; break; }
+                M.proj_item[p][n] = (uint32_t)seq_joint[u] | ((1u | (seq_pos[u] == 0 ? 2u : 0u)) << 8); ++n; cost[p] += 4;
+            }
+            if (!ok) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "projection plan: more than %d chain steps in one part", PROJ_MAXITEMS); }
+            M.proj_n[p] = (int8_t)n;
+            lo = hi;
+        }
+        // friction / torque / zero-padding column groups from column nparams to CW: each to the currently cheapest part
+        const int ntail = (CW - M.nparams + 7) / 8;
+        if (ntail > 32) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "projection plan: %d tail column groups", ntail); }
+        for (int nt = 0; nt < ntail; ++nt) {
+            int best = 0;
+            for (int p = 1; p < PROJ_PARTS; ++p) if (cost[p] < cost[best]) best = p;
+            M.proj_tail[best] |= 1u << nt; cost[best] += 3;
+            // block (joints 4 ks .., columns 8 nt ..) of [diag(dq) | diag(sign dq) | tau] is non-zero where a diagonal or the
+            // torque column crosses it
+            for (int fr = 0; fr < 2; ++fr) {
+                const int nd = M.nd, tcol = fr ? 2 * nd : 0, c0 = 8 * nt;
+                for (int ks = 0; ks < 3 && 4 * ks < nd; ++ks) {
+                    const int j0 = 4 * ks;
+                    bool need = (tcol >= c0 && tcol < c0 + 8);
+                    if (fr) need = need || (c0 < j0 + 4 && j0 < c0 + 8) || (c0 < nd + j0 + 4 && nd + j0 < c0 + 8);
+                    if (need) M.proj_tailks[fr][nt] |= (uint8_t)(1u << ks);
+                }
+            }
+        }
+    }
     int rc = device_sm_count(&m->sm_count);
     if (rc != SYSID_OK) { delete m; return rc; }
     *out = m;
