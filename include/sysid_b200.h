@@ -20,6 +20,9 @@
  *                             Y_proj/B_v/B_c through the per-sample API and hand them to Solver(...)  src/solver.py:6-29
  *   sysid_sdp_solve           Solver.solve_fully_consistent: cvxpy problem + problem.solve(solver=cp.MOSEK)
  *                             reference src/solver.py:123-210
+ *   sysid_sdp_plan_create / sysid_sdp_solve_plan   the same, split into the once-per-prior host part (Solver.__init__ and the
+ *                             problem build, src/solver.py:6-29,55-121) and a launch without host work; optional warm start
+ *   sysid_gram_accumulate_host_presolve   streaming statistics with the LMI fit of the first chunk solved behind the stream
  *   sysid_filtfilt / sysid_savgol  the scipy.signal.filtfilt / savgol_filter calls of read_data
  *                             reference demo/solo_identification.py:15-32 (the step immediately before the path)
  *   sysid_predict_rmse        SystemIdentification.print_tau_prediction_rmse   reference src/sys_identification.py:421-437
@@ -259,6 +262,43 @@ size_t sysid_sdp_workspace_bytes(int32_t num_links, int32_t ndof);
  * stats + k * stats_stride (same priors/ellipsoids), one thread block each. */
 int sysid_sdp_solve(const sysid_sdp_desc* desc, const double* stats, int64_t stats_stride, int32_t batch,
                     double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The same solve split in two, for callers that solve more than once with the same prior / ellipsoids / lambda (a streaming
+ * identify(), bootstrap batches): sysid_sdp_plan_create does the host work of Solver.__init__ + the problem build (reference
+ * src/solver.py:6-29,55-121: pull-back metrics, svec maps, float32 Q) once and uploads it (synchronises `stream`);
+ * sysid_sdp_solve_plan then launches with NO host work and NO synchronisation.  `desc` supplies only the scalars there
+ * (num_links, ndof, total_mass, epsilon, tol, max_iters).  workspace: sysid_sdp_solve_workspace_bytes(L, nd, batch).
+ * Warm start: warm_out (nullable, device, batch * sysid_sdp_warm_len doubles) receives [x | multipliers | sigma | valid] in
+ * unscaled units; warm_in (nullable) starts the iteration from such a record of a NEARBY problem -- the optimum is unique, so
+ * the start changes the number of Newton steps, not the answer.  A record that is not finite or not valid is ignored. */
+size_t sysid_sdp_plan_bytes(int32_t num_links);
+int sysid_sdp_plan_create(const sysid_sdp_desc* desc, void* plan, size_t plan_bytes, void* stream);
+size_t sysid_sdp_solve_workspace_bytes(int32_t num_links, int32_t ndof, int32_t batch);
+size_t sysid_sdp_warm_len(int32_t num_links, int32_t ndof);
+int sysid_sdp_solve_plan(const sysid_sdp_desc* desc, const void* plan, const double* stats, int64_t stats_stride, int32_t batch,
+                         double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes,
+                         const double* warm_in, double* warm_out, void* stream);
+
+/* sysid_gram_accumulate_host_ex with an LMI PRE-SOLVE hidden behind the stream (pre nullable = plain streaming).  The statistics
+ * are additive, so the fit of the first `samples` samples of the log is a point and a set of multipliers within the statistical
+ * noise of the final fit: it is solved as ONE thread block on an internal stream while the remaining chunks are uploaded and
+ * contracted (they leave it one SM), and its record (warm_out) warm-starts the final sysid_sdp_solve_plan, which then needs a
+ * handful of Newton steps instead of ~55.  On return, work submitted to `stream` is ordered after the pre-solve.  Skipped (record
+ * left invalid) when the log is shorter than 2 * samples.  All pointers in the struct are DEVICE pointers except desc. */
+typedef struct sysid_presolve {
+    const sysid_sdp_desc* desc;       /* host; scalars only */
+    const void* plan;                 /* sysid_sdp_plan_create */
+    void* sdp_workspace; size_t sdp_workspace_bytes;   /* sysid_sdp_solve_workspace_bytes(L, nd, 1) */
+    double* stats_snapshot;           /* stats_len doubles */
+    double* x_scratch;                /* c doubles */
+    sysid_sdp_info* info_scratch;     /* one record */
+    double* warm_out;                 /* sysid_sdp_warm_len doubles */
+    int64_t samples;                  /* length of the first chunk (0 = `chunk`) */
+} sysid_presolve;
+int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* const* arrays_host, const int32_t* dtypes,
+                                        const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,
+                                        double* stats, int64_t* info, void* workspace, size_t workspace_bytes, int64_t chunk,
+                                        const sysid_presolve* pre, void* stream);
 
 /* tau-prediction error of phi (nparams, multiplies the pinocchio-ordered regressor as is -- reference quirk Q1):
  * out (device): [0] = mean_i ||e_i||^2 (the reference's "total", no root), [1..ndof] = per-joint RMSE,

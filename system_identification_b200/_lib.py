@@ -48,6 +48,12 @@ class SdpInfo(C.Structure):
                 ("min_eig_J", C.c_double), ("min_eig_C", C.c_double), ("mass_residual", C.c_double)]
 
 
+class Presolve(C.Structure):
+    _fields_ = [("desc", C.POINTER(SdpDesc)), ("plan", C.c_void_p), ("sdp_workspace", C.c_void_p), ("sdp_workspace_bytes", C.c_size_t),
+                ("stats_snapshot", C.c_void_p), ("x_scratch", C.c_void_p), ("info_scratch", C.c_void_p), ("warm_out", C.c_void_p),
+                ("samples", C.c_int64)]
+
+
 SDP_INFO_DTYPE = np.dtype([("status", "<i4"), ("iterations", "<i4"), ("refactorizations", "<i4"), ("reserved", "<i4"),
                            ("primal_residual", "<f8"), ("dual_residual", "<f8"), ("rho", "<f8"), ("objective", "<f8"),
                            ("min_eig_J", "<f8"), ("min_eig_C", "<f8"), ("mass_residual", "<f8")])
@@ -69,6 +75,7 @@ _SIGNATURES = {
     "sysid_gram_host_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
     "sysid_gram_accumulate_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
     "sysid_gram_accumulate_host_ex": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
+    "sysid_gram_accumulate_host_presolve": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, C.POINTER(Presolve), _P]),
     "sysid_gram_from_stack": (C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P, C.c_size_t, _P]),
     "sysid_gram_from_stack_workspace_bytes": (C.c_size_t, [C.c_int32]),
     "sysid_filtfilt_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int64, C.c_int32]),
@@ -87,6 +94,11 @@ _SIGNATURES = {
     "sysid_physical_consistency": (C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "sysid_sdp_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "sysid_sdp_solve": (C.c_int, [C.POINTER(SdpDesc), _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "sysid_sdp_plan_bytes": (C.c_size_t, [C.c_int32]),
+    "sysid_sdp_plan_create": (C.c_int, [C.POINTER(SdpDesc), _P, C.c_size_t, _P]),
+    "sysid_sdp_solve_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "sysid_sdp_warm_len": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "sysid_sdp_solve_plan": (C.c_int, [C.POINTER(SdpDesc), _P, _P, C.c_int64, C.c_int32, _P, _P, _P, C.c_size_t, _P, _P, _P]),
     "sysid_predict_rmse": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, _P, _P, C.c_size_t, _P]),
     "sysid_predict_rmse_workspace_bytes": (C.c_size_t, [_P]),
 }

@@ -42,15 +42,21 @@ struct SdpParams {
     size_t ws_stride;          // doubles of workspace per problem
 };
 
-// workspace per problem (doubles): Hs (c*c) | Amat (L*22*10) | T (L*100) | tfric (2nd)
+// workspace per problem (doubles): Hs (c*c) | Amat (L*22*10) | T (L*100) | tfric (2nd) | pad (16) | row scales (m)
+// warm-start record of one problem (doubles): x (c, unscaled variables) | multipliers (m, unscaled constraint units) | sigma | valid |
+// kernel start | kernel end (%globaltimer, ns: lets the host see when a pre-solve hidden behind a stream actually ran)
+__host__ __device__ inline size_t sdp_warm_doubles(int L, int nd) {
+    return (10 * (size_t)L + 2 * (size_t)nd) + ((size_t)L * SDP_ROWS_PER_LINK + 2 * (size_t)nd) + 4;   // + kernel start / end (globaltimer ns)
+}
 __host__ __device__ inline size_t sdp_ws_doubles(int L, int nd) {
     const size_t c = 10 * (size_t)L + 2 * (size_t)nd;
-    return c * c + (size_t)L * SDP_ROWS_PER_LINK * 10 + (size_t)L * 100 + 2 * (size_t)nd + 16;
+    return c * c + (size_t)L * SDP_ROWS_PER_LINK * 10 + (size_t)L * 100 + 2 * (size_t)nd + 16 +
+           ((size_t)L * SDP_ROWS_PER_LINK + 2 * (size_t)nd);                               // + the row scales (warm start)
 }
 inline size_t sdp_plan_doubles(int L) { return (size_t)L * SDP_PLAN_LINK; }
 inline size_t sdp_workspace_bytes(int L, int nd) {
-    // plan + one problem; the launcher checks batch * per-problem against the size it is given
-    return sizeof(double) * (sdp_plan_doubles(L) + sdp_ws_doubles(L, nd));
+    // plan (+ 4 trailing scalars) + one problem; the launcher checks batch * per-problem against the size it is given
+    return sizeof(double) * (sdp_plan_doubles(L) + 4 + sdp_ws_doubles(L, nd));
 }
 
 // ------------------------------------------------------------------------------------------------ host: plan
@@ -493,7 +499,8 @@ __device__ inline void chol_solve_warp(const double* A, int n, int ld, const dou
 // ------------------------------------------------------------------------------------------------ the solver
 __global__ void __launch_bounds__(SDP_THREADS, 1)
 sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const double* __restrict__ stats_all,
-                double* __restrict__ ws_all, double* __restrict__ x_out_all, sysid_sdp_info* __restrict__ info_all) {
+                double* __restrict__ ws_all, double* __restrict__ x_out_all, sysid_sdp_info* __restrict__ info_all,
+                const double* __restrict__ warm_in_all, double* __restrict__ warm_out_all) {
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int L = prm.L, nd = prm.nd, c = prm.c, m = prm.m, np = 10 * L;
@@ -504,6 +511,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* Am = Hs + (size_t)c * c;                   // L*22*10 scaled constraint blocks
     double* Tm = Am + (size_t)L * SDP_ROWS_PER_LINK * 10;   // L*100, T_i row-major (upper triangular)
     double* tf = Tm + (size_t)L * 100;                 // 2nd friction scales
+    double* rsig = tf + 2 * (size_t)nd + 16;           // m  scale of every constraint row (one per LMI block): multipliers <-> unscaled units
     // shared memory carve-up
     const int ldw = c + 1;                             // odd: conflict-free column access
     double* W = sm;                                    // c*(c+1)  Newton matrix (lower triangle), Cholesky-factored in place
@@ -531,6 +539,8 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* pan = (4 * m + 8 * L >= SDP_PAN_DOUBLES) ? gy : red + 32;
     __shared__ double s_scalar[8];
 
+    unsigned long long t_start_ = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start_));
     const double n_rows = stats[(size_t)c * c + c + 1];
     const double inv_n = 1.0 / n_rows;
 
@@ -647,9 +657,11 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             double cc = 0.0;
             if (gsel < 2 && (r == 0 || r == 2 || r == 5 || r == 9)) cc = prm.eps * sig;
             c0[i * SDP_ROWS_PER_LINK + r0 + r] = cc;
+            rsig[i * SDP_ROWS_PER_LINK + r0 + r] = sig;
         }
     }
-    for (int k = tid; k < 2 * nd; k += SDP_THREADS) c0[L * SDP_ROWS_PER_LINK + k] = 0.0;
+    // friction rows g = y_k = x_k / tf_k: scale 1 / tf_k
+    for (int k = tid; k < 2 * nd; k += SDP_THREADS) { c0[L * SDP_ROWS_PER_LINK + k] = 0.0; rsig[L * SDP_ROWS_PER_LINK + k] = 1.0 / tf[k]; }
     __syncthreads();
 
     auto apply_A = [&](const double* yy, int r) -> double {   // (A yy)[r] + c0[r]
@@ -813,6 +825,32 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     for (int a = tid; a < c; a += SDP_THREADS) y[a] = at[a] * prm.total_mass / ata;
     for (int r = tid; r < m; r += SDP_THREADS) lam[r] = 0.0;
     __syncthreads();
+    // ---- warm start: point and multipliers of an earlier solve of a NEARBY problem (the same log seen in part: the statistics
+    // are additive, so the solve of the first streamed chunk is within the statistical noise of the final one).  The record holds
+    // unscaled quantities, re-expressed here in THIS problem's scaling: y = T^-1 x (T_i upper triangular), lam~ = lam / row scale.
+    // The fixed point does not depend on the start; a record that is not finite, or flagged invalid, is ignored.
+    if (warm_in_all != nullptr) {
+        const double* win = warm_in_all + (size_t)prob * sdp_warm_doubles(L, nd);
+        double bad = (win[c + m + 1] == 1.0 && win[c + m] > 0.0) ? 0.0 : 1.0;
+        for (int a = tid; a < c + m; a += SDP_THREADS) if (!(fabs(win[a]) < 1e300)) bad = 1.0;
+        bad = block_sum(bad, red, tid);
+        if (bad == 0.0) {
+            if (tid < L) {                                   // y_i = T_i^-1 x_i by back substitution
+                const double* Ti = Tm + (size_t)tid * 100;
+                double yy[10];
+                for (int a = 9; a >= 0; --a) {
+                    double sacc = win[10 * tid + a];
+                    for (int b = a + 1; b < 10; ++b) sacc -= Ti[10 * a + b] * yy[b];
+                    yy[a] = sacc / Ti[11 * a];
+                }
+                for (int a = 0; a < 10; ++a) y[10 * tid + a] = yy[a];
+            }
+            for (int k = tid; k < 2 * nd; k += SDP_THREADS) y[np + k] = win[np + k] / tf[k];
+            for (int r = tid; r < m; r += SDP_THREADS) lam[r] = win[c + r] / rsig[r];
+            sigma = fmin(fmax(win[c + m], 1.0), 1e6);
+        }
+        __syncthreads();
+    }
     for (int a = warp; a < c; a += SDP_THREADS / 32) {       // hy = Hs y  (Hs in global memory / L2)
         double s = 0.0;
         for (int b = lane; b < c; b += 32) s += Hs[(size_t)a * c + b] * y[b];
@@ -918,7 +956,21 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         x_out[a] = s;
         rhs[a] = s;
     }
+    if (warm_out_all != nullptr) {
+        double* wout = warm_out_all + (size_t)prob * sdp_warm_doubles(L, nd);
+        for (int r = tid; r < m; r += SDP_THREADS) wout[c + r] = lam[r] * rsig[r];
+        if (tid == 0) {
+            wout[c + m] = sigma; wout[c + m + 1] = (status == SYSID_OK || status == SDP_STATUS_INACCURATE) ? 1.0 : 0.0;
+            unsigned long long t1_;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1_));
+            wout[c + m + 2] = (double)t_start_; wout[c + m + 3] = (double)t1_;
+        }
+    }
     __syncthreads();
+    if (warm_out_all != nullptr) {
+        double* wout = warm_out_all + (size_t)prob * sdp_warm_doubles(L, nd);
+        for (int a = tid; a < c; a += SDP_THREADS) wout[a] = rhs[a];
+    }
     // objective in scaled variables: 1/2 y^T Hs y - gt^T y + const
     double part = 0.0;
     for (int a = tid; a < c; a += SDP_THREADS) {
@@ -926,7 +978,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         for (int b = 0; b < c; ++b) s += Hs[(size_t)a * c + b] * y[b];
         part += y[a] * (0.5 * s - gt[a]);
     }
-    const double obj = block_sum(part, red, tid) + prm.const_reg + 0.5 * stats[(size_t)c * c + c] * inv_n;
+    const double obj = block_sum(part, red, tid) + plan[(size_t)L * SDP_PLAN_LINK] + 0.5 * stats[(size_t)c * c + c] * inv_n;
     double mpart = 0.0;
     for (int i = tid; i < L; i += SDP_THREADS) mpart += rhs[10 * i];
     const double msum = block_sum(mpart, red, tid);
@@ -958,44 +1010,80 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     }
 }
 
-inline int sdp_solve_launch(const sysid_sdp_desc& d, const double* stats, int64_t stats_stride, int32_t batch,
-                            double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes,
-                            cudaStream_t st, char* msg, size_t msglen) {
+// Device plan = the per-link plan doubles followed by [const_reg, L, lambda, reg_type] (4 doubles).
+inline size_t sdp_plan_total_doubles(int L) { return sdp_plan_doubles(L) + 4; }
+
+inline int sdp_check_desc(const sysid_sdp_desc& d, bool need_arrays, char* msg, size_t msglen) {
     if (d.num_links < 1 || d.num_links > SDP_MAXL || d.ndof < 0 || d.ndof > SDP_MAXD) {
         snprintf(msg, msglen, "num_links %d / ndof %d outside this build's envelope (%d / %d)", d.num_links, d.ndof, SDP_MAXL, SDP_MAXD);
         return SYSID_ERR_UNSUPPORTED;
     }
-    if (!d.phi_prior || !d.semi_axes || !d.centers || batch < 1) { snprintf(msg, msglen, "bad sdp descriptor"); return SYSID_ERR_INVALID; }
+    if (need_arrays && (!d.phi_prior || !d.semi_axes || !d.centers)) { snprintf(msg, msglen, "bad sdp descriptor"); return SYSID_ERR_INVALID; }
     if (d.reg_type != SYSID_REG_CONSTANT_PULLBACK && d.reg_type != SYSID_REG_EUCLIDEAN) {
         snprintf(msg, msglen, "reg_type %d not supported (the reference marks 'entropic' as non-converging)", d.reg_type);
         return SYSID_ERR_UNSUPPORTED;
     }
-    const int L = d.num_links, nd = d.ndof;
-    const size_t plan_n = sdp_plan_doubles(L), ws_n = sdp_ws_doubles(L, nd);
-    const size_t need = sizeof(double) * (plan_n + ws_n * (size_t)batch);
-    if (workspace_bytes < need) { snprintf(msg, msglen, "workspace %zu B < %zu B", workspace_bytes, need); return SYSID_ERR_WORKSPACE; }
+    return SYSID_OK;
+}
+
+// Host part (once per prior / ellipsoids / lambda): pull-back metrics, svec maps, float32 Q -> device plan.  Synchronises
+// `st` (the host vector must outlive the copy); the solve launches below do not.
+inline int sdp_plan_upload(const sysid_sdp_desc& d, double* dplan, size_t plan_bytes, cudaStream_t st, char* msg, size_t msglen) {
+    int rc = sdp_check_desc(d, true, msg, msglen);
+    if (rc != SYSID_OK) return rc;
+    const size_t n = sdp_plan_total_doubles(d.num_links);
+    if (plan_bytes < sizeof(double) * n) { snprintf(msg, msglen, "plan buffer %zu B < %zu B", plan_bytes, sizeof(double) * n); return SYSID_ERR_WORKSPACE; }
     std::vector<double> plan;
     double const_reg = 0.0;
     if (!sdp_host::build_plan(d, plan, const_reg, msg, msglen)) return SYSID_ERR_INVALID;
-    double* dplan = (double*)workspace;
-    cudaError_t e = cudaMemcpyAsync(dplan, plan.data(), sizeof(double) * plan_n, cudaMemcpyHostToDevice, st);
+    plan.push_back(const_reg); plan.push_back((double)d.num_links); plan.push_back(d.lambda_reg); plan.push_back((double)d.reg_type);
+    cudaError_t e = cudaMemcpyAsync(dplan, plan.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st);
     if (e != cudaSuccess) { snprintf(msg, msglen, "plan upload failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
-    // the plan vector dies with this frame: pageable-source async copies are staged before returning, but make it explicit
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) { snprintf(msg, msglen, "stream sync failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
+    return SYSID_OK;
+}
+
+// Launch on a device plan: no host work, no synchronisation.  d supplies the scalars only (num_links, ndof, total_mass,
+// epsilon, tol, max_iters).  workspace: batch * sdp_ws_doubles doubles.
+inline int sdp_solve_planned(const sysid_sdp_desc& d, const double* dplan, const double* stats, int64_t stats_stride, int32_t batch,
+                             double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes,
+                             const double* warm_in, double* warm_out, cudaStream_t st, char* msg, size_t msglen) {
+    int rc = sdp_check_desc(d, false, msg, msglen);
+    if (rc != SYSID_OK) return rc;
+    if (batch < 1) { snprintf(msg, msglen, "bad batch"); return SYSID_ERR_INVALID; }
+    const int L = d.num_links, nd = d.ndof;
+    const size_t ws_n = sdp_ws_doubles(L, nd);
+    const size_t need = sizeof(double) * ws_n * (size_t)batch;
+    if (workspace_bytes < need) { snprintf(msg, msglen, "workspace %zu B < %zu B", workspace_bytes, need); return SYSID_ERR_WORKSPACE; }
     SdpParams prm;
     prm.L = L; prm.nd = nd; prm.c = 10 * L + 2 * nd; prm.m = SDP_ROWS_PER_LINK * L + 2 * nd;
-    prm.total_mass = d.total_mass; prm.eps = d.epsilon; prm.const_reg = const_reg; prm.tol = d.tol > 0 ? d.tol : 1e-10;
+    prm.total_mass = d.total_mass; prm.eps = d.epsilon; prm.const_reg = 0.0; prm.tol = d.tol > 0 ? d.tol : 1e-10;
     prm.max_iters = d.max_iters > 0 ? d.max_iters : SDP_DEFAULT_MAX_ITERS;
     prm.stats_stride = stats_stride; prm.ws_stride = ws_n;
     const size_t smem = sizeof(double) * ((size_t)prm.c * (prm.c + 1) + 10 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + 32 +
                                          ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES));
-    e = cudaFuncSetAttribute(sdp_alm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sdp_alm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { snprintf(msg, msglen, "smem opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
-    sdp_alm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, dplan + plan_n, x_out, info_out);
+    sdp_alm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, (double*)workspace, x_out, info_out, warm_in, warm_out);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msglen, "sdp launch failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
     return SYSID_OK;
+}
+
+// One-shot form (plan built and uploaded into the head of the workspace on every call; synchronises the stream once).
+inline int sdp_solve_launch(const sysid_sdp_desc& d, const double* stats, int64_t stats_stride, int32_t batch,
+                            double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes,
+                            cudaStream_t st, char* msg, size_t msglen) {
+    int rc = sdp_check_desc(d, true, msg, msglen);
+    if (rc != SYSID_OK) return rc;
+    if (batch < 1) { snprintf(msg, msglen, "bad sdp descriptor"); return SYSID_ERR_INVALID; }
+    const size_t plan_n = sdp_plan_total_doubles(d.num_links);
+    if (workspace_bytes < sizeof(double) * plan_n) { snprintf(msg, msglen, "workspace %zu B too small", workspace_bytes); return SYSID_ERR_WORKSPACE; }
+    rc = sdp_plan_upload(d, (double*)workspace, sizeof(double) * plan_n, st, msg, msglen);
+    if (rc != SYSID_OK) return rc;
+    return sdp_solve_planned(d, (const double*)workspace, stats, stats_stride, batch, x_out, info_out, (double*)workspace + plan_n,
+                             workspace_bytes - sizeof(double) * plan_n, nullptr, nullptr, st, msg, msglen);
 }
 
 }  // namespace sysid

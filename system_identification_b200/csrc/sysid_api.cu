@@ -3,7 +3,9 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -16,9 +18,33 @@
 
 using namespace sysid;
 
+// Internal streams / events of the host-streaming entry, created once per model handle (creating and destroying them per call
+// costs host time in front of a 19 ms stream).  One call at a time may borrow them (try-lock); a concurrent call on the same
+// handle falls back to per-call resources.
+struct HostStreamRes {
+    cudaStream_t s_copy = nullptr, s_solve = nullptr;
+    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copied[2], consumed[2], start, snap, solved
+    bool ok = false;
+    bool create() {
+        if (cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&s_solve, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int i = 0; i < 7; ++i) if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        ok = true;
+        return true;
+    }
+    void destroy() {
+        for (int i = 0; i < 7; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+        if (s_copy) cudaStreamDestroy(s_copy);       // pending work completes first; the runtime releases the stream afterwards
+        if (s_solve) cudaStreamDestroy(s_solve);
+        *this = HostStreamRes();
+    }
+};
+
 struct sysid_model {
     DevModel dev;
     int sm_count;
+    mutable std::mutex host_mu;
+    mutable HostStreamRes host_res;
 };
 
 namespace {
@@ -227,7 +253,10 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
     return SYSID_OK;
 }
 
-void sysid_model_destroy(sysid_model* model) { delete model; }
+void sysid_model_destroy(sysid_model* model) {
+    if (model && model->host_res.ok) model->host_res.destroy();
+    delete model;
+}
 
 int sysid_model_dims(const sysid_model* model, sysid_dims* out) {
     if (!model || !out) return fail(SYSID_ERR_INVALID, "null argument");
@@ -297,10 +326,24 @@ size_t sysid_gram_from_stack_workspace_bytes(int32_t c) {
     return sizeof(double) * (size_t)sms * PARTIAL_DOUBLES;
 }
 
+static int gram_accumulate_impl(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                                const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
+                                int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
+                                int reserve_sms, void* stream);
+
 int sysid_gram_accumulate(const sysid_model* model, const double* q, const double* dq, const double* ddq,
                           const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
                           int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
                           void* stream) {
+    return gram_accumulate_impl(model, q, dq, ddq, tau, contact, N, ld, weights, friction, stats, info, workspace, workspace_bytes, 0, stream);
+}
+
+// reserve_sms: leave that many SMs free (the persistent CTAs of this kernel take a whole SM each; a concurrent single-CTA
+// LMI pre-solve on another stream needs one)
+static int gram_accumulate_impl(const sysid_model* model, const double* q, const double* dq, const double* ddq,
+                                const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
+                                int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
+                                int reserve_sms, void* stream) {
     if (!model || !q || !dq || !ddq || !tau || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
@@ -308,7 +351,10 @@ int sysid_gram_accumulate(const sysid_model* model, const double* q, const doubl
     cudaStream_t st = (cudaStream_t)stream;
     const DevModel& M = model->dev;
     const long long nsb = (N + FSB - 1) / FSB;
-    const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
+    static const int debug_reserve = [] { const char* e = std::getenv("SYSID_DEBUG_RESERVE_SMS"); return e ? std::atoi(e) : 0; }();   // diagnostic
+    if (debug_reserve > reserve_sms) reserve_sms = debug_reserve;
+    const int max_ctas = (model->sm_count - reserve_sms > 1) ? model->sm_count - reserve_sms : 1;
+    const int grid = (int)(nsb < max_ctas ? nsb : max_ctas);
     if (workspace_bytes < sizeof(double) * (size_t)grid * PARTIAL_DOUBLES)
         return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, sizeof(double) * (size_t)grid * PARTIAL_DOUBLES);
     int rc = opt_in_smem(gram_fused_kernel, GRAM_SMEM_BYTES);
@@ -350,7 +396,17 @@ int sysid_gram_accumulate_host_ex(const sysid_model* model, const void* const* a
                                   const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,
                                   double* stats, int64_t* info, void* workspace, size_t workspace_bytes, int64_t chunk,
                                   void* stream) {
+    return sysid_gram_accumulate_host_presolve(model, arrays_host, dtypes, lds_host, N, weights_host, friction, stats, info,
+                                               workspace, workspace_bytes, chunk, nullptr, stream);
+}
+
+int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* const* arrays_host, const int32_t* dtypes,
+                                        const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,
+                                        double* stats, int64_t* info, void* workspace, size_t workspace_bytes, int64_t chunk,
+                                        const sysid_presolve* pre, void* stream) {
     if (!model || !arrays_host || !dtypes || !lds_host || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (pre && (!pre->desc || !pre->plan || !pre->sdp_workspace || !pre->stats_snapshot || !pre->x_scratch || !pre->info_scratch || !pre->warm_out))
+        return fail(SYSID_ERR_INVALID, "null presolve argument");
     const DevModel& M = model->dev;
     const int channels[5] = {M.nq, M.nv, M.nv, M.nd, M.n_ee};
     for (int a = 0; a < 5; ++a) {
@@ -366,28 +422,46 @@ int sysid_gram_accumulate_host_ex(const sysid_model* model, const void* const* a
     const size_t per_sample = (size_t)M.nq + 2 * (size_t)M.nv + (size_t)M.nd + (size_t)M.n_ee + 1;
     double* stage[2] = {(double*)((char*)workspace + gram_ws), (double*)((char*)workspace + gram_ws) + per_sample * (size_t)chunk};
     float* land[2] = {(float*)(stage[1] + per_sample * (size_t)chunk), (float*)(stage[1] + per_sample * (size_t)chunk) + per_sample * (size_t)chunk};
-    cudaStream_t cp = nullptr;
-    cudaEvent_t copied[2] = {nullptr, nullptr}, consumed[2] = {nullptr, nullptr}, start = nullptr;
-    int rc = SYSID_OK;
-    auto cleanup = [&]() {
-        for (int b = 0; b < 2; ++b) { if (copied[b]) cudaEventDestroy(copied[b]); if (consumed[b]) cudaEventDestroy(consumed[b]); }
-        if (start) cudaEventDestroy(start);
-        if (cp) cudaStreamDestroy(cp);       // pending copies complete first; the runtime releases the stream afterwards
-    };
-#define HOST_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(SYSID_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
-    HOST_TRY(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
-    HOST_TRY(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
-    for (int b = 0; b < 2; ++b) {
-        HOST_TRY(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
-        HOST_TRY(cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+    // streams / events: the handle's own set when free, else a per-call set
+    std::unique_lock<std::mutex> lk(model->host_mu, std::try_to_lock);
+    HostStreamRes local;
+    HostStreamRes* R = nullptr;
+    if (lk.owns_lock()) {
+        if (!model->host_res.ok && !model->host_res.create()) { model->host_res.destroy(); return fail(SYSID_ERR_CUDA, "creating the internal streams failed"); }
+        R = &model->host_res;
+    } else {
+        if (!local.create()) { local.destroy(); return fail(SYSID_ERR_CUDA, "creating the internal streams failed"); }
+        R = &local;
     }
+    cudaStream_t cp = R->s_copy, sv = R->s_solve;
+    cudaEvent_t* copied = &R->ev[0]; cudaEvent_t* consumed = &R->ev[2];
+    cudaEvent_t start = R->ev[4], snap = R->ev[5], solved = R->ev[6];
+    int rc = SYSID_OK;
+    auto cleanup = [&]() { if (R == &local) local.destroy(); };
+    // LMI pre-solve (optional): the statistics are additive, so the fit of the first pre->samples samples is a point (and a set
+    // of multipliers) within the statistical noise of the final fit.  It runs as ONE thread block on an internal stream beside the
+    // remaining chunks, which leave it one SM; its result (pre->warm_out) warm-starts the final sysid_sdp_solve_plan.
+    const size_t warm_n = pre ? sdp_warm_doubles(pre->desc->num_links, pre->desc->ndof) : 0;
+    int64_t first = chunk;
+    bool presolve = false;
+    if (pre) {
+        first = (pre->samples > 0 && pre->samples < chunk) ? pre->samples : chunk;
+        presolve = (N >= 2 * first);
+    }
+    bool presolve_running = false;
+#define HOST_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(SYSID_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
+    if (pre) HOST_TRY(cudaMemsetAsync(pre->warm_out, 0, sizeof(double) * warm_n, st));      // "no record" until the pre-solve has written one
     // the staging buffers may still be read by earlier work on `stream`
     HOST_TRY(cudaEventRecord(start, st));
     HOST_TRY(cudaStreamWaitEvent(cp, start, 0));
     long long k = 0;
-    for (int64_t lo = 0; lo < N; lo += chunk, ++k) {
+    for (int64_t lo = 0; lo < N; ++k) {
         const int b = (int)(k & 1);
-        const int64_t n = (N - lo < chunk) ? (N - lo) : chunk;
+        // chunk sizes ramp up from 16 384 samples: the first kernel starts after 9 MB have crossed PCIe instead of 72 MB
+        int64_t want = (k < 20) ? ((int64_t)16384 << k) : chunk;
+        if (want > chunk) want = chunk;
+        if (presolve && !presolve_running && lo < first && lo + want > first) want = first - lo;      // a boundary exactly at `first`
+        const int64_t n = (N - lo < want) ? (N - lo) : want;
         if (k >= 2) HOST_TRY(cudaStreamWaitEvent(cp, consumed[b], 0));
         double* dst[6];
         size_t off = 0;
@@ -414,11 +488,25 @@ int sysid_gram_accumulate_host_ex(const sysid_model* model, const void* const* a
                 widen_f32_kernel<<<blocks, 256, 0, st>>>(land[b] + (dst[a] - stage[b]), dst[a], n, chunk, channels[a]);
                 HOST_TRY(cudaGetLastError());
             }
-        rc = sysid_gram_accumulate(model, dst[0], dst[1], dst[2], dst[3], M.n_ee > 0 ? dst[4] : nullptr, n, chunk,
-                                   weights_host ? dst[5] : nullptr, friction, stats, info, workspace, gram_ws, st);
+        rc = gram_accumulate_impl(model, dst[0], dst[1], dst[2], dst[3], M.n_ee > 0 ? dst[4] : nullptr, n, chunk,
+                                  weights_host ? dst[5] : nullptr, friction, stats, info, workspace, gram_ws, presolve_running ? 1 : 0, st);
         if (rc != SYSID_OK) { cleanup(); return rc; }
         HOST_TRY(cudaEventRecord(consumed[b], st));
+        if (presolve && !presolve_running && lo + n >= first) {
+            const size_t slen = sysid_stats_len(model, friction);
+            HOST_TRY(cudaMemcpyAsync(pre->stats_snapshot, stats, sizeof(double) * slen, cudaMemcpyDeviceToDevice, st));
+            HOST_TRY(cudaEventRecord(snap, st));
+            HOST_TRY(cudaStreamWaitEvent(sv, snap, 0));
+            char msg[256] = "";
+            rc = sdp_solve_planned(*pre->desc, (const double*)pre->plan, pre->stats_snapshot, (int64_t)slen, 1, pre->x_scratch,
+                                   pre->info_scratch, pre->sdp_workspace, pre->sdp_workspace_bytes, nullptr, pre->warm_out, sv, msg, sizeof(msg));
+            if (rc != SYSID_OK) { fail(rc, "pre-solve: %s", msg); cleanup(); return rc; }
+            HOST_TRY(cudaEventRecord(solved, sv));
+            presolve_running = true;
+        }
+        lo += n;
     }
+    if (presolve_running) HOST_TRY(cudaStreamWaitEvent(st, solved, 0));      // later work on `stream` sees the warm-start record
 #undef HOST_TRY
     cleanup();
     return SYSID_OK;
@@ -645,6 +733,33 @@ int sysid_sdp_solve(const sysid_sdp_desc* desc, const double* stats, int64_t sta
     char msg[256] = "";
     int rc = sdp_solve_launch(*desc, stats, stats_stride, batch, x_out, info_out, workspace, workspace_bytes,
                               (cudaStream_t)stream, msg, sizeof(msg));
+    if (rc != SYSID_OK) return fail(rc, "%s", msg);
+    return SYSID_OK;
+}
+
+size_t sysid_sdp_plan_bytes(int32_t num_links) { return sizeof(double) * sdp_plan_total_doubles(num_links); }
+
+int sysid_sdp_plan_create(const sysid_sdp_desc* desc, void* plan, size_t plan_bytes, void* stream) {
+    if (!desc || !plan) return fail(SYSID_ERR_INVALID, "null argument");
+    char msg[256] = "";
+    int rc = sdp_plan_upload(*desc, (double*)plan, plan_bytes, (cudaStream_t)stream, msg, sizeof(msg));
+    if (rc != SYSID_OK) return fail(rc, "%s", msg);
+    return SYSID_OK;
+}
+
+size_t sysid_sdp_solve_workspace_bytes(int32_t num_links, int32_t ndof, int32_t batch) {
+    return sizeof(double) * sdp_ws_doubles(num_links, ndof) * (size_t)(batch > 0 ? batch : 1);
+}
+
+size_t sysid_sdp_warm_len(int32_t num_links, int32_t ndof) { return sdp_warm_doubles(num_links, ndof); }
+
+int sysid_sdp_solve_plan(const sysid_sdp_desc* desc, const void* plan, const double* stats, int64_t stats_stride, int32_t batch,
+                         double* x_out, sysid_sdp_info* info_out, void* workspace, size_t workspace_bytes,
+                         const double* warm_in, double* warm_out, void* stream) {
+    if (!desc || !plan || !stats || !x_out || !info_out || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    char msg[256] = "";
+    int rc = sdp_solve_planned(*desc, (const double*)plan, stats, stats_stride, batch, x_out, info_out, workspace, workspace_bytes,
+                               warm_in, warm_out, (cudaStream_t)stream, msg, sizeof(msg));
     if (rc != SYSID_OK) return fail(rc, "%s", msg);
     return SYSID_OK;
 }

@@ -122,12 +122,13 @@ class DeviceModel:
         return stats
 
     def gram_accumulate_host(self, q, dq, ddq, tau, cnt, friction=True, weights=None, stats=None, info=None, chunk=131072,
-                             device=None):
+                             device=None, presolve=None, presolve_samples=0):
         """gram_accumulate for arrays still in HOST memory: float64 OR float32 torch CPU tensors / numpy arrays, channel-major
         with unit inner stride (pinned memory for full PCIe speed) -- exactly what the reference's read_data returns
         (float32 q / contact, float64 dq / ddq / tau; demo/solo_identification.py:10-33).  The upload is chunked and
-        overlapped with the kernel inside the library (sysid_gram_accumulate_host_ex); float32 arrays cross PCIe as float32
-        and are widened exactly on the device.  Returns the device statistics."""
+        overlapped with the kernel inside the library (sysid_gram_accumulate_host_presolve); float32 arrays cross PCIe as
+        float32 and are widened exactly on the device.  presolve: an SdpPlan whose LMI problem is solved on the first chunk's
+        statistics behind the rest of the stream (its record warm-starts the final solve).  Returns the device statistics."""
         hs = []
         for a, ch, name in ((q, self.nq, "q"), (dq, self.nv, "dq"), (ddq, self.nv, "ddq"), (tau, self.nd, "tau"), (cnt, self.n_ee, "contact")):
             t = torch.from_numpy(a) if isinstance(a, np.ndarray) else a
@@ -152,9 +153,14 @@ class DeviceModel:
         ptrs = (C.c_void_p * 5)(*[t.data_ptr() if t.shape[0] > 0 else None for t in hs])
         dts = (C.c_int32 * 5)(*[0 if t.dtype == torch.float64 else 1 for t in hs])
         lds = (C.c_int64 * 5)(*[max(t.stride(0), N) if t.shape[0] > 1 else N for t in hs])
-        _lib.check(self.lib.sysid_gram_accumulate_host_ex(self.handle, ptrs, dts, lds, N,
-                                                          C.c_void_p(wh.data_ptr()) if wh is not None else None,
-                                                          1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), chunk, _stream()))
+        pre = None
+        if presolve is not None:
+            # presolve: an SdpPlan -- the LMI fit of the first chunk is solved behind the stream and left in presolve.warm
+            pre = presolve.presolve_struct(presolve_samples)
+        _lib.check(self.lib.sysid_gram_accumulate_host_presolve(self.handle, ptrs, dts, lds, N,
+                                                                C.c_void_p(wh.data_ptr()) if wh is not None else None,
+                                                                1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), chunk,
+                                                                C.byref(pre) if pre is not None else None, _stream()))
         return stats
 
     def predict_rmse(self, q, dq, ddq, tau, cnt, phi):
@@ -280,9 +286,91 @@ def sdp_solve(stats, num_links, ndof, phi_prior, ellipsoids, total_mass, lambda_
     x = torch.empty((batch, c), dtype=torch.float64, device=stats.device)
     info = torch.zeros(batch * _lib.SDP_INFO_DTYPE.itemsize, dtype=torch.uint8, device=stats.device)
     one = lib.sysid_sdp_workspace_bytes(num_links, ndof)
-    plan_bytes = 8 * 320 * num_links
+    plan_bytes = lib.sysid_sdp_plan_bytes(num_links)
     nbytes = plan_bytes + (one - plan_bytes) * batch
     ws = torch.empty(nbytes, dtype=torch.uint8, device=stats.device)
     _lib.check(lib.sysid_sdp_solve(C.byref(d), _ptr(stats), slen, batch, _ptr(x), _ptr(info), _ptr(ws), ws.numel(), _stream()))
     info_np = info.cpu().numpy().view(_lib.SDP_INFO_DTYPE)
     return x, info_np
+
+
+class SdpPlan:
+    """Device-resident plan of the LMI-constrained fit for one (prior, ellipsoids, total mass, lambda, reg_type): the host work
+    of the reference's Solver.__init__ + problem build (src/solver.py:6-29,55-121) done ONCE; solve() then launches without
+    host work or synchronisation.  Also owns the solver workspace and the warm-start record of the pre-solve."""
+
+    def __init__(self, num_links, ndof, phi_prior, ellipsoids, total_mass, lambda_reg=1e-1, tol=1e-10, max_iters=0,
+                 reg_type="constant_pullback", epsilon=1e-6, device=None):
+        _require_cuda()
+        self.lib = _lib.load()
+        if reg_type not in _lib.REG_TYPES:
+            raise ValueError(f"reg_type {reg_type!r} is not supported on this path")
+        self.L, self.nd = int(num_links), int(ndof)
+        self.c = 10 * self.L + 2 * self.nd
+        self.slen = self.c * self.c + self.c + 2
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._phi0 = np.ascontiguousarray(np.asarray(phi_prior).astype(np.float64))
+        self._sa = np.ascontiguousarray(np.array([e["semi_axes"] for e in ellipsoids], dtype=np.float64).reshape(-1))
+        self._ce = np.ascontiguousarray(np.array([e["center"] for e in ellipsoids], dtype=np.float64).reshape(-1))
+        if self._phi0.size != 10 * self.L or self._sa.size != 3 * self.L or self._ce.size != 3 * self.L:
+            raise ValueError("phi_prior / bounding_ellipsoids do not match num_links")
+        d = _lib.SdpDesc()
+        d.num_links = self.L; d.ndof = self.nd
+        d.phi_prior = self._phi0.ctypes.data_as(C.POINTER(C.c_double))
+        d.semi_axes = self._sa.ctypes.data_as(C.POINTER(C.c_double))
+        d.centers = self._ce.ctypes.data_as(C.POINTER(C.c_double))
+        d.total_mass = float(total_mass); d.lambda_reg = float(lambda_reg); d.reg_type = _lib.REG_TYPES[reg_type]
+        d.epsilon = float(epsilon); d.tol = float(tol); d.max_iters = int(max_iters)
+        self.desc = d
+        self.plan = torch.empty(self.lib.sysid_sdp_plan_bytes(self.L), dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.sysid_sdp_plan_create(C.byref(d), _ptr(self.plan), self.plan.numel(), _stream()))
+        self.wlen = int(self.lib.sysid_sdp_warm_len(self.L, self.nd))
+        self.warm = torch.zeros(self.wlen, dtype=torch.float64, device=self.device)           # record of the pre-solve
+        self._ws = {}
+        self._pre = None
+
+    def key(self):
+        return (self.L, self.nd, self._phi0.tobytes(), self._sa.tobytes(), self._ce.tobytes(), self.desc.total_mass, self.desc.lambda_reg,
+                self.desc.reg_type, self.desc.epsilon, self.desc.tol, self.desc.max_iters)
+
+    def _workspace(self, batch, tag=""):
+        k = (batch, tag)
+        if k not in self._ws:
+            self._ws[k] = torch.empty(self.lib.sysid_sdp_solve_workspace_bytes(self.L, self.nd, batch), dtype=torch.uint8, device=self.device)
+        return self._ws[k]
+
+    def presolve_struct(self, samples=0):
+        if self._pre is None:
+            self._pre_bufs = (self._workspace(1, "pre"), torch.empty(self.slen, dtype=torch.float64, device=self.device),
+                              torch.empty(self.c, dtype=torch.float64, device=self.device),
+                              torch.zeros(_lib.SDP_INFO_DTYPE.itemsize, dtype=torch.uint8, device=self.device))
+            p = _lib.Presolve()
+            p.desc = C.pointer(self.desc); p.plan = self.plan.data_ptr()
+            p.sdp_workspace = self._pre_bufs[0].data_ptr(); p.sdp_workspace_bytes = self._pre_bufs[0].numel()
+            p.stats_snapshot = self._pre_bufs[1].data_ptr(); p.x_scratch = self._pre_bufs[2].data_ptr()
+            p.info_scratch = self._pre_bufs[3].data_ptr(); p.warm_out = self.warm.data_ptr()
+            self._pre = p
+        self._pre.samples = int(samples)
+        return self._pre
+
+    def presolve_info(self):
+        """Solver record of the last pre-solve (numpy structured scalar); synchronises."""
+        return self._pre_bufs[3].cpu().numpy().view(_lib.SDP_INFO_DTYPE)[0] if self._pre is not None else None
+
+    def solve(self, stats, batch=1, warm=None, x_out=None, info_out=None, sync_info=True):
+        """stats: CUDA fp64 (batch, c*c+c+2) or flat.  warm: None, or a CUDA fp64 tensor of batch * warm_len doubles (e.g.
+        self.warm after a pre-solve).  Returns (x (batch, c) CUDA, info) -- info is the numpy record array when sync_info, else
+        the raw device buffer (no synchronisation)."""
+        stats = stats.contiguous()
+        if stats.dtype != torch.float64 or not stats.is_cuda or stats.numel() != batch * self.slen:
+            raise ValueError(f"stats: expected CUDA float64 with {batch}*{self.slen} elements")
+        x = x_out if x_out is not None else torch.empty((batch, self.c), dtype=torch.float64, device=stats.device)
+        info = info_out if info_out is not None else torch.zeros(batch * _lib.SDP_INFO_DTYPE.itemsize, dtype=torch.uint8, device=stats.device)
+        ws = self._workspace(batch)
+        if warm is not None and (warm.dtype != torch.float64 or not warm.is_cuda or warm.numel() != batch * self.wlen):
+            raise ValueError("warm: expected CUDA float64 with batch * warm_len elements")
+        _lib.check(self.lib.sysid_sdp_solve_plan(C.byref(self.desc), _ptr(self.plan), _ptr(stats), self.slen, batch, _ptr(x), _ptr(info),
+                                                 _ptr(ws), ws.numel(), _ptr(warm), None, _stream()))
+        if sync_info:
+            return x, info.cpu().numpy().view(_lib.SDP_INFO_DTYPE)
+        return x, info

@@ -498,3 +498,40 @@ def test_filters_vs_scipy_fixture_and_live():
     yr = F.filtfilt(b, a, torch.flip(xl[:2], dims=[1]).contiguous())
     # forward-backward == backward-forward away from the edge transients (the two passes commute; only the padding differs)
     assert (torch.flip(yr, dims=[1]) - y1)[:, 5000:-5000].abs().max().item() <= 1e-9
+
+
+def test_presolve_warm_start_same_optimum_fewer_steps():
+    """identify() on host arrays with the LMI pre-solve hidden behind the stream == the cold solve (the optimum is unique), with
+    fewer Newton steps in the final solve; an invalid / non-finite warm record is ignored; the plan-based solve equals the
+    one-shot C-ABI entry."""
+    from system_identification_b200.ops import SdpPlan, sdp_solve
+    from system_identification_b200.sys_identification import SystemIdentification
+    flat = H.flat_model("g1_12dof")
+    N = 80000
+    q, dq, ddq, cnt = H.synth.make_trajectory(flat, N, 77)
+    si = SystemIdentification.from_flat_model(flat)
+    dm = si.device_model
+    dev = list(_up((q, dq, ddq, np.zeros((12, N)), cnt)))
+    tau = _device_identifiable_tau(flat, dm, dev, seed=5).cpu().numpy()
+    host = (q.astype(np.float32), dq, ddq, tau, cnt.astype(np.float32))
+    from system_identification_b200.identify import identify
+    phi_c, bv_c, bc_c, info_c = identify(si, *host, return_info=True, presolve=False, chunk=16384)
+    phi_w, bv_w, bc_w, info_w = identify(si, *host, return_info=True, presolve=True, chunk=16384)
+    assert info_c["status"] == 0 and info_w["status"] == 0 and info_w["presolve_status"] in (0, 1)
+    xw, xc = np.concatenate([phi_w, bv_w, bc_w]), np.concatenate([phi_c, bv_c, bc_c])
+    assert H.rel(xw, xc) <= 1e-6
+    for i in range(13):
+        assert H.rel(phi_w[10 * i:10 * i + 10], phi_c[10 * i:10 * i + 10]) <= 1e-5
+    assert info_w["iterations"] < info_c["iterations"]
+    # plan-based solve == one-shot entry; garbage warm records are ignored
+    st = dm.gram_accumulate(*_up((q, dq, ddq, tau, cnt)))
+    plan = SdpPlan(13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass)
+    x1, i1 = plan.solve(st)
+    x0, i0 = sdp_solve(st, 13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass)
+    assert torch.equal(x1, x0) and int(i1[0]["iterations"]) == int(i0[0]["iterations"])
+    bad = torch.full((plan.wlen,), float("nan"), dtype=torch.float64, device="cuda")
+    x2, i2 = plan.solve(st, warm=bad)
+    assert torch.equal(x2, x0)
+    zero = torch.zeros(plan.wlen, dtype=torch.float64, device="cuda")           # valid flag 0
+    x3, _ = plan.solve(st, warm=zero)
+    assert torch.equal(x3, x0)
