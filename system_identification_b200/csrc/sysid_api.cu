@@ -381,6 +381,10 @@ size_t sysid_gram_host_workspace_bytes(const sysid_model* model, int64_t chunk) 
 }
 
 namespace {
+__global__ void copy_f64_kernel(const double* __restrict__ src, double* __restrict__ dst, int64_t n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) dst[e] = src[e];
+}
 // float32 landing buffer -> fp64 staging buffer (exact widening, what numpy does when the reference mixes its float32 q /
 // contact arrays into fp64 arithmetic): channels x n, both with leading dimension ld
 __global__ void widen_f32_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t n, int64_t ld, int channels) {
@@ -455,13 +459,20 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
     HOST_TRY(cudaEventRecord(start, st));
     HOST_TRY(cudaStreamWaitEvent(cp, start, 0));
     long long k = 0;
+    int64_t want = 0;
     for (int64_t lo = 0; lo < N; ++k) {
         const int b = (int)(k & 1);
-        // chunk sizes ramp up from 16 384 samples: the first kernel starts after 9 MB have crossed PCIe instead of 72 MB
-        int64_t want = (k < 20) ? ((int64_t)16384 << k) : chunk;
+        // chunk sizes ramp up from 16 384 samples by x1.5: the first kernel starts after 9 MB have crossed PCIe instead of 72 MB, and
+        // with two staging buffers the copy of chunk k+2 (which may only start when chunk k is consumed) stays hidden behind the
+        // kernel of chunk k+1 as long as it is < 1.77x longer (552 B/sample at ~53 GB/s against ~18.4 ns/sample of compute)
+        if (k == 0) want = 16384; else want += want / 2;
         if (want > chunk) want = chunk;
-        if (presolve && !presolve_running && lo < first && lo + want > first) want = first - lo;      // a boundary exactly at `first`
-        const int64_t n = (N - lo < want) ? (N - lo) : want;
+        // whole waves: every persistent CTA of the launch gets the same number of super-batches (no tail of one super-batch, which
+        // at 37 super-batches per CTA is 2.7 % of the launch)
+        const int64_t wave = (int64_t)FSB * (model->sm_count - (presolve_running ? 1 : 0));
+        int64_t take = (want >= 8 * wave) ? want - want % wave : want - want % FSB;
+        if (take <= 0) take = want;
+        const int64_t n = (N - lo < take) ? (N - lo) : take;
         if (k >= 2) HOST_TRY(cudaStreamWaitEvent(cp, consumed[b], 0));
         double* dst[6];
         size_t off = 0;
@@ -494,7 +505,10 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
         HOST_TRY(cudaEventRecord(consumed[b], st));
         if (presolve && !presolve_running && lo + n >= first) {
             const size_t slen = sysid_stats_len(model, friction);
-            HOST_TRY(cudaMemcpyAsync(pre->stats_snapshot, stats, sizeof(double) * slen, cudaMemcpyDeviceToDevice, st));
+            // snapshot by a kernel, not cudaMemcpyAsync: a device-to-device copy would queue on a copy engine behind the 72 MB
+            // host-to-device transfer of the next chunk and stall `stream` for more than a millisecond
+            copy_f64_kernel<<<(unsigned)((slen + 255) / 256), 256, 0, st>>>(stats, pre->stats_snapshot, (int64_t)slen);
+            HOST_TRY(cudaGetLastError());
             HOST_TRY(cudaEventRecord(snap, st));
             HOST_TRY(cudaStreamWaitEvent(sv, snap, 0));
             char msg[256] = "";
