@@ -134,6 +134,18 @@ int sysid_gram_accumulate(const sysid_model* model, const double* q, const doubl
                           int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* Block bootstrap (BASELINE.json configs[4]: many resamples of one log).  sysid_gram_blocks: ONE launch of the fused kernel that
+ * returns one statistics vector per block of `block` consecutive samples (stats_blocks + k * stats_stride, k < ceil(N / block));
+ * the statistics are additive, so the statistics of a resample that draws block k w_k times are sum_k w_k stats_k:
+ * sysid_combine_stats forms out (B x slen) = weights (B x K, row-major) x stats_blocks (K x slen) for all B resamples in one launch
+ * (fp64 tensor pipe).  The reference has no bootstrap; each resample is the reference's identification (demo/solo_identification.py:
+ * 67-88) of the log with its blocks repeated.  slen = c*c + c + 2 must be a multiple of 8 (it is for c = 154 and c = 130). */
+size_t sysid_gram_blocks_workspace_bytes(const sysid_model* model, int64_t N, int64_t block);
+int sysid_gram_blocks(const sysid_model* model, const double* q, const double* dq, const double* ddq, const double* tau,
+                      const double* contact, int64_t N, int64_t ld, int64_t block, int32_t friction, double* stats_blocks,
+                      int64_t stats_stride, int64_t* info, void* workspace, size_t workspace_bytes, void* stream);
+int sysid_combine_stats(const double* weights, int64_t B, int64_t K, const double* stats_blocks, int64_t slen, double* out, void* stream);
+
 /* Same statistics from HOST arrays (the layout read_data returns; pinned memory for full PCIe speed): the log is
  * streamed through two device staging buffers in chunks of `chunk` samples; the copy of chunk k+1 (internal copy
  * stream, cudaMemcpy2DAsync) overlaps the kernels of chunk k on `stream`.  stats / info / workspace are DEVICE pointers;

@@ -72,6 +72,9 @@ _SIGNATURES = {
     "sysid_stats_len": (C.c_size_t, [_P, C.c_int32]),
     "sysid_gram_workspace_bytes": (C.c_size_t, [_P]),
     "sysid_gram_accumulate": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, _P]),
+    "sysid_gram_blocks_workspace_bytes": (C.c_size_t, [_P, C.c_int64, C.c_int64]),
+    "sysid_gram_blocks": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "sysid_combine_stats": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, _P]),
     "sysid_gram_host_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
     "sysid_gram_accumulate_host": (C.c_int, [_P, _P, _P, _P, _P, _P, C.c_int64, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),
     "sysid_gram_accumulate_host_ex": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, C.c_int32, _P, _P, _P, C.c_size_t, C.c_int64, _P]),

@@ -6,10 +6,11 @@ times.  Because the fused kernel returns ADDITIVE sufficient statistics, a resam
 once:
 
   block == 1   sample-level bootstrap: one weighted sysid_gram_accumulate launch per resample (multinomial weights),
-  block  > 1   moving-block bootstrap for time series: one launch per block of `block` consecutive samples, then
-               stats_b = sum_k w_bk stats_k for all resamples at once (a (B x K) @ (K x c^2+c+2) product),
+  block  > 1   moving-block bootstrap for time series: ONE launch of the fused kernel in segmented mode (sysid_gram_blocks: one
+               statistics vector per block of `block` consecutive samples), then stats_b = sum_k w_bk stats_k for all resamples
+               in ONE launch on the fp64 tensor pipe (sysid_combine_stats),
 
-followed by ONE batched sysid_sdp_solve launch (one thread block per resample).  Under torch.distributed the resamples
+followed by ONE batched sysid_sdp_solve_plan launch (one thread block per resample) -- three launches for B fits.  Under torch.distributed the resamples
 shard by problem over the ranks (no data-path collective) and are gathered on every rank.
 """
 from __future__ import annotations
@@ -18,7 +19,8 @@ import numpy as np
 import torch
 
 from . import distributed as D
-from .ops import sdp_solve, to_device
+from .identify import _plan_for
+from .ops import combine_stats, to_device
 
 
 def bootstrap_weights(n_units, B, seed):
@@ -45,22 +47,23 @@ def bootstrap_identify(sysid, q, dq, ddq, tau, cnt, B=1024, block=1, seed=1005, 
     Wl = torch.from_numpy(W[lo:hi]).to(dev[0].device)
     nb = hi - lo
     if block == 1:
+        # sample-level bootstrap: B weighted passes (the work is inherently B Grams; prefer block > 1 for time series)
         stats = torch.zeros((nb, slen), dtype=torch.float64, device=dev[0].device)
         for b in range(nb):
             dm.gram_accumulate(*dev, friction=friction, weights=Wl[b].contiguous(), stats=stats[b])
     else:
-        per_block = torch.zeros((K, slen), dtype=torch.float64, device=dev[0].device)
-        for k in range(K):
-            sl = [a[:, k * block:min(N, (k + 1) * block)] for a in dev]
-            dm.gram_accumulate(*sl, friction=friction, stats=per_block[k])
-        stats = Wl @ per_block                              # (nb, slen): every statistic is additive over blocks
+        # moving-block bootstrap: ONE launch for the K per-block statistics, ONE for all resamples (stats_b = sum_k w_bk stats_k)
+        dev = [a if a.stride(1) == 1 else a.contiguous() for a in dev]
+        if len({a.stride(0) for a in dev}) != 1:
+            dev = [a.contiguous() for a in dev]
+        per_block = dm.gram_blocks(*dev, block, friction=friction)
+        stats = combine_stats(Wl.contiguous(), per_block) if nb > 0 else torch.zeros((0, slen), dtype=torch.float64, device=dev[0].device)
     x = torch.empty((nb, c), dtype=torch.float64, device=dev[0].device)
     info, err = None, None
     try:
         if nb > 0:
-            x, info = sdp_solve(stats, L, nd, sysid.get_phi_prior(), sysid.get_bounding_ellipsoids(), sysid.get_robot_mass(),
-                                lambda_reg=lambda_reg, tol=tol, max_iters=int(max_iters) * NEWTON_STEPS_PER_IPM_ITER, reg_type=reg_type,
-                                batch=nb)
+            plan = _plan_for(sysid, L, nd, lambda_reg, tol, max_iters, reg_type)       # host work once, then ONE batched launch
+            x, info = plan.solve(stats, batch=nb)
     except Exception as e:                                  # noqa: BLE001 -- every rank must still reach the collective below
         err = e
     if ws > 1:

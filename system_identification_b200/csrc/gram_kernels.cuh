@@ -133,46 +133,48 @@ constexpr int GRAM_MAXNT = WarpTiles<16, -1>::MAX_NT;
 
 // All F phases of one super-batch, executed by a group of NT threads (index t) separated by SYNC().
 #define SYSID_F_PHASES(SB, NT, SYNC, CONTACT, AFTER_STAGE)                                                               \
-    phase_stage<SB, NT>(M, args.io, base, args.N, inp, t);                                                               \
+    phase_stage<SB, NT>(M, args.io, base, Nlim, inp, t);                                                               \
     AFTER_STAGE                                                                                                          \
     SYNC();                                                                                                              \
-    for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, args.N, inp, ctx, scr, s_bad, it);              \
+    for (int it = t; it < SB * MAXD; it += NT) phase_sincos<SB>(M, base, Nlim, inp, ctx, scr, s_bad, it);              \
     SYNC();                                                                                                              \
     F_TICK(0)                                                                                                            \
-    for (int it = t; it < 2 * ((SB * M.nfch + 31) & ~31); it += NT) phase_chains<SB>(M, base, args.N, inp, ctx, scr, it); \
+    for (int it = t; it < 2 * ((SB * M.nfch + 31) & ~31); it += NT) phase_chains<SB>(M, base, Nlim, inp, ctx, scr, it); \
     SYNC();                                                                                                              \
     F_TICK(1)                                                                                                            \
-    for (int it = t; it < SB * MAXEE * (MAXCH + 1); it += NT) phase_feet<SB>(M, base, args.N, inp, ctx, scr, it);        \
+    for (int it = t; it < SB * MAXEE * (MAXCH + 1); it += NT) phase_feet<SB>(M, base, Nlim, inp, ctx, scr, it);        \
     SYNC();                                                                                                              \
     F_TICK(2)                                                                                                            \
     CONTACT(SB, NT, SYNC)
 
 // contact part, rmse kernel: S = J J^T -> Cholesky -> W = L^-1 J -> packed projector P = I - W^T W
 #define SYSID_CONTACT_PROJ(SB, NT, SYNC)                                                                                 \
-    for (int it = t; it < SB * (MAXEE * (MAXEE + 1) / 2); it += NT) phase_sblocks<SB>(M, base, args.N, ctx, scr, it);    \
+    for (int it = t; it < SB * (MAXEE * (MAXEE + 1) / 2); it += NT) phase_sblocks<SB>(M, base, Nlim, ctx, scr, it);    \
     SYNC();                                                                                                              \
-    for (int it = t; it < SB; it += NT) phase_chol<SB>(base, args.N, ctx, scr, s_bad, it);                               \
+    for (int it = t; it < SB; it += NT) phase_chol<SB>(base, Nlim, ctx, scr, s_bad, it);                               \
     SYNC();                                                                                                              \
     F_TICK(3)                                                                                                            \
-    for (int it = t; it < SB * MAXV; it += NT) phase_wcols<SB>(M, base, args.N, ctx, scr, it);                           \
+    for (int it = t; it < SB * MAXV; it += NT) phase_wcols<SB>(M, base, Nlim, ctx, scr, it);                           \
     SYNC();                                                                                                              \
     F_TICK(4)                                                                                                            \
-    phase_proj<SB, NT>(base, args.N, inp, ctx, scr, s_bad, t, s_stat);                                                   \
+    phase_proj<SB, NT>(base, Nlim, inp, ctx, scr, s_bad, t, s_stat);                                                   \
     SYNC();
 // contact part, Gram kernel: Householder QR of J_c^T -> orthonormal basis Q of null(J_c)
 #define SYSID_CONTACT_QBASIS(SB, NT, SYNC)                                                                               \
-    for (int it = t; it < ((16 * SB + 31) & ~31); it += NT) phase_qbuild<SB>(M, base, args.N, ctx, scr, s_bad, it);      \
+    for (int it = t; it < ((16 * SB + 31) & ~31); it += NT) phase_qbuild<SB>(M, base, Nlim, ctx, scr, s_bad, it);      \
     SYNC();                                                                                                              \
     F_TICK(3)                                                                                                            \
-    phase_finish<SB>(base, args.N, inp, ctx, s_bad, t, s_stat);                                                          \
-    for (int it = t; it < SB * NQMAX; it += NT) phase_qcols<SB>(base, args.N, ctx, scr, it);                             \
+    phase_finish<SB>(base, Nlim, inp, ctx, s_bad, t, s_stat);                                                          \
+    for (int it = t; it < SB * NQMAX; it += NT) phase_qcols<SB>(base, Nlim, ctx, scr, it);                             \
     SYNC();
 
 struct GramArgs {
     SampleIO io;
     long long N;
     int friction;
-    double* partial;      // [gridDim][PARTIAL_DOUBLES]
+    double* partial;      // [gridDim][PARTIAL_DOUBLES]; segmented mode: [segments][PARTIAL_DOUBLES]
+    long long seg_len;    // 0: one Gram of the whole launch (super-batches dealt round-robin to the CTAs).  > 0: one Gram per SEGMENT of
+                          // seg_len consecutive samples (block bootstrap): segments dealt round-robin, each worked through by one CTA
 };
 
 #ifdef SYSID_PHASE_CLOCKS
@@ -219,8 +221,11 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     tmem_fence_before_sync();
 #endif
     double acc[GRAM_MAXNT][2];
-    double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
-    const long long nsb = (args.N + FSB - 1) / FSB;
+    const bool segmented = args.seg_len > 0;
+    const long long nseg = segmented ? (args.N + args.seg_len - 1) / args.seg_len : 1;
+#if !defined(SYSID_PARK_FILL)
+    if (segmented) return;                     // diagnostic parking policies: whole-launch mode only (the host refuses earlier)
+#endif
 #ifdef SYSID_PHASE_CLOCKS
     long long clkF = 0, clkC = 0, clkM = 0, clk0, clkSub[6] = {0, 0, 0, 0, 0, 0};
 #endif
@@ -233,27 +238,33 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #ifdef SYSID_PHASE_CLOCKS
     clk0 = clock64();
 #endif
-    for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
-        const long long base = sb * FSB;
+    for (long long seg = segmented ? blockIdx.x : 0; seg < nseg; seg += segmented ? gridDim.x : 1) {
+    const long long seg_base = segmented ? seg * args.seg_len : 0;
+    const long long Nlim = segmented ? min(args.N, seg_base + args.seg_len) : args.N;
+    const long long nsb = (Nlim - seg_base + FSB - 1) / FSB;
+    double* partial = args.partial + (size_t)(segmented ? seg : (long long)blockIdx.x) * PARTIAL_DOUBLES;
+    bool first_sb = true;
+    for (long long sb = segmented ? 0 : blockIdx.x; sb < nsb; sb += segmented ? 1 : gridDim.x) {
+        const long long base = seg_base + sb * FSB;
         // The Gram accumulators (56 registers per thread) are parked in TENSOR MEMORY (tcgen05.st / tcgen05.ld, 115 KB of
         // the SM's otherwise idle 256 KB) whenever no M phase is running, so that the F phases and the tile fill get the
         // whole register file instead of spilling around them; see the policy note above the kernel.
 #if defined(SYSID_PARK_L2)
-#define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
+#define SYSID_PARK_ACC if (!first_sb) store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
 #elif defined(SYSID_PARK_FILL)
 #define SYSID_PARK_ACC                                   // already parked: the accumulators only visit registers for the M phases
 #else
-#define SYSID_PARK_ACC if (sb != (long long)blockIdx.x) tmem_park<GRAM_MAXNT>(tpark, acc);
+#define SYSID_PARK_ACC if (!first_sb) tmem_park<GRAM_MAXNT>(tpark, acc);
 #endif
         SYSID_F_PHASES(FSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_QBASIS, SYSID_PARK_ACC)
 #if defined(SYSID_PARK_FILL)
-        if (sb == (long long)blockIdx.x) {
+        if (first_sb) {
 #pragma unroll
             for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
             tmem_park<GRAM_MAXNT>(tpark, acc);
         }
 #else
-        if (sb != (long long)blockIdx.x) {
+        if (!first_sb) {
 #ifdef SYSID_PARK_L2
             load_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
 #else
@@ -266,9 +277,10 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
 #endif
         if (t < FSB) s_bad[t] = 0;
         PHASE_TICK(clkF)
-        prefetch_inputs<FSB, GRAM_THREADS>(M, args.io, (sb + gridDim.x) * FSB, args.N, t);     // lands in L2 during the rounds below
+        first_sb = false;
+        prefetch_inputs<FSB, GRAM_THREADS>(M, args.io, seg_base + (sb + (segmented ? 1 : (long long)gridDim.x)) * FSB, Nlim, t);     // lands in L2 during the rounds below
 #ifndef SYSID_FILL_DMMA
-        const int nsub = (int)min((long long)(FSB / FTS), (args.N - base + FTS - 1) / FTS);
+        const int nsub = (int)min((long long)(FSB / FTS), (Nlim - base + FTS - 1) / FTS);
         for (int sub = 0; sub < nsub; ++sub) {
             const int ksteps = phase_fill_q<FTS, TILE_LD, GRAM_THREADS>(M, ctx, tile, sub * FTS, args.friction, t);
             __syncthreads();
@@ -284,7 +296,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
             PHASE_TICK(clkM)
         }
 #else
-        const int nsamp = (int)min((long long)FSB, args.N - base);
+        const int nsamp = (int)min((long long)FSB, Nlim - base);
         for (int s0 = 0; s0 < nsamp;) {
             // the round: up to FTS samples, as long as their rows (18 - rank J_c each, 0 for a skipped sample) fit the tile
             int off[FTS + 1], cnt = 0;
@@ -326,22 +338,30 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         }
 #endif
     }
+    // flush: this CTA's partial Gram (whole-launch mode: once, after its last super-batch) or the segment's Gram
 #if defined(SYSID_PARK_FILL)
-    if ((long long)blockIdx.x < nsb) tmem_unpark<GRAM_MAXNT>(tpark, acc);
+    if (!first_sb) tmem_unpark<GRAM_MAXNT>(tpark, acc);
     else {
 #pragma unroll
         for (int k = 0; k < GRAM_MAXNT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
     }
 #endif
     store_dispatch<GRAM_WARPS, GRAM_MAXNT>(warp, partial, lane, acc);
-#ifndef SYSID_PARK_L2
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(s_tmem, TMEM_PARK_COLS);
-#endif
+    __syncthreads();                           // s_stat is complete (phase_finish of the last super-batch) and may be reset below
     if (tid == 0) {
         partial[GRAM_NTILES * 64 + 0] = s_stat[0];
         partial[GRAM_NTILES * 64 + 1] = s_stat[1];
         partial[GRAM_NTILES * 64 + 2] = s_stat[2];
+        if (segmented) { s_stat[0] = 0.0; s_stat[1] = 0.0; s_stat[2] = 0.0; }
+    }
+    __syncthreads();
+    }   // segments
+#ifndef SYSID_PARK_L2
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(s_tmem, TMEM_PARK_COLS);
+#endif
+    double* partial = args.partial + (size_t)blockIdx.x * PARTIAL_DOUBLES;
+    if (tid == 0 && !segmented) {
 #ifdef SYSID_PHASE_CLOCKS
         partial[GRAM_NTILES * 64 + 3] = (double)clkF; partial[GRAM_NTILES * 64 + 4] = (double)clkC; partial[GRAM_NTILES * 64 + 5] = (double)clkM;
         for (int k = 0; k < 6; ++k) partial[GRAM_NTILES * 64 + 6 + k] = (double)clkSub[k];
@@ -389,8 +409,12 @@ gram_stack_kernel(const StackArgs args) {
 
 // Deterministic reduction of the per-CTA partial Grams into stats = [G (c x c) | r (c) | s | n] (ADDS into stats).
 // Element (i, j), i >= j, of the (c+1) x (c+1) augmented Gram lives in tile tri(i/8, j/8).
+// gridDim.y > 1 (block bootstrap): statistics block y is the single partial y -> stats + y * stats_stride.
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, int c, double n_rows_per_weight,
-                                   double n_add_fixed, double* __restrict__ stats, long long* __restrict__ info) {
+                                   double n_add_fixed, double* __restrict__ stats, long long* __restrict__ info,
+                                   long long stats_stride = 0) {
+    partial += (size_t)blockIdx.y * nparts * PARTIAL_DOUBLES;
+    stats += (size_t)blockIdx.y * stats_stride;
     const int ca = c + 1;
     const int total = ca * (ca + 1) / 2;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -421,7 +445,45 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int npart
             f1 += partial[(size_t)p * PARTIAL_DOUBLES + GRAM_NTILES * 64 + 2];
         }
         stats[(size_t)c * c + c + 1] += n_rows_per_weight * wsum + n_add_fixed;
-        if (info) { info[0] += (long long)f0; info[1] += (long long)f1; }
+        if (info) {
+            if (gridDim.y > 1) { atomicAdd((unsigned long long*)&info[0], (unsigned long long)f0); atomicAdd((unsigned long long*)&info[1], (unsigned long long)f1); }
+            else { info[0] += (long long)f0; info[1] += (long long)f1; }
+        }
+    }
+}
+
+// out (B x E) = Wt (B x K) S (K x E): the statistics of B bootstrap resamples from the per-block statistics S and the
+// multiplicities Wt (every statistic is additive over blocks, n included).  A warp owns an 8 x 64 strip of `out` (eight DMMA
+// tiles), A and B fragments straight from global memory (S is a few tens of MB: L2-resident).  E must be a multiple of 8.
+constexpr int COMBINE_WARPS = 4;
+__global__ void __launch_bounds__(32 * COMBINE_WARPS)
+combine_stats_kernel(const double* __restrict__ Wt, long long B, long long K, const double* __restrict__ S, long long E,
+                     double* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
+    const long long e0 = ((long long)blockIdx.x * COMBINE_WARPS + warp) * 64, b0 = (long long)blockIdx.y * 8;
+    if (e0 >= E) return;
+    const int ntile = (int)min(8LL, (E - e0) / 8);
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    const bool rowok = b0 + r < B;
+    const double* wrow = Wt + (rowok ? b0 + r : 0) * K;
+    for (long long k = 0; k < K; k += 4) {
+        const bool kok = k + kk < K;
+        const double a = (rowok && kok) ? wrow[k + kk] : 0.0;
+        const double* srow = S + (kok ? k + kk : 0) * E + e0 + r;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            if (t < ntile) {
+                const double b = kok ? srow[8 * t] : 0.0;
+                dmma884(acc[t][0], acc[t][1], a, b);
+            }
+        }
+    }
+    if (rowok) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+            if (t < ntile) *reinterpret_cast<double2*>(out + (b0 + r) * E + e0 + 8 * t + 2 * kk) = make_double2(acc[t][0], acc[t][1]);
     }
 }
 
@@ -532,6 +594,7 @@ rmse_kernel(const __grid_constant__ DevModel M, const RmseArgs args) {
 #endif
     const long long nsb = (args.N + RSB - 1) / RSB;
     __syncthreads();
+    const long long Nlim = args.N;
     for (long long sb = blockIdx.x; sb < nsb; sb += gridDim.x) {
         const long long base = sb * RSB;
         SYSID_F_PHASES(RSB, GRAM_THREADS, __syncthreads, SYSID_CONTACT_PROJ, )

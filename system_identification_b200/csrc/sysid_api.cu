@@ -361,7 +361,7 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     if (rc) return rc;
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, weights, ld);
-    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace;
+    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = 0;
     gram_fused_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
     CUDA_TRY(cudaGetLastError());
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
@@ -369,6 +369,62 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, (double)M.nv, 0.0, stats,
                                                              (long long*)info);
     CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+// ---- block bootstrap (BASELINE configs[4]): one statistics vector per block of consecutive samples, ONE launch -----------------
+size_t sysid_gram_blocks_workspace_bytes(const sysid_model* model, int64_t N, int64_t block) {
+    if (!model || N < 0 || block <= 0) return 0;
+    const size_t nseg = (size_t)((N + block - 1) / block);
+    return sizeof(double) * (nseg > 0 ? nseg : 1) * PARTIAL_DOUBLES;
+}
+
+int sysid_gram_blocks(const sysid_model* model, const double* q, const double* dq, const double* ddq, const double* tau,
+                      const double* contact, int64_t N, int64_t ld, int64_t block, int32_t friction, double* stats_blocks,
+                      int64_t stats_stride, int64_t* info, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!model || !q || !dq || !ddq || !tau || !stats_blocks || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
+    if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
+    if (N < 0 || ld < N || block <= 0) return fail(SYSID_ERR_INVALID, "bad N/ld/block");
+    if (N == 0) return SYSID_OK;
+#if !defined(SYSID_PARK_FILL)
+    return fail(SYSID_ERR_UNSUPPORTED, "segmented statistics need the default accumulator parking policy");
+#endif
+    const DevModel& M = model->dev;
+    const size_t slen = sysid_stats_len(model, friction);
+    if (stats_stride < (int64_t)slen) return fail(SYSID_ERR_INVALID, "stats_stride smaller than the statistics vector");
+    const long long nseg = (N + block - 1) / block;
+    if (workspace_bytes < sysid_gram_blocks_workspace_bytes(model, N, block)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = opt_in_smem(gram_fused_kernel, GRAM_SMEM_BYTES);
+    if (rc) return rc;
+    GramArgs a{};
+    a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
+    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = block;
+    const int grid = (int)(nseg < model->sm_count ? nseg : model->sm_count);
+    gram_fused_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    CUDA_TRY(cudaGetLastError());
+    const int c = M.nparams + (friction ? 2 * M.nd : 0);
+    const int total = (c + 1) * (c + 2) / 2;
+    CUDA_TRY(cudaMemsetAsync(stats_blocks, 0, sizeof(double) * (size_t)stats_stride * (size_t)nseg, st));
+    for (long long y0 = 0; y0 < nseg; y0 += 65535) {
+        const unsigned ny = (unsigned)((nseg - y0 < 65535) ? (nseg - y0) : 65535);
+        gram_reduce_kernel<<<dim3((total + 255) / 256, ny), 256, 0, st>>>((const double*)workspace + (size_t)y0 * PARTIAL_DOUBLES, 1, c, (double)M.nv, 0.0,
+                                                                        stats_blocks + (size_t)y0 * stats_stride, (long long*)info, (long long)stats_stride);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SYSID_OK;
+}
+
+int sysid_combine_stats(const double* weights, int64_t B, int64_t K, const double* stats_blocks, int64_t slen, double* out, void* stream) {
+    if (!weights || !stats_blocks || !out) return fail(SYSID_ERR_INVALID, "null argument");
+    if (B < 0 || K <= 0 || slen <= 0 || slen % 8 != 0) return fail(SYSID_ERR_INVALID, "bad B/K/slen (slen must be a multiple of 8)");
+    if (B == 0) return SYSID_OK;
+    const unsigned gx = (unsigned)((slen + 64 * COMBINE_WARPS - 1) / (64 * COMBINE_WARPS));
+    for (int64_t b0 = 0; b0 < B; b0 += 8 * 65535) {
+        const unsigned gy = (unsigned)(((B - b0 < 8 * 65535 ? B - b0 : 8 * 65535) + 7) / 8);
+        combine_stats_kernel<<<dim3(gx, gy), 32 * COMBINE_WARPS, 0, (cudaStream_t)stream>>>(weights + b0 * K, B - b0, K, stats_blocks, slen, out + b0 * slen);
+        CUDA_TRY(cudaGetLastError());
+    }
     return SYSID_OK;
 }
 

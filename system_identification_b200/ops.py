@@ -121,6 +121,24 @@ class DeviceModel:
                                                   ws.numel(), _stream()))
         return stats
 
+    def gram_blocks(self, q, dq, ddq, tau, cnt, block, friction=True, info=None):
+        """One statistics vector per block of `block` consecutive samples, in ONE launch of the fused kernel (segmented mode):
+        returns (K, stats_len) with K = ceil(N / block).  Block bootstrap: resample statistics = weights @ this (combine_stats)."""
+        q = _chan(q, self.nq, "q"); dq = _chan(dq, self.nv, "dq"); ddq = _chan(ddq, self.nv, "ddq")
+        tau = _chan(tau, self.nd, "tau"); cnt = _chan(cnt, self.n_ee, "contact")
+        N = q.shape[1]
+        ld = self._common_ld(q, dq, ddq, tau, cnt)
+        block = int(block)
+        if block < 1:
+            raise ValueError("block must be >= 1")
+        K = (N + block - 1) // block
+        slen = self.stats_len(friction)
+        out = torch.empty((K, slen), dtype=torch.float64, device=q.device)
+        ws = self._workspace("gram_blocks", self.lib.sysid_gram_blocks_workspace_bytes(self.handle, N, block), q.device)
+        _lib.check(self.lib.sysid_gram_blocks(self.handle, _ptr(q), _ptr(dq), _ptr(ddq), _ptr(tau), _ptr(cnt), N, ld, block,
+                                              1 if friction else 0, _ptr(out), slen, _ptr(info), _ptr(ws), ws.numel(), _stream()))
+        return out
+
     def gram_accumulate_host(self, q, dq, ddq, tau, cnt, friction=True, weights=None, stats=None, info=None, chunk=131072,
                              device=None, presolve=None, presolve_samples=0):
         """gram_accumulate for arrays still in HOST memory: float64 OR float32 torch CPU tensors / numpy arrays, channel-major
@@ -207,6 +225,23 @@ def gram_from_stack(A, b, stats=None):
     ws = torch.empty(nbytes, dtype=torch.uint8, device=A.device)
     _lib.check(lib.sysid_gram_from_stack(_ptr(A), _ptr(b), rows, c, _ptr(stats), _ptr(ws), ws.numel(), _stream()))
     return stats
+
+
+def combine_stats(weights, stats_blocks):
+    """(B, K) multiplicities x (K, stats_len) per-block statistics -> (B, stats_len) resample statistics, one launch on the fp64
+    tensor pipe (sysid_combine_stats)."""
+    _require_cuda()
+    lib = _lib.load()
+    if weights.dtype != torch.float64 or not weights.is_cuda or weights.dim() != 2 or not weights.is_contiguous():
+        raise ValueError("weights: expected contiguous CUDA float64 (B, K)")
+    if stats_blocks.dtype != torch.float64 or not stats_blocks.is_cuda or stats_blocks.dim() != 2 or not stats_blocks.is_contiguous():
+        raise ValueError("stats_blocks: expected contiguous CUDA float64 (K, stats_len)")
+    B, K = weights.shape
+    if stats_blocks.shape[0] != K:
+        raise ValueError("weights and stats_blocks disagree on the number of blocks")
+    out = torch.empty((B, stats_blocks.shape[1]), dtype=torch.float64, device=weights.device)
+    _lib.check(lib.sysid_combine_stats(_ptr(weights), B, K, _ptr(stats_blocks), stats_blocks.shape[1], _ptr(out), _stream()))
+    return out
 
 
 def tsqr(A, b=None):

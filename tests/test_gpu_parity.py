@@ -535,3 +535,51 @@ def test_presolve_warm_start_same_optimum_fewer_steps():
     zero = torch.zeros(plan.wlen, dtype=torch.float64, device="cuda")           # valid flag 0
     x3, _ = plan.solve(st, warm=zero)
     assert torch.equal(x3, x0)
+
+
+def test_bootstrap_1024_solo_20k_full_size():
+    """BASELINE configs[4] at full size: 1024 moving-block resamples of the 20 000-sample Solo-12 log in three launches
+    (segmented fused kernel -> resample combination on the tensor pipe -> batched LMI solve).  Per-block statistics against the
+    oracle's C twin, resample statistics against physically replicated logs, fits against the oracle's solve."""
+    from oracle import sdp as osdp
+    from oracle.cbuild import COracle
+    from system_identification_b200.bootstrap import bootstrap_identify, bootstrap_weights
+    from system_identification_b200.ops import combine_stats
+    from system_identification_b200.sys_identification import SystemIdentification
+    N, B, block, c = 20000, 1024, 100, 154
+    flat = H.flat_model("solo12")
+    q, dq, ddq, cnt = H.synth.make_trajectory(flat, N, H.synth.SEEDS["solo12_bootstrap"])
+    si = SystemIdentification.from_flat_model(flat)
+    dm = si.device_model
+    dev = list(_up((q, dq, ddq, np.zeros((12, N)), cnt)))
+    dev[3] = H.synth.identifiable_tau_device(flat, dm, dev, seed=31, perturb=0.1, bv_max=0.02, bc_max=0.05, noise=0.05)
+    data = (q, dq, ddq, dev[3].cpu().numpy(), cnt)
+    # per-block statistics: one launch; blocks 0, 77 and the last (ragged: 20 000 = 200 x 100, so also try block = 96)
+    co = COracle(H.oracle_tree(flat), flat.ee_names)
+    for blk in (100, 96):
+        pb = dm.gram_blocks(*dev, blk).cpu().numpy()
+        K = (N + blk - 1) // blk
+        assert pb.shape == (K, c * c + c + 2)
+        for k in (0, 77, K - 1):
+            so, _ = co.gram(*(a[:, k * blk:min(N, (k + 1) * blk)] for a in data))
+            assert H.rel(pb[k], so) <= 1e-12
+        assert H.rel(pb.sum(0), dm.gram_accumulate(*dev).cpu().numpy()) <= 1e-13
+    x, info, stats = bootstrap_identify(si, *dev, B=B, block=block, seed=1005, return_stats=True)
+    assert x.shape == (B, c) and set(int(i["status"]) for i in info) <= {0, 1}
+    K = N // block
+    W = bootstrap_weights(K, B, 1005)
+    for b in (0, 511, 1023):
+        idx = np.concatenate([np.arange(k * block, (k + 1) * block) for k in range(K) for _ in range(int(W[b, k]))])
+        rep = dm.gram_accumulate(*(a[:, idx].contiguous() for a in dev)).cpu().numpy()
+        assert H.rel(stats[b].cpu().numpy(), rep) <= 1e-12
+        G, r, s, n = H.split_stats(rep, c)
+        prob = osdp.build_problem(G, r, s, n, 13, flat.phi_prior, flat.robot_mass, flat.ellipsoids, 12)
+        xo, _ = osdp.solve_alm(prob)
+        assert H.rel(x[b], xo) <= TOL_PHI
+    # the combination kernel against a float64 matmul
+    Wd = torch.from_numpy(W[:37]).cuda()
+    pb = dm.gram_blocks(*dev, block)
+    assert H.rel(combine_stats(Wd, pb).cpu().numpy(), (Wd @ pb).cpu().numpy()) <= 1e-14
+    # spread of the resampled fits around the full-log fit: non-degenerate and centred
+    phi_full = si.identify(*dev)
+    assert np.abs(x[:, :130].mean(0) - phi_full).max() <= 5 * x[:, :130].std(0).max() and x[:, 0].std() > 0
