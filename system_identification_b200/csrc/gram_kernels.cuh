@@ -198,6 +198,10 @@ struct GramArgs {
 #define SYSID_PARK_FILL 1
 #endif
 
+// SEG = false: one Gram of the whole launch; SEG = true: one Gram per segment of args.seg_len samples (block bootstrap).  A template
+// parameter, not a runtime flag: the bookkeeping of the segmented mode costs the whole-launch kernel registers it does not have
+// (128 per thread, 0 spills; with a runtime flag ptxas spilled 28 bytes and the 1 M-sample launch took 2.5 % longer).
+template <bool SEG>
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     extern __shared__ __align__(16) double smem[];
@@ -221,7 +225,7 @@ gram_fused_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     tmem_fence_before_sync();
 #endif
     double acc[GRAM_MAXNT][2];
-    const bool segmented = args.seg_len > 0;
+    constexpr bool segmented = SEG;
     const long long nseg = segmented ? (args.N + args.seg_len - 1) / args.seg_len : 1;
 #if !defined(SYSID_PARK_FILL)
     if (segmented) return;                     // diagnostic parking policies: whole-launch mode only (the host refuses earlier)

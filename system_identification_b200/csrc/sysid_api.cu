@@ -357,12 +357,12 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     const int grid = (int)(nsb < max_ctas ? nsb : max_ctas);
     if (workspace_bytes < sizeof(double) * (size_t)grid * PARTIAL_DOUBLES)
         return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, sizeof(double) * (size_t)grid * PARTIAL_DOUBLES);
-    int rc = opt_in_smem(gram_fused_kernel, GRAM_SMEM_BYTES);
+    int rc = opt_in_smem(gram_fused_kernel<false>, GRAM_SMEM_BYTES);
     if (rc) return rc;
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, weights, ld);
     a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = 0;
-    gram_fused_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    gram_fused_kernel<false><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
     CUDA_TRY(cudaGetLastError());
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
     const int total = (c + 1) * (c + 2) / 2;
@@ -395,13 +395,13 @@ int sysid_gram_blocks(const sysid_model* model, const double* q, const double* d
     const long long nseg = (N + block - 1) / block;
     if (workspace_bytes < sysid_gram_blocks_workspace_bytes(model, N, block)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = opt_in_smem(gram_fused_kernel, GRAM_SMEM_BYTES);
+    int rc = opt_in_smem(gram_fused_kernel<true>, GRAM_SMEM_BYTES);
     if (rc) return rc;
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
     a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = block;
     const int grid = (int)(nseg < model->sm_count ? nseg : model->sm_count);
-    gram_fused_kernel<<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    gram_fused_kernel<true><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
     CUDA_TRY(cudaGetLastError());
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
     const int total = (c + 1) * (c + 2) / 2;

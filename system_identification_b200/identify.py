@@ -35,6 +35,8 @@ def _host_streamable(arrays, weights):
 
 
 PRESOLVE_MIN_SAMPLES = 16384      # shortest first chunk worth a pre-solve (below that the warm start is too noisy to pay for itself)
+PRESOLVE_MIN_LOG = 600_000        # the pre-solve (a cold solve, ~9 ms) only pays when the rest of the stream hides it: the statistics of
+                                  # 600 k samples take ~11 ms; on shorter (or sharded) logs the final solve would just wait for it
 
 
 def _plan_for(sysid, L, nd, lambda_reg, tol, max_iters, reg_type):
@@ -62,8 +64,9 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
     contiguous shard; with sharded=True each rank passes only its shard.  Returns phi (10 L,) [, b_v, b_c, info].
 
     Host arrays (what the reference's read_data returns) are streamed: chunked upload overlapped with the fused kernel, and
-    -- presolve=True -- the LMI fit of the first chunk's statistics solved behind the rest of the stream; its point and
-    multipliers warm-start the final solve (same unique optimum, a handful of Newton steps instead of ~55).
+    -- presolve=True, logs of at least PRESOLVE_MIN_LOG samples per rank ("force": any length) -- the LMI fit of the first
+    chunk's statistics solved behind the rest of the stream; its point and multipliers warm-start the final solve (same unique
+    optimum, about half the Newton steps).
 
     Deviations from the reference that are REPORTED, never silent (a RuntimeWarning each, counts in info):
       * samples with a non-finite input are skipped (the reference would propagate NaN into the whole stack);
@@ -101,7 +104,7 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
     if _host_streamable(arrays, weights):
         # host float64 / float32 arrays: chunked upload overlapped with the kernel inside the library
         n0 = min(int(chunk), max(PRESOLVE_MIN_SAMPLES, n_loc // 8))
-        use_pre = bool(presolve) and plan is not None and n_loc >= 2 * n0
+        use_pre = (presolve is True and n_loc >= PRESOLVE_MIN_LOG or presolve == "force") and plan is not None and n_loc >= 2 * n0
         dm.gram_accumulate_host(*arrays, friction=friction, weights=weights, stats=stats, info=counts, chunk=chunk,
                                 presolve=plan if use_pre else None, presolve_samples=n0)
         warm = plan.warm if use_pre else None

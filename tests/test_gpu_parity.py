@@ -516,7 +516,7 @@ def test_presolve_warm_start_same_optimum_fewer_steps():
     host = (q.astype(np.float32), dq, ddq, tau, cnt.astype(np.float32))
     from system_identification_b200.identify import identify
     phi_c, bv_c, bc_c, info_c = identify(si, *host, return_info=True, presolve=False, chunk=16384)
-    phi_w, bv_w, bc_w, info_w = identify(si, *host, return_info=True, presolve=True, chunk=16384)
+    phi_w, bv_w, bc_w, info_w = identify(si, *host, return_info=True, presolve="force", chunk=16384)
     assert info_c["status"] == 0 and info_w["status"] == 0 and info_w["presolve_status"] in (0, 1)
     xw, xc = np.concatenate([phi_w, bv_w, bc_w]), np.concatenate([phi_c, bv_c, bc_c])
     assert H.rel(xw, xc) <= 1e-6
