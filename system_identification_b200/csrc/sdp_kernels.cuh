@@ -14,6 +14,7 @@
 #pragma once
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,6 +39,8 @@ struct SdpParams {
     int L, nd, c, m;
     double total_mass, eps, const_reg, tol;
     int max_iters;
+    int start_mode;            // 0: cold start at the prior (default), 1: minimum-norm point of the mass equality (round 1); diagnostic
+    int stall_break;           // 1: leave an inner loop after two consecutive tiny line-search steps (default), 0: round-1 behaviour
     long long stats_stride;
     size_t ws_stride;          // doubles of workspace per problem
 };
@@ -825,7 +828,10 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     const double ata = dot_c(at, at);
     // cold start: the prior (friction coefficients 0), moved onto the mass equality along at -- where the reference starts cvxpy
     // (src/solver.py:19) and, measured on the oracle's twin of this iteration, 25 % fewer Newton steps than the minimum-norm point
-    if (tid < L) {
+    if (prm.start_mode == 1) {
+        const double ata0 = dot_c(at, at);
+        for (int a = tid; a < c; a += SDP_THREADS) y[a] = at[a] * prm.total_mass / ata0;
+    } else if (tid < L) {
         const double* Ti = Tm + (size_t)tid * 100;
         const double* p0 = plan + (size_t)tid * SDP_PLAN_LINK + 320;
         double yy[10];
@@ -836,7 +842,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         }
         for (int a = 0; a < 10; ++a) y[10 * tid + a] = yy[a];
     }
-    for (int k = tid; k < 2 * nd; k += SDP_THREADS) y[np + k] = 0.0;
+    if (prm.start_mode != 1) for (int k = tid; k < 2 * nd; k += SDP_THREADS) y[np + k] = 0.0;
     for (int r = tid; r < m; r += SDP_THREADS) lam[r] = 0.0;
     __syncthreads();
     {
@@ -941,7 +947,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             tiny = (t <= 1e-4) ? tiny + 1 : 0;
             for (int a = tid; a < c; a += SDP_THREADS) { y[a] = yt[a]; hy[a] += t * Ka[a]; }
             __syncthreads();
-            if (tiny >= 2) break;
+            if (tiny >= 2 && prm.stall_break) break;
         }
         // multiplier update lam <- Proj_K(lam - sigma g(y)) = pw ; KKT residual |lam_new - lam| / sigma
         double part = 0.0, pg = 0.0;
@@ -1085,6 +1091,9 @@ inline int sdp_solve_planned(const sysid_sdp_desc& d, const double* dplan, const
     prm.total_mass = d.total_mass; prm.eps = d.epsilon; prm.const_reg = 0.0; prm.tol = d.tol > 0 ? d.tol : 1e-10;
     prm.max_iters = d.max_iters > 0 ? d.max_iters : SDP_DEFAULT_MAX_ITERS;
     prm.stats_stride = stats_stride; prm.ws_stride = ws_n;
+    static const int dbg_start = [] { const char* e = std::getenv("SYSID_SDP_START"); return e ? std::atoi(e) : 0; }();       // diagnostic
+    static const int dbg_stall = [] { const char* e = std::getenv("SYSID_SDP_STALL_BREAK"); return e ? std::atoi(e) : 1; }();
+    prm.start_mode = dbg_start; prm.stall_break = dbg_stall;
     const size_t smem = sizeof(double) * ((size_t)prm.c * (prm.c + 1) + 10 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + 32 +
                                          ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES));
     cudaError_t e = cudaFuncSetAttribute(sdp_alm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
