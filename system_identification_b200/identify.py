@@ -83,12 +83,16 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         q, dq, ddq, tau, cnt = (a[:, lo:hi] for a in (q, dq, ddq, tau, cnt))
         if weights is not None:
             weights = weights[lo:hi]
+    fixed = not sysid._floating_base
+    if fixed:                                   # floating_base=False: emulated on the free-flyer kernels (urdf.py::flatten)
+        q, dq, ddq, tau, cnt = sysid._to_floating(q, dq, ddq, tau, cnt)
     arrays = (q, dq, ddq, tau, cnt)
     n_loc = arrays[0].shape[1]
     device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
     L, nd = sysid.get_num_links(), (sysid.joints_dof if friction else 0)
-    c = 10 * L + 2 * nd
-    slen = c * c + c + 2
+    c = 10 * L + 2 * nd                         # columns of the problem that is solved
+    cdev = dm.ncols(friction)                   # columns of the statistics the kernels produce (fixed base: + the pinned root body)
+    slen = cdev * cdev + cdev + 2
     err = None
     plan = None
     if rank == 0:
@@ -126,7 +130,7 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         try:
             if err is not None:
                 raise err
-            x, info_dev = plan.solve(stats, warm=warm, sync_info=False)
+            x, info_dev = plan.solve(sysid._stats_to_fixed(stats, friction) if fixed else stats, warm=warm, sync_info=False)
             out[:c] = x[0]
             out[c] = info_dev[:4].view(torch.int32)[0].to(torch.float64)
         except Exception as e:                                           # noqa: BLE001 -- re-raised below, on every rank
@@ -146,7 +150,7 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         raise ValueError("identify(): no usable sample (every sample of the log has a non-finite input or zero weight)")
     if n_skipped:
         warnings.warn(f"identify(): {n_skipped} sample(s) with a non-finite input were skipped (the reference would propagate NaN)", RuntimeWarning, stacklevel=2)
-    if n_rankloss:
+    if n_rankloss and not fixed:                # (the anchors of a fixed base are rank deficient by construction: 9 rows, rank 6)
         warnings.warn(f"identify(): the contact Jacobian lost row rank in {n_rankloss} sample(s); dependent rows were dropped "
                       "(pinv semantics, cutoff 1e-13 of the largest squared row norm)", RuntimeWarning, stacklevel=2)
     if status not in (0, 1):   # 1 = optimal_inaccurate, accepted like the reference accepts cp.OPTIMAL_INACCURATE

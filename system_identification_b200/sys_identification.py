@@ -30,11 +30,6 @@ class SystemIdentification(object):
     def __init__(self, urdf_file, config_file, floating_base):
         self._urdf_path = urdf_file
         self._floating_base = floating_base
-        if not floating_base:
-            # reference src/sys_identification.py:15-18,29-37 (pin.buildModelFromUrdf(path), _base_dof = 0, S = I): no demo
-            # uses it and the kernels' tree layout assumes the free-flyer root
-            raise NotImplementedError("floating_base=False (fixed-base models) is not supported by the B200 path: the kernels "
-                                      "assume a free-flyer root joint, as every reference driver script uses")
         with open(config_file, "r") as file:
             config = yaml.safe_load(file)
         robot_config = config.get("robot", {})
@@ -57,21 +52,31 @@ class SystemIdentification(object):
     def _init_from_flat(self, flat: FlatModel):
         self._flat = flat
         self._device_model = None
-        self.nq = flat.nq
-        self.nv = flat.nv
-        self._base_dof = 6
-        self.joints_dof = self.nv - self._base_dof
-        self._S = np.zeros((self.joints_dof, self.nv))
-        self._S[:, self._base_dof:] = np.eye(self.joints_dof)
+        self._fixed = not flat.floating_base
+        if self._fixed:
+            # reference src/sys_identification.py:15-18,34-37: nq = nv = number of joints, S = I.  The kernels run the free-flyer
+            # model with the base pinned (urdf.py::flatten); inputs are widened and outputs sliced below.
+            self.joints_dof = flat.nv - 6
+            self.nq = self.nv = self.joints_dof
+            self._base_dof = 0
+            self._S = np.eye(self.joints_dof)
+        else:
+            self.nq = flat.nq
+            self.nv = flat.nv
+            self._base_dof = 6
+            self.joints_dof = self.nv - self._base_dof
+            self._S = np.zeros((self.joints_dof, self.nv))
+            self._S[:, self._base_dof:] = np.eye(self.joints_dof)
         self._robot_name = flat.name
         self._robot_mass = flat.robot_mass
         self._link_names = list(flat.link_names)
-        self._end_eff_frame_names = list(flat.ee_names)
+        self._n_anchor = 3 if self._fixed else 0               # virtual contacts that pin the base (always in stance)
+        self._end_eff_frame_names = list(flat.ee_names)[self._n_anchor:]
         self._nb_ee = len(self._end_eff_frame_names)
         self._num_inertial_params = 10
         self._num_links = len(self._link_names)
-        if self._num_links != flat.nbodies:
-            raise ValueError(f"len(link_names) = {self._num_links} must equal the number of moving bodies {flat.nbodies}")
+        if self._num_links != flat.nbodies - (1 if self._fixed else 0):
+            raise ValueError(f"len(link_names) = {self._num_links} must equal the number of moving bodies {flat.nbodies - (1 if self._fixed else 0)}")
         self._phi_prior = np.zeros((self._num_inertial_params * self._num_links), dtype=np.float32)
         self.B_v = np.eye(self.joints_dof)
         self.B_c = np.eye(self.joints_dof)
@@ -203,7 +208,59 @@ class SystemIdentification(object):
         self._prev_sig[kind] = sig
         return hit
 
+    # ------------------------------------------------------------------ fixed-base emulation (floating_base=False)
+    def _to_floating(self, q, dq, ddq, tau, cnt):
+        """Fixed-base arrays ((nd, N) or (nd,)) -> the free-flyer kernels' arrays: base pinned at the identity with zero twist,
+        the three anchors in stance.  float64 numpy or CUDA tensors (same kind out)."""
+        import torch
+        def widen(a, head):
+            if isinstance(a, torch.Tensor):
+                a = a.to(torch.float64)
+                h = torch.tensor(head, dtype=torch.float64, device=a.device)
+                h = h.reshape(-1, *([1] * (a.dim() - 1))).expand(len(head), *a.shape[1:])
+                return torch.cat([h, a], dim=0).contiguous()
+            a = np.asarray(a, dtype=np.float64)
+            h = np.broadcast_to(np.asarray(head, dtype=np.float64).reshape(-1, *([1] * (a.ndim - 1))), (len(head),) + a.shape[1:])
+            return np.ascontiguousarray(np.concatenate([h, a], axis=0))
+        z6 = [0.0] * 6
+        cnt = cnt if (isinstance(cnt, torch.Tensor) or np.asarray(cnt).size) else np.zeros((0,) + np.asarray(q).shape[1:])
+        out = (widen(q, [0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0]), widen(dq, z6), widen(ddq, z6),
+               tau if isinstance(tau, torch.Tensor) else (None if tau is None else np.asarray(tau, dtype=np.float64)), widen(cnt, [1.0, 1.0, 1.0]))
+        return out
+
+    def _fixed_cols(self, friction=True):
+        """Columns of the free-flyer row block that belong to the fixed-base problem: the root body's ten are dropped."""
+        nbF, d = self._flat.nbodies, self.joints_dof
+        cols = list(range(10, 10 * nbF))
+        if friction:
+            cols += list(range(10 * nbF, 10 * nbF + 2 * d))
+        return np.array(cols)
+
+    def _stats_to_fixed(self, stats_F, friction=True):
+        """[G | r | s | n] of the free-flyer emulation -> the fixed-base problem's (root-body columns dropped; n = N nd: the
+        reference counts the rows of ITS stack, quirk Q4)."""
+        import torch
+        nbF, d = self._flat.nbodies, self.joints_dof
+        cF = 10 * nbF + (2 * d if friction else 0)
+        idx = torch.as_tensor(self._fixed_cols(friction), device=stats_F.device)
+        G = stats_F[:cF * cF].view(cF, cF).index_select(0, idx).index_select(1, idx)
+        r = stats_F[cF * cF:cF * cF + cF].index_select(0, idx)
+        tail = stats_F[cF * cF + cF:cF * cF + cF + 2] * torch.tensor([1.0, d / (d + 6.0)], dtype=torch.float64, device=stats_F.device)
+        return torch.cat([G.reshape(-1), r, tail]).contiguous()
+
     def _one_sample(self, q, dq, ddq, tau, cnt):
+        if self._fixed and not getattr(self, "_in_fixed", False):
+            qF, dqF, ddqF, tauF, cntF = self._to_floating(np.asarray(q, dtype=np.float64), np.asarray(dq, dtype=np.float64),
+                                                          np.asarray(ddq, dtype=np.float64), tau, np.asarray(cnt, dtype=np.float64))
+            self._in_fixed = True
+            try:
+                A, b = self._one_sample(qF, dqF, ddqF, tauF, cntF)
+            finally:
+                self._in_fixed = False
+            return A[6:][:, self._fixed_cols(True)], b[6:]
+        return self._one_sample_floating(q, dq, ddq, tau, cnt)
+
+    def _one_sample_floating(self, q, dq, ddq, tau, cnt):
         """Per-sample compat path: (A (nv, c), b (nv)) of one sample; served from a block launch when the arguments are
         column views of the log (see above), else one launch of the projected-batch kernel with N = 1."""
         from .ops import to_device
@@ -223,7 +280,8 @@ class SystemIdentification(object):
         dev = to_device(packed.reshape(-1, 1))
         o = 0
         parts = []
-        for n in (self.nq, self.nv, self.nv, self.joints_dof, self._nb_ee):
+        fl = self._flat
+        for n in (fl.nq, fl.nv, fl.nv, self.joints_dof, fl.n_ee):
             parts.append(dev[o:o + n]); o += n
         A, b = dm.projected_batch(*parts, friction=True)
         out = (A[0].cpu().numpy(), b[0].cpu().numpy())
@@ -309,14 +367,26 @@ class SystemIdentification(object):
 
     def gram(self, q, dq, ddq, tau, cnt, friction=True, weights=None):
         """Fused regressor+projector+Gram over all columns of the five (channels x N) arrays -> device stats tensor."""
+        if self._fixed:
+            q, dq, ddq, tau, cnt = self._to_floating(q, dq, ddq, tau, cnt)
         dev = self._upload(q, dq, ddq, tau, cnt)
-        return self.device_model.gram_accumulate(*dev, friction=friction, weights=weights)
+        st = self.device_model.gram_accumulate(*dev, friction=friction, weights=weights)
+        return self._stats_to_fixed(st, friction) if self._fixed else st
 
     def tau_prediction_rmse(self, q, dq, ddq, torque, cnt, phi):
         """(total, per-joint) with the reference's formulas: total = mean_i ||e_i||^2 (no root), per joint = RMSE."""
         import torch
+        phi = np.asarray(phi, dtype=np.float64)
+        if self._fixed:
+            q, dq, ddq, torque, cnt = self._to_floating(q, dq, ddq, torque, cnt)
+            phi = np.concatenate([np.zeros(10), phi])                   # the pinned root body does not move
         dev = self._upload(q, dq, ddq, torque, cnt)
-        out = self.device_model.predict_rmse(*dev, torch.as_tensor(np.asarray(phi, dtype=np.float64))).cpu().numpy()
+        out = self.device_model.predict_rmse(*dev, torch.as_tensor(phi)).cpu().numpy()
+        if self._fixed:
+            # the reference slices (y @ phi)[6:] whatever the base (src/sys_identification.py:429-430): on a fixed-base model that
+            # drops the first six JOINTS; total = mean_i sum_k e_ik^2 = sum_k rmse_k^2 over the joints that are kept
+            pj = out[1:][6:].copy()
+            return float(np.sum(pj ** 2)), pj
         return float(out[0]), out[1:].copy()
 
     def identify(self, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=1000, reg_type="constant_pullback",

@@ -107,8 +107,11 @@ class UrdfRobot:
 
     # ------------------------------------------------------------------ kinematic tree
     def flatten(self, floating_base=True, gravity=(0.0, 0.0, -9.81)) -> FlatModel:
-        if not floating_base:
-            raise ValueError("only floating_base=True is on the accelerated path (all reference demos use it)")
+        # floating_base=False (reference src/sys_identification.py:15-18: pin.buildModelFromUrdf(path), the root link welded to the
+        # universe) is EMULATED on the free-flyer kernels: the same tree, the base pinned at the identity with zero twist, and three
+        # virtual point contacts on the root body that are always "in stance" -- their Jacobian rows [I | -[r_k]x | 0] span the six
+        # base coordinates, so the contact null space is exactly {base twist = 0} x null(J_c restricted to the joints)
+        # (load_robot adds the contacts; SystemIdentification converts inputs and slices outputs)
         kids = {n: [] for n in self.links}
         has_parent = set()
         for j in self.joints.values():
@@ -147,6 +150,7 @@ class UrdfRobot:
             lower=np.array(rec["lo"]), upper=np.array(rec["hi"]), gravity=np.array(gravity, dtype=np.float64),
             body_params=np.array(rec["params"]))
         m._frames = frames
+        m.floating_base = bool(floating_base)
         return m
 
     @staticmethod
@@ -270,6 +274,9 @@ def merged_priors(robot: UrdfRobot, m: FlatModel, files_root, mesh_fallbacks=Non
     return phi, ell
 
 
+FIXED_BASE_ANCHORS = ((0.25, 0.0, 0.0), (0.0, 0.25, 0.0), (0.0, 0.0, 0.25))      # three non-collinear points on the root body
+
+
 def load_robot(urdf_file, config, floating_base=True, files_root=None, mesh_fallbacks=None, merged=False) -> FlatModel:
     """URDF + parsed YAML 'robot' section -> fully populated FlatModel."""
     robot = UrdfRobot(urdf_file)
@@ -277,13 +284,20 @@ def load_robot(urdf_file, config, floating_base=True, files_root=None, mesh_fall
     m.name = config.get("name") or m.name
     m.robot_mass = config.get("mass")
     m.link_names = list(config.get("link_names", []))
-    m.ee_names = list(config.get("end_effectors_frame_names", []))
+    m.ee_names = list(config.get("end_effectors_frame_names", []) or [])
     ee_joint, ee_off = [], []
+    if not floating_base:
+        for k, off in enumerate(FIXED_BASE_ANCHORS):
+            ee_joint.append(1); ee_off.append(np.array(off))
+        if len(m.ee_names) > 1:
+            raise ValueError("fixed-base emulation leaves room for one contact frame (three of the four contact slots pin the base)")
     for n in m.ee_names:
         if n not in m._frames:
             raise ValueError(f"end-effector frame {n!r} is not a link of {urdf_file}")
         jid, pose = m._frames[n]
         ee_joint.append(jid); ee_off.append(pose.p)
+    if not floating_base:
+        m.ee_names = [f"__fixed_base_anchor_{k}" for k in range(len(FIXED_BASE_ANCHORS))] + m.ee_names
     m.ee_joint = np.array(ee_joint, dtype=np.int32)
     m.ee_offset = np.array(ee_off, dtype=np.float64).reshape(-1, 3)
     if files_root is None:
