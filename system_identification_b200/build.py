@@ -19,7 +19,7 @@ HEADER = os.path.join("..", "..", "include", "sysid_b200.h")
 # translation unit -> the files it depends on
 UNITS = {
     "sysid_api.cu": ["sysid_api.cu", "gram_kernels.cuh", "kinematics.cuh", "phases.cuh", "model.cuh", "sdp_kernels.cuh",
-                     "filter_kernels.cuh", "gram_tiles.inc", "tmem_park.cuh", HEADER],
+                     "filter_kernels.cuh", "gram_tiles.inc", "tmem_park.cuh", "proj_phase.cuh", "bigmodel.cuh", HEADER],
     "ingest_api.cu": ["ingest_api.cu", "ingest_kernels.cuh", HEADER],
     "extras_api.cu": ["extras_api.cu", "tsqr_kernels.cuh", HEADER],
 }

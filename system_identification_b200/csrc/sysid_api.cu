@@ -15,6 +15,7 @@
 #include "gram_kernels.cuh"
 #include "sdp_kernels.cuh"
 #include "filter_kernels.cuh"
+#include "bigmodel.cuh"
 
 using namespace sysid;
 
@@ -41,7 +42,9 @@ struct HostStreamRes {
 };
 
 struct sysid_model {
-    DevModel dev;
+    DevModel dev;                  // fused path (trees inside the compiled envelope); dims are valid for every model
+    bool big = false;              // tree outside the envelope (G1-29dof): stages 1-2 through bigmodel.cuh
+    big::BigModel bm;
     int sm_count;
     mutable std::mutex host_mu;
     mutable HostStreamRes host_res;
@@ -58,6 +61,10 @@ int set_error(int code, const char* message) {
     return code;
 }
 }  // namespace sysid
+
+namespace {
+__global__ void add_rankloss_kernel(const int* __restrict__ count, long long* __restrict__ info) { info[0] += (long long)count[0]; }
+}  // namespace
 
 namespace {
 
@@ -113,7 +120,7 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
     *out = nullptr;
     if (!d->parent || !d->jtype || !d->axis || !d->place_R || !d->place_p) return fail(SYSID_ERR_INVALID, "null tree array");
     if (d->njoints < 2) return fail(SYSID_ERR_INVALID, "tree needs at least the universe and a root joint");
-    if (d->njoints > MAXJ) return fail(SYSID_ERR_UNSUPPORTED, "njoints %d exceeds this build's envelope (%d)", d->njoints, MAXJ);
+    if (d->njoints > big::BJ) return fail(SYSID_ERR_UNSUPPORTED, "njoints %d exceeds this build's envelope (%d)", d->njoints, big::BJ);
     if (d->n_ee < 0 || d->n_ee > MAXEE) return fail(SYSID_ERR_UNSUPPORTED, "n_ee %d exceeds this build's envelope (%d)", d->n_ee, MAXEE);
     if (d->n_ee > 0 && (!d->ee_joint || !d->ee_offset)) return fail(SYSID_ERR_INVALID, "null end-effector array");
     if (d->jtype[1] != SYSID_JT_FREEFLYER || d->parent[1] != 0)
@@ -121,7 +128,43 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
     sysid_model* m = new (std::nothrow) sysid_model;
     if (!m) return fail(SYSID_ERR_INVALID, "out of host memory");
     std::memset(&m->dev, 0, sizeof(DevModel));
+    std::memset(&m->bm, 0, sizeof(big::BigModel));
     DevModel& M = m->dev;
+    {
+        // does the tree fit the fused kernels' envelope?  (bodies, chain depth; everything else is checked below)
+        int depth_[big::BJ] = {0}, maxdepth = 0;
+        bool sane = true;
+        for (int j = 2; j < d->njoints; ++j) {
+            if (d->parent[j] < 1 || d->parent[j] >= j) { sane = false; break; }
+            depth_[j] = depth_[d->parent[j]] + 1;
+            if (depth_[j] > maxdepth) maxdepth = depth_[j];
+        }
+        if (sane && (d->njoints > MAXJ || maxdepth > MAXCH)) {
+            big::BigModel& B = m->bm;
+            const int nb = d->njoints - 1;
+            if (10 * nb + 2 * (nb - 1) + 1 > big::BCW || 6 + nb - 1 > big::BV) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "tree with %d joints exceeds the large-model path (%d columns)", d->njoints, big::BCW); }
+            B.njoints = d->njoints; B.nb = nb; B.n_ee = d->n_ee; B.nv = 6 + nb - 1; B.nq = 7 + nb - 1; B.nd = nb - 1; B.nparams = 10 * nb;
+            for (int j = 0; j < d->njoints; ++j) {
+                B.parent[j] = d->parent[j]; B.jtype[j] = d->jtype[j];
+                B.idx_v[j] = (j <= 1) ? 0 : 6 + (j - 2); B.idx_q[j] = (j <= 1) ? 0 : 7 + (j - 2);
+                for (int k = 0; k < 3; ++k) { B.axis[j][k] = d->axis[3 * j + k]; B.pp[j][k] = d->place_p[3 * j + k]; }
+                for (int k = 0; k < 9; ++k) B.pR[j][k] = d->place_R[9 * j + k];
+                if (j >= 2 && (d->jtype[j] < SYSID_JT_RX || d->jtype[j] > SYSID_JT_RU)) { delete m; return fail(SYSID_ERR_UNSUPPORTED, "joint %d: only revolute joints below the free-flyer root", j); }
+            }
+            for (int k = 0; k < 3; ++k) B.gravity[k] = d->gravity[k];
+            for (int k = 0; k < d->n_ee; ++k) {
+                if (d->ee_joint[k] < 1 || d->ee_joint[k] >= d->njoints) { delete m; return fail(SYSID_ERR_INVALID, "end effector %d: joint %d out of range", k, d->ee_joint[k]); }
+                B.ee_joint[k] = d->ee_joint[k];
+                for (int e = 0; e < 3; ++e) B.ee_off[k][e] = d->ee_offset[3 * k + e];
+            }
+            m->big = true;
+            M.njoints = B.njoints; M.nb = B.nb; M.n_ee = B.n_ee; M.nv = B.nv; M.nq = B.nq; M.nd = B.nd; M.nparams = B.nparams;   // dims only
+            int rc = device_sm_count(&m->sm_count);
+            if (rc != SYSID_OK) { delete m; return rc; }
+            *out = m;
+            return SYSID_OK;
+        }
+    }
     M.njoints = d->njoints; M.nb = d->njoints - 1; M.n_ee = d->n_ee;
     M.nv = 6 + (M.nb - 1); M.nq = 7 + (M.nb - 1); M.nd = M.nb - 1; M.nparams = 10 * M.nb;
     for (int j = 0; j < d->njoints; ++j) {
@@ -266,11 +309,53 @@ int sysid_model_dims(const sysid_model* model, sysid_dims* out) {
     return SYSID_OK;
 }
 
+// ---- large-model path (bigmodel.cuh): one chunk of <= BIG_CHUNK samples through kin -> rows -> tail -> contact -> zrows ----------
+static int big_chunk_rows(const sysid_model* model, const SampleIO& io, long long base, int ns, int friction, bool contacts,
+                          const big::BigWs& w, cudaStream_t st) {
+    const big::BigModel& B = model->bm;
+    CUDA_TRY(cudaMemsetAsync(w.Yt, 0, sizeof(double) * (size_t)ns * B.nv * big::BCW, st));
+    big::big_kin_kernel<<<(ns + 127) / 128, 128, 0, st>>>(B, io, base, ns, w.kin);
+    big::big_rows_kernel<<<(ns * B.nb + 127) / 128, 128, 0, st>>>(B, ns, w.kin, w.Yt);
+    big::big_tail_kernel<<<(ns * B.nd + 127) / 128, 128, 0, st>>>(B, io, base, ns, friction, w.Yt);
+    if (contacts) {
+        big::big_contact_kernel<<<(ns + 63) / 64, 64, 0, st>>>(B, io, base, ns, w.kin, w.W, w.m3, w.rankloss);
+        const long long tot = (long long)ns * big::BMR * big::BCW;
+        big::big_zrows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, ns, w.Yt, w.W, w.m3, w.Z);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+static size_t big_workspace_bytes(const sysid_model* model) { return big::big_workspace(model->bm, nullptr).bytes + 256; }
+
+// per-sample outputs of the large-model path need scratch the small-model ABI has no argument for: stream-ordered allocation
+static int big_batch(const sysid_model* model, const SampleIO& io, int64_t N, int friction, double* Y, double* A, double* b, double* P, cudaStream_t st) {
+    void* buf = nullptr;
+    CUDA_TRY(cudaMallocAsync(&buf, big_workspace_bytes(model), st));
+    const big::BigWs w = big::big_workspace(model->bm, buf);
+    const big::BigModel& B = model->bm;
+    const int ncols = B.nparams + (friction ? 2 * B.nd : 0);
+    int rc = SYSID_OK;
+    for (int64_t lo = 0; lo < N && rc == SYSID_OK; lo += big::BIG_CHUNK) {
+        const int ns = (int)((N - lo < big::BIG_CHUNK) ? (N - lo) : big::BIG_CHUNK);
+        rc = big_chunk_rows(model, io, lo, ns, friction, A || b || P, w, st);
+        if (rc != SYSID_OK) break;
+        const long long tot = (long long)ns * B.nv * big::BCW;
+        big::big_emit_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, ns, ncols, ncols, w.Yt, w.W, w.Z, w.m3,
+            Y ? Y + (size_t)lo * B.nv * B.nparams : nullptr, A ? A + (size_t)lo * B.nv * ncols : nullptr,
+            b ? b + (size_t)lo * B.nv : nullptr, P ? P + (size_t)lo * B.nv * B.nv : nullptr);
+        if (cudaGetLastError() != cudaSuccess) rc = fail(SYSID_ERR_CUDA, "large-model emit kernel failed");
+    }
+    cudaFreeAsync(buf, st);
+    return rc;
+}
+
 int sysid_regressor_batch(const sysid_model* model, const double* q, const double* dq, const double* ddq,
                           int64_t N, int64_t ld, double* Y_out, void* stream) {
     if (!model || !q || !dq || !ddq || !Y_out) return fail(SYSID_ERR_INVALID, "null argument");
     if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
     if (N == 0) return SYSID_OK;
+    if (model->big) return big_batch(model, make_io(q, dq, ddq, nullptr, nullptr, nullptr, ld), N, 0, Y_out, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     const DevModel& M = model->dev;
     CUDA_TRY(cudaMemsetAsync(Y_out, 0, sizeof(double) * (size_t)N * M.nv * M.nparams, st));
@@ -296,6 +381,7 @@ int sysid_projected_batch(const sysid_model* model, const double* q, const doubl
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
     if (N == 0) return SYSID_OK;
+    if (model->big) return big_batch(model, make_io(q, dq, ddq, tau, contact, nullptr, ld), N, friction ? 1 : 0, nullptr, A_out, b_out, P_out, (cudaStream_t)stream);
     cudaStream_t st = (cudaStream_t)stream;
     int rc = opt_in_smem(sample_batch_kernel<1>, DBG_SMEM_BYTES);
     if (rc) return rc;
@@ -316,7 +402,36 @@ size_t sysid_stats_len(const sysid_model* model, int32_t friction) {
 
 size_t sysid_gram_workspace_bytes(const sysid_model* model) {
     if (!model) return 0;
+    if (model->big) return big_workspace_bytes(model);
     return sizeof(double) * (size_t)model->sm_count * PARTIAL_DOUBLES;
+}
+
+// large-model statistics: chunks through HBM, two DMMA SYRK passes per chunk (Ytilde^T Ytilde - Z^T Z), deterministic reduction
+static int big_gram(const sysid_model* model, const SampleIO& io, int64_t N, int friction, double* stats, int64_t* info,
+                    void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (io.weights) return fail(SYSID_ERR_UNSUPPORTED, "per-sample weights are not available on the large-model path");
+    if (workspace_bytes < big_workspace_bytes(model)) return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, big_workspace_bytes(model));
+    const big::BigModel& B = model->bm;
+    const big::BigWs w = big::big_workspace(B, (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
+    const int c = B.nparams + (friction ? 2 * B.nd : 0);
+    CUDA_TRY(cudaMemsetAsync(w.partial, 0, sizeof(double) * (size_t)big::BIG_NZ * big::SY_NBLK * big::SY_BLK * big::SY_BLK, st));
+    CUDA_TRY(cudaMemsetAsync(w.rankloss, 0, sizeof(int) * 4, st));
+    for (int64_t lo = 0; lo < N; lo += big::BIG_CHUNK) {
+        const int ns = (int)((N - lo < big::BIG_CHUNK) ? (N - lo) : big::BIG_CHUNK);
+        int rc = big_chunk_rows(model, io, lo, ns, friction, true, w, st);
+        if (rc != SYSID_OK) return rc;
+        big::big_syrk_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, 0, st>>>(w.Yt, (long long)ns * B.nv, 1.0, w.partial);
+        big::big_syrk_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, 0, st>>>(w.Z, (long long)ns * big::BMR, -1.0, w.partial);
+        CUDA_TRY(cudaGetLastError());
+    }
+    const int total = (c + 1) * (c + 2) / 2;
+    big::big_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(w.partial, big::BIG_NZ, c, (double)B.nv * (double)N, stats);
+    CUDA_TRY(cudaGetLastError());
+    if (info) {
+        add_rankloss_kernel<<<1, 1, 0, st>>>(w.rankloss, (long long*)info);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return SYSID_OK;
 }
 
 size_t sysid_gram_from_stack_workspace_bytes(int32_t c) {
@@ -349,6 +464,7 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
     if (N == 0) return SYSID_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (model->big) return big_gram(model, make_io(q, dq, ddq, tau, contact, weights, ld), N, friction ? 1 : 0, stats, info, workspace, workspace_bytes, st);
     const DevModel& M = model->dev;
     const long long nsb = (N + FSB - 1) / FSB;
     static const int debug_reserve = [] { const char* e = std::getenv("SYSID_DEBUG_RESERVE_SMS"); return e ? std::atoi(e) : 0; }();   // diagnostic
@@ -385,6 +501,7 @@ int sysid_gram_blocks(const sysid_model* model, const double* q, const double* d
     if (!model || !q || !dq || !ddq || !tau || !stats_blocks || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N < 0 || ld < N || block <= 0) return fail(SYSID_ERR_INVALID, "bad N/ld/block");
+    if (model->big) return fail(SYSID_ERR_UNSUPPORTED, "per-block statistics are not available on the large-model path");
     if (N == 0) return SYSID_OK;
 #if !defined(SYSID_PARK_FILL)
     return fail(SYSID_ERR_UNSUPPORTED, "segmented statistics need the default accumulator parking policy");
@@ -621,6 +738,7 @@ int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_
 
 size_t sysid_predict_rmse_workspace_bytes(const sysid_model* model) {
     if (!model) return 0;
+    if (model->big) return big_workspace_bytes(model);
     return sizeof(double) * (size_t)model->sm_count * RMSE_PARTIAL;
 }
 
@@ -631,6 +749,26 @@ int sysid_predict_rmse(const sysid_model* model, const double* q, const double* 
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N <= 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
     cudaStream_t st = (cudaStream_t)stream;
+    if (model->big) {
+        if (workspace_bytes < big_workspace_bytes(model)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
+        const big::BigModel& B = model->bm;
+        const big::BigWs w = big::big_workspace(B, (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
+        const SampleIO io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
+        double* sums = w.e2 + (size_t)big::BIG_CHUNK * big::BV;
+        CUDA_TRY(cudaMemsetAsync(sums, 0, sizeof(double) * big::BV, st));
+        const int ctau = B.nparams;                     // no friction columns in this pass: the torque column follows the body columns
+        for (int64_t lo = 0; lo < N; lo += big::BIG_CHUNK) {
+            const int ns = (int)((N - lo < big::BIG_CHUNK) ? (N - lo) : big::BIG_CHUNK);
+            int rc = big_chunk_rows(model, io, lo, ns, 0, true, w, st);
+            if (rc != SYSID_OK) return rc;
+            big::big_err_kernel<<<(ns * B.nd + 127) / 128, 128, 0, st>>>(B, ns, ctau, w.Yt, w.W, w.Z, w.m3, phi, w.e2);
+            big::big_err_sum_kernel<<<1, 64, 0, st>>>(ns, B.nd, w.e2, sums);
+            CUDA_TRY(cudaGetLastError());
+        }
+        big::big_err_final_kernel<<<1, 32, 0, st>>>(B.nd, N, sums, out);
+        CUDA_TRY(cudaGetLastError());
+        return SYSID_OK;
+    }
     const long long nsb = (N + RSB - 1) / RSB;
     const int grid = (int)(nsb < model->sm_count ? nsb : model->sm_count);
     if (workspace_bytes < sizeof(double) * (size_t)grid * RMSE_PARTIAL) return fail(SYSID_ERR_WORKSPACE, "workspace too small");

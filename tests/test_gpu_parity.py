@@ -215,9 +215,17 @@ def test_api_errors_are_reported_not_thrown_across_the_abi():
     big = copy.deepcopy(flat)
     big.parent = np.concatenate([flat.parent, [13]]).astype(np.int32); big.jtype = np.concatenate([flat.jtype, [1]]).astype(np.int32)
     big.axis = np.vstack([flat.axis, [1, 0, 0]]); big.place_R = np.concatenate([flat.place_R, np.eye(3)[None]]); big.place_p = np.vstack([flat.place_p, [0, 0, 0]])
+    h = _lib.create_model(big)                                      # 15 joints: outside the fused kernels' envelope, served by the large-model path
+    d = _lib.Dims(); lib.sysid_model_dims(h, __import__("ctypes").byref(d))
+    assert (d.nv, d.nbodies) == (19, 14)
+    lib.sysid_model_destroy(h)
+    huge = copy.deepcopy(flat)
+    extra = 30
+    huge.parent = np.concatenate([flat.parent, 13 + np.arange(extra)]).astype(np.int32); huge.jtype = np.concatenate([flat.jtype, np.ones(extra)]).astype(np.int32)
+    huge.axis = np.vstack([flat.axis] + [[1, 0, 0]] * extra); huge.place_R = np.concatenate([flat.place_R, np.tile(np.eye(3)[None], (extra, 1, 1))]); huge.place_p = np.vstack([flat.place_p, np.zeros((extra, 3))])
     with pytest.raises(_lib.SysidError) as e:
-        _lib.create_model(big)
-    assert e.value.code == -2                                       # outside the compiled envelope
+        _lib.create_model(huge)
+    assert e.value.code == -2                                       # 44 joints: outside every compiled envelope
 
 
 @pytest.mark.parametrize("name", H.ROBOTS)
