@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsysid_b200.so")
+LIB_PATH = os.environ.get("SYSID_B200_LIB") or os.path.join(_HERE, "libsysid_b200.so")   # the override is for diagnostic builds (build.py)
 
 SYSID_OK = 0
 SYSID_ERR_NOT_OPTIMAL = -4

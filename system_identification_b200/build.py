@@ -19,7 +19,7 @@ HEADER = os.path.join("..", "..", "include", "sysid_b200.h")
 # translation unit -> the files it depends on
 UNITS = {
     "sysid_api.cu": ["sysid_api.cu", "gram_kernels.cuh", "kinematics.cuh", "phases.cuh", "model.cuh", "sdp_kernels.cuh",
-                     "filter_kernels.cuh", "gram_tiles.inc", "tmem_park.cuh", "proj_phase.cuh", "bigmodel.cuh", HEADER],
+                     "filter_kernels.cuh", "gram_tiles.inc", "tmem_park.cuh", "proj_phase.cuh", "bigmodel.cuh", "gram_struct.cuh", "gram_tiles_struct.inc", HEADER],
     "ingest_api.cu": ["ingest_api.cu", "ingest_kernels.cuh", HEADER],
     "extras_api.cu": ["extras_api.cu", "tsqr_kernels.cuh", HEADER],
 }
@@ -42,7 +42,13 @@ def _stale(target, deps):
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("SYSID_NVCC_EXTRA", "").split()      # e.g. -DSYSID_PHASE_CLOCKS for tools/phase_clocks.py
-    force = force or bool(extra)
+    global OBJ, LIB
+    if extra:
+        # diagnostic builds never replace the shipped library: libsysid_b200_diag.so, loaded with SYSID_B200_LIB=<path>
+        tag = os.environ.get("SYSID_LIB_TAG", "diag")
+        OBJ = os.path.join(HERE, "_obj_" + tag)
+        LIB = os.path.join(HERE, "libsysid_b200_" + tag + ".so")
+        force = True
     os.makedirs(OBJ, exist_ok=True)
     relink = force or not os.path.exists(LIB)
     for src, deps in UNITS.items():

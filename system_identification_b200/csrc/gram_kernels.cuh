@@ -412,11 +412,14 @@ gram_stack_kernel(const StackArgs args) {
 }
 
 // Deterministic reduction of the per-CTA partial Grams into stats = [G (c x c) | r (c) | s | n] (ADDS into stats).
-// Element (i, j), i >= j, of the (c+1) x (c+1) augmented Gram lives in tile tri(i/8, j/8).
+// Element (a, b) of the augmented Gram in TILE coordinates lives in tile tri(a/8, b/8) of the lower triangle (both orders exist in
+// a diagonal tile); ColMap takes a column of the statistics (0 .. c, c = the torque column) to its tile column -- the identity for
+// gram_fused_kernel / gram_stack_kernel, the class layout for gram_struct_kernel.
 // gridDim.y > 1 (block bootstrap): statistics block y is the single partial y -> stats + y * stats_stride.
+struct ColMap { uint8_t p[CW]; };
 __global__ void gram_reduce_kernel(const double* __restrict__ partial, int nparts, int c, double n_rows_per_weight,
                                    double n_add_fixed, double* __restrict__ stats, long long* __restrict__ info,
-                                   long long stats_stride = 0) {
+                                   const ColMap cm, long long stats_stride = 0) {
     partial += (size_t)blockIdx.y * nparts * PARTIAL_DOUBLES;
     stats += (size_t)blockIdx.y * stats_stride;
     const int ca = c + 1;
@@ -428,8 +431,10 @@ __global__ void gram_reduce_kernel(const double* __restrict__ partial, int npart
         while (i * (i + 1) / 2 > e) --i;
         while ((i + 1) * (i + 2) / 2 <= e) ++i;
         const int j = e - i * (i + 1) / 2;
-        const int ti = i >> 3, tj = j >> 3;
-        const int off = (ti * (ti + 1) / 2 + tj) * 64 + (i & 7) * 8 + (j & 7);
+        const int pi = cm.p[i], pj = cm.p[j];
+        const int a = (pi >> 3) >= (pj >> 3) ? pi : pj, b = (pi >> 3) >= (pj >> 3) ? pj : pi;
+        const int ti = a >> 3, tj = b >> 3;
+        const int off = (ti * (ti + 1) / 2 + tj) * 64 + (a & 7) * 8 + (b & 7);
         double sum = 0.0;
         for (int p = 0; p < nparts; ++p) sum += partial[(size_t)p * PARTIAL_DOUBLES + off];
         if (i < c) {

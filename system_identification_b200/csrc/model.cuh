@@ -11,6 +11,7 @@ constexpr int MAXD = 12;     // actuated joints
 constexpr int MAXEE = 4;     // contact frames
 constexpr int MAXCH = 6;     // longest foot chain (joints between the foot and the root, root excluded)
 constexpr int CW = 160;      // padded width of one stacked row: 10*nb + 2*d + 1 (tau column) <= 155 -> 160
+constexpr int ST_MAXLEG = 4;  // legs (simple chains below the root) the structured-basis Gram kernel handles
 constexpr int PROJ_PARTS = 4;      // the projection phase of the fused kernel deals every sample's bodies to this many warps
 constexpr int PROJ_MAXITEMS = 12;  // chain-walk steps of one part (prefix joints it only accumulates + joints whose body it emits)
 
@@ -50,6 +51,21 @@ struct DevModel {
     uint8_t proj_root[PROJ_PARTS];
     uint32_t proj_tail[PROJ_PARTS];
     uint8_t proj_tailks[2][32];      // [friction][column group]: which 4-joint k-steps of the group are structurally non-zero
+    // structured null-space basis (gram_struct.cuh): every child of the root heads a simple chain ("leg") with at most one contact
+    // frame; the legs are dealt to two column classes of <= 6 joints.  Tile columns: class X at 72 X + [10 slot .. | 60 + slot
+    // (viscous) | 66 + slot (Coulomb)], torque column 144, root body 146..155.
+    int8_t st_ok;                    // 1: the model satisfies the above and the structured kernel serves it
+    int8_t st_nslot[2];              // joints of class A / B
+    int8_t st_slotjoint[2][6];       // class slot -> joint, -1: unused
+    int8_t st_cfoot[ST_MAXLEG];      // contact frame on leg c (index into ee_*), -1: none
+    int8_t st_ccls[ST_MAXLEG];       // column class of leg c
+    uint32_t st_jrec[MAXJ];          // per joint >= 2: leg | position in the leg << 2 | class << 5 | class slot << 6 | body column << 9 | viscous column << 17
+    // tile fill: one warp task = one body for all rows of a tile; kind << 4 | argument, kind 0: dense rows x joint (argument),
+    // 1: dense rows x root body + torque column, 2 / 3: class A / B rows x class slot (argument); sorted by cost, heaviest first
+    int8_t st_ntask;
+    int8_t st_maxlen;                // joints of the longest leg
+    int8_t st_nred;                  // columns of the reduced contact Jacobian: 6 + 3 (legs with a contact frame)
+    uint8_t st_task[32];
 };
 
 }  // namespace sysid

@@ -109,16 +109,38 @@ __device__ __forceinline__ void prefetch_inputs(const DevModel& M, const SampleI
 template <int SB, int NT>
 __device__ __forceinline__ void phase_stage(const DevModel& M, const SampleIO& io, long long base, long long N,
                                             double* __restrict__ inp, int t) {
-    for (int it = t; it < IN_CHANNELS * SB; it += NT) {
-        const int ch = it / SB, s = it - ch * SB;
-        const long long i = base + s;
-        double v = (ch == IN_WGT) ? 1.0 : 0.0;
-        if (i < N) {
-            const double* p = channel_ptr(M, io, ch, i);
-            if (p) v = *p;
-        }
-        inp[it] = v;
-    }
+    // One pass per input array with the channel count known at compile time (a generic channel -> pointer decode cost ~90
+    // instructions per element); every load of the thread is issued before the first store, so the super-batch still pays one
+    // global-memory latency.
+    const long long ld = io.ld;
+    const int nd = M.nd, nv = M.nv, n_ee = M.n_ee;
+    constexpr int KQ = ((4 + MAXD) * SB + NT - 1) / NT, KV = (MAXV * SB + NT - 1) / NT, KT = (MAXD * SB + NT - 1) / NT, KC = (MAXEE * SB + NT - 1) / NT;
+    double vq[KQ], vdq[KV], vddq[KV], vtau[KT], vcnt[KC];
+    auto load = [&](const double* __restrict__ src, int nch, int nch_max, int k) {
+        // element (ch, i) of src at src[ch * ld + i]; channels [nch, nch_max) and samples past N read as 0
+        const int it = t + k * NT, ch = it / SB, sl = it - ch * SB;
+        const long long i = base + sl;
+        return (src && it < nch_max * SB && ch < nch && i < N) ? src[ch * ld + i] : 0.0;
+    };
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) vq[k] = load(io.q + 3 * ld, 4 + nd, 4 + MAXD, k);
+#pragma unroll
+    for (int k = 0; k < KV; ++k) { vdq[k] = load(io.dq, nv, MAXV, k); vddq[k] = load(io.ddq, nv, MAXV, k); }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) vtau[k] = load(io.tau, nd, MAXD, k);
+#pragma unroll
+    for (int k = 0; k < KC; ++k) vcnt[k] = load(io.cnt, n_ee, MAXEE, k);
+    double w = 1.0;
+    if (t < SB && io.weights && base + t < N) w = io.weights[base + t];
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) if (t + k * NT < (4 + MAXD) * SB) inp[IN_Q * SB + t + k * NT] = vq[k];
+#pragma unroll
+    for (int k = 0; k < KV; ++k) if (t + k * NT < MAXV * SB) { inp[IN_DQ * SB + t + k * NT] = vdq[k]; inp[IN_DDQ * SB + t + k * NT] = vddq[k]; }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (t + k * NT < MAXD * SB) inp[IN_TAU * SB + t + k * NT] = vtau[k];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) if (t + k * NT < MAXEE * SB) inp[IN_CNT * SB + t + k * NT] = vcnt[k];
+    if (t < SB) inp[IN_WGT * SB + t] = w;
 }
 
 // ---------------------------------------------------------------------------------------------- sincos
@@ -273,7 +295,7 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
 // ---------------------------------------------------------------------------------------------- feet
 // Thread per (sample, stance slot, e): e < MAXCH -> leg column e of the slot's contact Jacobian rows,
 // e == MAXCH -> the slot's world-aligned lever arm and the stance bookkeeping.
-template <int SB>
+template <int SB, int JLOFF = CX_P + 78>
 __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
                                            double* __restrict__ ctx, double* __restrict__ scr, int t) {
     if (t >= SB * MAXEE * (MAXCH + 1)) return;
@@ -323,7 +345,7 @@ __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, lo
     const double bx = rf[0] - X[9], by = rf[1] - X[10], bz = rf[2] - X[11];
     const double a0 = Rb[0] * ax0 + Rb[1] * ax1 + Rb[2] * ax2, a1 = Rb[3] * ax0 + Rb[4] * ax1 + Rb[5] * ax2, a2 = Rb[6] * ax0 + Rb[7] * ax1 + Rb[8] * ax2;
     const double dx = Rb[0] * bx + Rb[1] * by + Rb[2] * bz, dy = Rb[3] * bx + Rb[4] * by + Rb[5] * bz, dz = Rb[6] * bx + Rb[7] * by + Rb[8] * bz;
-    double* jl = c + CXT_JL + 3 * (slot * MAXCH + e);
+    double* jl = c + JLOFF + 3 * (slot * MAXCH + e);      // CXT_JL unless the caller keeps the leg columns elsewhere
     jl[0] = a1 * dz - a2 * dy;
     jl[1] = a2 * dx - a0 * dz;
     jl[2] = a0 * dy - a1 * dx;

@@ -13,6 +13,7 @@
 
 #include "../../include/sysid_b200.h"
 #include "gram_kernels.cuh"
+#include "gram_struct.cuh"
 #include "sdp_kernels.cuh"
 #include "filter_kernels.cuh"
 #include "bigmodel.cuh"
@@ -100,6 +101,96 @@ SampleIO make_io(const double* q, const double* dq, const double* ddq, const dou
     SampleIO io;
     io.q = q; io.dq = dq; io.ddq = ddq; io.tau = tau; io.cnt = cnt; io.weights = w; io.ld = ld;
     return io;
+}
+
+// Does the structured-basis Gram kernel (gram_struct.cuh) serve this tree?  Every child of the root must head a simple chain
+// with consecutive joint numbers, at most one contact frame per chain (three or more joints from the root), at most four chains,
+// and the chains must split into two column classes of at most six joints.  Fills the st_* plan of the model image.
+void plan_struct_basis(DevModel& M) {
+    M.st_ok = 0;
+    if (M.nfch < 1 || M.nfch > ST_MAXLEG) return;
+    int total = 0;
+    for (int c = 0; c < M.nfch; ++c) {
+        if (M.fch_own[c] != 0 || M.parent[M.fch[c][0]] != 1) return;
+        for (int e = 1; e < M.fch_len[c]; ++e) if (M.fch[c][e] != M.fch[c][0] + e || M.parent[M.fch[c][e]] != M.fch[c][e - 1]) return;
+        total += M.fch_len[c];
+        M.st_cfoot[c] = -1;
+    }
+    if (total != M.nd) return;
+    int leg_of[MAXJ];
+    for (int j = 0; j < MAXJ; ++j) leg_of[j] = -1;
+    for (int c = 0; c < M.nfch; ++c) for (int e = 0; e < M.fch_len[c]; ++e) leg_of[M.fch[c][e]] = c;
+    for (int k = 0; k < M.n_ee; ++k) {
+        if (M.ee_joint[k] == 1) continue;                          // a frame on the root body: base part only
+        const int c = leg_of[M.ee_joint[k]];
+        if (c < 0 || M.st_cfoot[c] >= 0 || M.chain_len[k] < 3) return;
+        for (int e = 0; e < M.chain_len[k]; ++e) if (M.chain[k][e] != M.fch[c][0] + M.chain_len[k] - 1 - e) return;
+        M.st_cfoot[c] = (int8_t)k;
+    }
+    // two classes of at most six joints: the most balanced split
+    int best = -1, best_diff = 99;
+    for (int mask = 0; mask < (1 << M.nfch); ++mask) {
+        int nA = 0, nB = 0;
+        for (int c = 0; c < M.nfch; ++c) ((mask >> c) & 1 ? nB : nA) += M.fch_len[c];
+        if (nA > 6 || nB > 6) continue;
+        const int diff = nA > nB ? nA - nB : nB - nA;
+        if (diff < best_diff) { best_diff = diff; best = mask; }
+    }
+    if (best < 0) return;
+    int nslot[2] = {0, 0};
+    for (int X = 0; X < 2; ++X) for (int e = 0; e < 6; ++e) M.st_slotjoint[X][e] = -1;
+    for (int c = 0; c < M.nfch; ++c) {
+        const int X = (best >> c) & 1;
+        M.st_ccls[c] = (int8_t)X;
+        for (int e = 0; e < M.fch_len[c]; ++e) {
+            const int j = M.fch[c][e], slot = nslot[X]++;
+            M.st_slotjoint[X][slot] = (int8_t)j;
+            M.st_jrec[j] = (uint32_t)c | ((uint32_t)e << 2) | ((uint32_t)X << 5) | ((uint32_t)slot << 6) |
+                           ((uint32_t)(72 * X + 10 * slot) << 9) | ((uint32_t)(72 * X + 60 + slot) << 17);
+        }
+    }
+    M.st_nslot[0] = (int8_t)nslot[0]; M.st_nslot[1] = (int8_t)nslot[1];
+    { int nf = 0, ml = 0; for (int c = 0; c < M.nfch; ++c) { nf += M.st_cfoot[c] >= 0; if (M.fch_len[c] > ml) ml = M.fch_len[c]; } M.st_nred = (int8_t)(6 + 3 * nf); M.st_maxlen = (int8_t)ml; }
+    // warp tasks of the tile fill, heaviest first (cost ~ emit + walk length)
+    {
+        int code[32], cost[32], n = 0;
+        for (int j = 2; j < M.njoints; ++j) { code[n] = (0 << 4) | j; cost[n] = 20 + 3 * (int)((M.st_jrec[j] >> 2) & 7); ++n; }
+        code[n] = 1 << 4; cost[n] = 19; ++n;
+        for (int X = 0; X < 2; ++X)
+            for (int e = 0; e < nslot[X]; ++e) { code[n] = ((2 + X) << 4) | e; cost[n] = 8 + (int)((M.st_jrec[M.st_slotjoint[X][e]] >> 2) & 7) + (e == 0 ? 3 : 0); ++n; }
+        if (n > 32 || n > 2 * GRAM_WARPS) return;
+        for (int a = 0; a < n; ++a)
+            for (int b = a + 1; b < n; ++b)
+                if (cost[b] > cost[a]) { int tc = cost[a]; cost[a] = cost[b]; cost[b] = tc; tc = code[a]; code[a] = code[b]; code[b] = tc; }
+        M.st_ntask = (int8_t)n;
+        for (int a = 0; a < n; ++a) M.st_task[a] = (uint8_t)code[a];
+    }
+    M.st_ok = 1;
+}
+
+// column of the statistics (0 .. c, c = the torque column) -> column of the Gram tiles
+ColMap make_colmap(const DevModel& M, int friction, bool structured) {
+    ColMap cm;
+    for (int i = 0; i < CW; ++i) cm.p[i] = (uint8_t)i;
+    if (!structured) return cm;
+    const int np = M.nparams, nd = M.nd;
+    for (int col = 0; col < np; ++col) {
+        const int j = col / 10 + 1;
+        cm.p[col] = (uint8_t)((j == 1 ? ST_ROOTCOL : (int)((M.st_jrec[j] >> 9) & 255)) + col % 10);
+    }
+    int c = np;
+    if (friction) {
+        for (int k = 0; k < nd; ++k) { cm.p[np + k] = (uint8_t)((M.st_jrec[k + 2] >> 17) & 255); cm.p[np + nd + k] = (uint8_t)(((M.st_jrec[k + 2] >> 17) & 255) + 6); }
+        c = np + 2 * nd;
+    }
+    cm.p[c] = (uint8_t)ST_TAUCOL;
+    return cm;
+}
+
+// SYSID_GRAM_LEGACY=1 forces the unstructured kernel (A/B timing, parity of the two kernels against each other)
+bool use_struct(const sysid_model* model) {
+    static const bool legacy = [] { const char* e = std::getenv("SYSID_GRAM_LEGACY"); return e && e[0] == '1'; }();
+    return model->dev.st_ok && !legacy;
 }
 
 }  // namespace
@@ -290,6 +381,7 @@ int sysid_model_create(const sysid_tree_desc* d, sysid_model** out) {
             }
         }
     }
+    plan_struct_basis(M);
     int rc = device_sm_count(&m->sm_count);
     if (rc != SYSID_OK) { delete m; return rc; }
     *out = m;
@@ -466,24 +558,33 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     cudaStream_t st = (cudaStream_t)stream;
     if (model->big) return big_gram(model, make_io(q, dq, ddq, tau, contact, weights, ld), N, friction ? 1 : 0, stats, info, workspace, workspace_bytes, st);
     const DevModel& M = model->dev;
-    const long long nsb = (N + FSB - 1) / FSB;
+    const long long nsb = use_struct(model) ? (N + ST_SB - 1) / ST_SB : (N + FSB - 1) / FSB;
     static const int debug_reserve = [] { const char* e = std::getenv("SYSID_DEBUG_RESERVE_SMS"); return e ? std::atoi(e) : 0; }();   // diagnostic
     if (debug_reserve > reserve_sms) reserve_sms = debug_reserve;
     const int max_ctas = (model->sm_count - reserve_sms > 1) ? model->sm_count - reserve_sms : 1;
     const int grid = (int)(nsb < max_ctas ? nsb : max_ctas);
     if (workspace_bytes < sizeof(double) * (size_t)grid * PARTIAL_DOUBLES)
         return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, sizeof(double) * (size_t)grid * PARTIAL_DOUBLES);
-    int rc = opt_in_smem(gram_fused_kernel<false>, GRAM_SMEM_BYTES);
-    if (rc) return rc;
+    const bool structured = use_struct(model);
+    static const bool debug_kernel = std::getenv("SYSID_DEBUG_KERNEL") != nullptr;
+    if (debug_kernel) fprintf(stderr, "[sysid] gram kernel: %s (st_ok %d)\n", structured ? "structured" : "unstructured", (int)model->dev.st_ok);
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, weights, ld);
     a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = 0;
-    gram_fused_kernel<false><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    if (structured) {
+        int rc = opt_in_smem(gram_struct_kernel<false>, ST_SMEM_BYTES);
+        if (rc) return rc;
+        gram_struct_kernel<false><<<grid, GRAM_THREADS, ST_SMEM_BYTES, st>>>(M, a);
+    } else {
+        int rc = opt_in_smem(gram_fused_kernel<false>, GRAM_SMEM_BYTES);
+        if (rc) return rc;
+        gram_fused_kernel<false><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    }
     CUDA_TRY(cudaGetLastError());
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
     const int total = (c + 1) * (c + 2) / 2;
     gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, (double)M.nv, 0.0, stats,
-                                                             (long long*)info);
+                                                             (long long*)info, make_colmap(M, friction ? 1 : 0, structured));
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
 }
@@ -512,13 +613,20 @@ int sysid_gram_blocks(const sysid_model* model, const double* q, const double* d
     const long long nseg = (N + block - 1) / block;
     if (workspace_bytes < sysid_gram_blocks_workspace_bytes(model, N, block)) return fail(SYSID_ERR_WORKSPACE, "workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = opt_in_smem(gram_fused_kernel<true>, GRAM_SMEM_BYTES);
-    if (rc) return rc;
+    const bool structured = use_struct(model);
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
     a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = block;
     const int grid = (int)(nseg < model->sm_count ? nseg : model->sm_count);
-    gram_fused_kernel<true><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    if (structured) {
+        int rc = opt_in_smem(gram_struct_kernel<true>, ST_SMEM_BYTES);
+        if (rc) return rc;
+        gram_struct_kernel<true><<<grid, GRAM_THREADS, ST_SMEM_BYTES, st>>>(M, a);
+    } else {
+        int rc = opt_in_smem(gram_fused_kernel<true>, GRAM_SMEM_BYTES);
+        if (rc) return rc;
+        gram_fused_kernel<true><<<grid, GRAM_THREADS, GRAM_SMEM_BYTES, st>>>(M, a);
+    }
     CUDA_TRY(cudaGetLastError());
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
     const int total = (c + 1) * (c + 2) / 2;
@@ -526,7 +634,8 @@ int sysid_gram_blocks(const sysid_model* model, const double* q, const double* d
     for (long long y0 = 0; y0 < nseg; y0 += 65535) {
         const unsigned ny = (unsigned)((nseg - y0 < 65535) ? (nseg - y0) : 65535);
         gram_reduce_kernel<<<dim3((total + 255) / 256, ny), 256, 0, st>>>((const double*)workspace + (size_t)y0 * PARTIAL_DOUBLES, 1, c, (double)M.nv, 0.0,
-                                                                        stats_blocks + (size_t)y0 * stats_stride, (long long*)info, (long long)stats_stride);
+                                                                        stats_blocks + (size_t)y0 * stats_stride, (long long*)info,
+                                                                        make_colmap(M, friction ? 1 : 0, structured), (long long)stats_stride);
         CUDA_TRY(cudaGetLastError());
     }
     return SYSID_OK;
@@ -642,8 +751,9 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
         if (want > chunk) want = chunk;
         // whole waves: every persistent CTA of the launch gets the same number of super-batches (no tail of one super-batch, which
         // at 37 super-batches per CTA is 2.7 % of the launch)
-        const int64_t wave = (int64_t)FSB * (model->sm_count - (presolve_running ? 1 : 0));
-        int64_t take = (want >= 8 * wave) ? want - want % wave : want - want % FSB;
+        const int64_t sbs = use_struct(model) ? ST_SB : FSB;       // samples per super-batch of the kernel that will run
+        const int64_t wave = sbs * (model->sm_count - (presolve_running ? 1 : 0));
+        int64_t take = (want >= 8 * wave) ? want - want % wave : want - want % sbs;
         if (take <= 0) take = want;
         const int64_t n = (N - lo < take) ? (N - lo) : take;
         if (k >= 2) HOST_TRY(cudaStreamWaitEvent(cp, consumed[b], 0));
@@ -731,7 +841,7 @@ int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_
     gram_stack_kernel<<<grid, GRAM_THREADS, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     const int total = (c + 1) * (c + 2) / 2;
-    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, 0.0, (double)rows, stats, nullptr);
+    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, 0.0, (double)rows, stats, nullptr, make_colmap(DevModel{}, 0, false));
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
 }
