@@ -26,6 +26,12 @@ namespace sysid {
 #include "gram_tiles_struct.inc"
 static_assert(STILES_MAX_NT == 14, "tensor-memory parking moves 56 registers per thread");
 
+// k-steps of the M loops are NOT unrolled: the sixteen per-warp code variants are re-fetched every round (measured on the 1 M-sample
+// G1 log: unroll 1 / 2 / 4 = 64.6 / 61.6 / 50.9 Msamples/s)
+#ifndef SYSID_ST_MMA_UNROLL
+#define SYSID_ST_MMA_UNROLL 1
+#endif
+constexpr int ST_MMA_UNROLL = SYSID_ST_MMA_UNROLL;
 #ifndef SYSID_ST_SB
 #define SYSID_ST_SB 25
 #endif
@@ -182,6 +188,9 @@ __device__ __forceinline__ void phase_legqr(const DevModel& M, long long base, l
 // norms and elimination remainders are those of J_c, the leg parts having only been rotated).  Lane b assembles the base part of
 // its row; the leg part was written by phase_legqr.  Leaves rank in SC_META, the number of dense vectors in CX_NQ and the number
 // of stored sparse vectors in CX_NQ + 1.
+// The pivot loop is ROLLED: after pivot p every lane shifts its row one coordinate to the left, so the pivot coordinate is
+// always x[0] and the register array keeps static indices (unrolled over the pivots this phase was 30 KB of code that ran once
+// per super-batch, i.e. always from a cold instruction cache).
 template <int SB, int NRED>
 __device__ __forceinline__ void phase_qbuild_red(const DevModel& M, long long base, long long N, double* __restrict__ ctx,
                                                  double* __restrict__ scr, int* s_bad, int t) {
@@ -212,46 +221,49 @@ __device__ __forceinline__ void phase_qbuild_red(const DevModel& M, long long ba
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(full, mx, o));
     const double tol = 1e-13 * mx;
-    __syncwarp();
-    int cur = 0, rank = 0, dropped = 0;
-#pragma unroll
+    __syncwarp();                                            // every lane holds its row: the slots may now take reflectors
+    int cur = 0, rank = 0, dropped = 0;                      // uniform per half-warp
+#pragma unroll 1
     for (int p = 0; p < (MR < NRED ? MR : NRED); ++p) {
+        if (!__any_sync(full, cur < m3)) break;
+        // x[r] holds coordinate p + r of the lane's row (zeros past NRED - p).  Next row whose remainder is not negligible:
         bool found = false;
-        while (__any_sync(full, !found && cur < m3)) {
-            double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
 #pragma unroll
-            for (int r = p; r < NRED; ++r) { if (r % 3 == 0) t0 = fma(x[r], x[r], t0); else if (r % 3 == 1) t1 = fma(x[r], x[r], t1); else t2 = fma(x[r], x[r], t2); }
-            const double tail2 = __shfl_sync(full, t0 + t1 + t2, hbase + min(cur, 15));
+        for (int r = 0; r < NRED; ++r) { if (r % 3 == 0) t0 = fma(x[r], x[r], t0); else if (r % 3 == 1) t1 = fma(x[r], x[r], t1); else t2 = fma(x[r], x[r], t2); }
+        const double mytail2 = t0 + t1 + t2;
+        while (__any_sync(full, !found && cur < m3)) {
+            const double tail2 = __shfl_sync(full, mytail2, hbase + min(cur, 15));
             if (!found && cur < m3) {
                 if (tail2 > tol) found = true;
-                else { ++cur; dropped = 1; }
+                else { ++cur; dropped = 1; }                // dependent row: dropped (pinv semantics)
             }
         }
         if (__any_sync(full, found)) {
             double* vrow = sc + SC_WM + p * MAXV;
             if (found && b == cur) {
-                double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+                const double nt = mytail2 * rsqrt(mytail2);
+                const double alpha = (x[0] >= 0.0) ? nt : -nt;
+                const double inv = rsqrt(2.0 * (mytail2 + fabs(x[0]) * nt));       // 1 / |x + alpha e_0|
+                for (int r = 0; r < p; ++r) vrow[r] = 0.0;
 #pragma unroll
-                for (int r = p; r < NRED; ++r) { if (r % 3 == 0) t0 = fma(x[r], x[r], t0); else if (r % 3 == 1) t1 = fma(x[r], x[r], t1); else t2 = fma(x[r], x[r], t2); }
-                const double tail2 = t0 + t1 + t2;
-                const double nt = tail2 * rsqrt(tail2);
-                const double alpha = (x[p] >= 0.0) ? nt : -nt;
-                const double inv = rsqrt(2.0 * (tail2 + fabs(x[p]) * nt));
-#pragma unroll
-                for (int r = 0; r < NRED; ++r) vrow[r] = (r < p) ? 0.0 : ((r == p) ? (x[r] + alpha) * inv : x[r] * inv);
+                for (int r = 0; r < NRED; ++r) if (p + r < NRED) vrow[p + r] = (r == 0) ? (x[0] + alpha) * inv : x[r] * inv;
             }
             __syncwarp();
             if (found && b > cur && b < m3) {
-                const double2* v2 = reinterpret_cast<const double2*>(vrow);
                 double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                for (int r2 = p / 2; r2 < NRED / 2; ++r2) { const double2 q = v2[r2]; d0 = fma(q.x, x[2 * r2], d0); d1 = fma(q.y, x[2 * r2 + 1], d1); }
+                for (int r = 0; r < NRED; ++r) { const double q = (p + r < NRED) ? vrow[p + r] : 0.0; if (r & 1) d1 = fma(q, x[r], d1); else d0 = fma(q, x[r], d0); }
                 const double d = -2.0 * (d0 + d1);
 #pragma unroll
-                for (int r2 = p / 2; r2 < NRED / 2; ++r2) { const double2 q = v2[r2]; x[2 * r2] = fma(d, q.x, x[2 * r2]); x[2 * r2 + 1] = fma(d, q.y, x[2 * r2 + 1]); }
+                for (int r = 0; r < NRED; ++r) { const double q = (p + r < NRED) ? vrow[p + r] : 0.0; x[r] = fma(d, q, x[r]); }
             }
             if (found) { ++cur; ++rank; }
         }
+        // coordinate p is done for every remaining row
+#pragma unroll
+        for (int r = 0; r + 1 < NRED; ++r) x[r] = x[r + 1];
+        x[NRED - 1] = 0.0;
     }
     if (b == 0 && s < SB) {
         int nd = 0, nsv = 0;
@@ -341,7 +353,7 @@ __device__ __forceinline__ void phase_rowdesc(const DevModel& M, long long base,
         nd = (int)c[CX_NQ]; nsvtot = (int)c[CX_NQ + 1];
         for (int sl = 0; sl < MAXEE; ++sl) { const int kf = (int)sc[SC_META + 1 + sl]; if (kf >= 0) stmask |= 1 << kf; }
     }
-    int nsv[ST_MAXLEG], nun[ST_MAXLEG], sb[ST_MAXLEG], us[ST_MAXLEG], nX[2] = {0, 0};
+    int nsv[ST_MAXLEG], nun[ST_MAXLEG], sb[ST_MAXLEG], us[ST_MAXLEG], nA = 0, nB = 0;      // static indices only: registers
 #pragma unroll
     for (int leg = 0; leg < ST_MAXLEG; ++leg) {
         nsv[leg] = 0; nun[leg] = 0; sb[leg] = 0; us[leg] = 0;
@@ -354,29 +366,31 @@ __device__ __forceinline__ void phase_rowdesc(const DevModel& M, long long base,
                 nsv[leg] = ln - 3; nun[leg] = flen - ln; us[leg] = ln;
                 for (int k2 = 0; k2 < MAXEE; ++k2) if (k2 < kf && ((stmask >> k2) & 1) && M.chain_len[k2] > 0) sb[leg] += M.chain_len[k2] - 3;
             } else nun[leg] = flen;
-            nX[M.st_ccls[leg]] += nsv[leg] + nun[leg];
+            if (M.st_ccls[leg]) nB += nsv[leg] + nun[leg]; else nA += nsv[leg] + nun[leg];
         }
     }
     // exclusive prefix inside the round (ST_TS consecutive lanes)
-    int v[3] = {nd, nX[0], nX[1]}, ex[3], tot[3];
+    int incD = nd, incA = nA, incB = nB;
 #pragma unroll
-    for (int q = 0; q < 3; ++q) {
-        int inc = v[q];
-#pragma unroll
-        for (int k = 1; k < ST_TS; ++k) { const int up = __shfl_up_sync(full, v[q], k); if (lane % ST_TS >= k) inc += up; }
-        ex[q] = inc - v[q]; tot[q] = inc;
+    for (int k = 1; k < ST_TS; ++k) {
+        const int uD = __shfl_up_sync(full, nd, k), uA = __shfl_up_sync(full, nA, k), uB = __shfl_up_sync(full, nB, k);
+        if (lane % ST_TS >= k) { incD += uD; incA += uA; incB += uB; }
     }
     if (s >= SB) return;
     const int rd = s / ST_TS;
-    if (lane % ST_TS == ST_TS - 1) { cnt[rd][0] = tot[0]; cnt[rd][1] = tot[1]; cnt[rd][2] = tot[2]; }
-    for (int k = 0; k < nd; ++k) descD[rd][ex[0] + k] = st_desc(s, nsvtot + k);
-    int o[2] = {ex[1], ex[2]};
+    if (lane % ST_TS == ST_TS - 1) { cnt[rd][0] = incD; cnt[rd][1] = incA; cnt[rd][2] = incB; }
+    const int exD = incD - nd;
+    for (int k = 0; k < nd; ++k) descD[rd][exD + k] = st_desc(s, nsvtot + k);
+    int oA = incA - nA, oB = incB - nB;
 #pragma unroll
     for (int leg = 0; leg < ST_MAXLEG; ++leg) {
         if (leg < M.nfch) {
             const int X = M.st_ccls[leg];
-            for (int i = 0; i < nsv[leg]; ++i) descS[X][rd][o[X]++] = st_desc(s, sb[leg] + i);
-            for (int i = 0; i < nun[leg]; ++i) descS[X][rd][o[X]++] = st_desc(s, 16 + M.fch[leg][0] - 2 + us[leg] + i);
+            int o = X ? oB : oA;
+            uint32_t* dst = descS[X][rd];
+            for (int i = 0; i < nsv[leg]; ++i) dst[o++] = st_desc(s, sb[leg] + i);
+            for (int i = 0; i < nun[leg]; ++i) dst[o++] = st_desc(s, 16 + M.fch[leg][0] - 2 + us[leg] + i);
+            if (X) oB = o; else oA = o;
         }
     }
 }
@@ -496,7 +510,7 @@ __device__ __forceinline__ void st_mma_warp(const double* __restrict__ tileD, in
     using T = STiles<W>;
     {
         const double* base = tileD + (lane & 3) * TILE_LD + (lane >> 2);
-#pragma unroll MMA_UNROLL
+#pragma unroll ST_MMA_UNROLL
         for (int ks = 0; ks < ksD; ++ks) {
             double frag[T::NG];
 #pragma unroll
@@ -507,7 +521,7 @@ __device__ __forceinline__ void st_mma_warp(const double* __restrict__ tileD, in
     }
     if constexpr (T::NTA > 0) {
         const double* base = tileA + (lane & 3) * ST_SLD + (lane >> 2);
-#pragma unroll 2
+#pragma unroll ST_MMA_UNROLL
         for (int ks = 0; ks < ksA; ++ks) {
             double frag[T::NGA];
 #pragma unroll
@@ -518,7 +532,7 @@ __device__ __forceinline__ void st_mma_warp(const double* __restrict__ tileD, in
     }
     if constexpr (T::NTB > 0) {
         const double* base = tileB + (lane & 3) * ST_SLD + (lane >> 2);
-#pragma unroll 2
+#pragma unroll ST_MMA_UNROLL
         for (int ks = 0; ks < ksB; ++ks) {
             double frag[T::NGB];
 #pragma unroll
