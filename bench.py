@@ -46,7 +46,7 @@ def parse():
     return ap.parse_args()
 
 
-KERNEL_SOURCES = ("gram_kernels.cuh", "phases.cuh", "tmem_park.cuh", "gram_tiles.inc")
+KERNEL_SOURCES = ("gram_struct.cuh", "gram_tiles_struct.inc", "gram_kernels.cuh", "phases.cuh", "tmem_park.cuh", "gram_tiles.inc")
 
 
 def kernel_source_stamp():

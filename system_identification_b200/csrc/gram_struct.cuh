@@ -413,8 +413,7 @@ __device__ __forceinline__ void st_emit(const double* __restrict__ c, int j, con
 // A WARP takes one task = one body for all rows of a tile (lane = row): the pose, body motion and Pluecker axes of a sample are
 // then read by all of its rows at once (shared-memory broadcast) and the walk down the leg is warp-uniform.  Every row -- dense,
 // stored sparse or unit vector (a row of the identity table `unit`) -- is a coefficient vector of 18 numbers, so ONE straight-line
-// code path serves them all: the walk runs MAXLEN joints with the coefficients beyond the body's depth masked to zero (all its
-// loads are independent and issued up front), a unit vector simply multiplies zeros.  Tasks (M.st_task, sorted by cost on the
+// code path serves them all: the walk is unrolled to MAXLEN joints behind warp-uniform guards, a unit vector simply multiplies zeros.  Tasks (M.st_task, sorted by cost on the
 // host): kind 0 dense rows x joint body; 1 dense rows x (root body, torque column, padding); 2 / 3 class rows x class slot (slot 0
 // also writes the row's torque block).  Warp w takes tasks w and 2 NW - 1 - w of the sorted list (heavy with light).
 template <int NT, int MAXLEN>
@@ -476,12 +475,12 @@ __device__ __forceinline__ void phase_fill_struct(const DevModel& M, const doubl
         for (int cc = 0; cc < 6; ++cc) d[cc] = Qk[cc] * wsq;
 #pragma unroll
         for (int e2 = 0; e2 < MAXLEN; ++e2) {
-            const int je = (e2 <= pos) ? jf + e2 : j;               // beyond the body's depth: a valid address, coefficient 0
-            const double cf = (e2 <= pos) ? Qk[4 + je] * wsq : 0.0;
-            if (e2 == pos) pj = cf;
-            const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (je - 2));
+            if (e2 <= pos) {                                        // warp-uniform: joints beyond the body's depth are skipped
+                pj = Qk[4 + jf + e2] * wsq;
+                const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (jf + e2 - 2));
 #pragma unroll
-            for (int cc = 0; cc < 3; ++cc) { const double2 ak = A2[cc]; d[2 * cc] = fma(cf, ak.x, d[2 * cc]); d[2 * cc + 1] = fma(cf, ak.y, d[2 * cc + 1]); }
+                for (int cc = 0; cc < 3; ++cc) { const double2 ak = A2[cc]; d[2 * cc] = fma(pj, ak.x, d[2 * cc]); d[2 * cc + 1] = fma(pj, ak.y, d[2 * cc + 1]); }
+            }
         }
         st_emit(c, j, d, row + bcol);
         const double dv = c[CX_DQ + j - 2];

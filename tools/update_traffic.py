@@ -4,8 +4,9 @@
     ncu -i gpurun_out/gram_fused_r02.ncu-rep --page raw --csv > gpurun_out/raw_r02.csv
     python tools/update_traffic.py gpurun_out/raw_r02.csv 1000000
 
-The JSON carries a content stamp of the kernel sources (sha256 of csrc/gram_kernels.cuh, phases.cuh, tmem_park.cuh,
-gram_tiles.inc) and the git sha of HEAD: bench.py reports the traffic only while the stamp matches the tree it runs from."""
+The dominant kernel of the benchmarked configuration is gram_struct_kernel (G1-12dof is a legged tree); gram_fused_kernel is matched
+for captures of the unstructured path.  The JSON carries a content stamp of the kernel sources (bench.KERNEL_SOURCES) and the git
+sha of HEAD: bench.py reports the traffic only while the stamp matches the tree it runs from."""
 import csv
 import json
 import os
@@ -24,17 +25,18 @@ def main():
     hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     names, units = rows[hdr], rows[hdr + 1]
     kcol = names.index("Kernel Name")
-    body = [r for r in rows[hdr + 2:] if len(r) == len(names) and "gram_fused" in r[kcol]]
+    body = [r for r in rows[hdr + 2:] if len(r) == len(names) and ("gram_struct" in r[kcol] or "gram_fused" in r[kcol])]
     if not body:
-        raise SystemExit("no gram_fused_kernel launch in " + path)
+        raise SystemExit("no gram_struct_kernel / gram_fused_kernel launch in " + path)
     r = body[-1]
+    kernel = "gram_struct_kernel" if "gram_struct" in r[kcol] else "gram_fused_kernel"
 
     def metric(name):
         i = names.index(name)
         return float(r[i].replace(",", "")) * UNIT.get(units[i], 1.0)
     from bench import kernel_source_stamp
     sha = subprocess.run(["git", "rev-parse", "--short", "HEAD"], cwd=ROOT, capture_output=True, text=True).stdout.strip()
-    out = {"kernel": "gram_fused_kernel", "samples_per_launch": samples,
+    out = {"kernel": kernel, "samples_per_launch": samples,
            "dram_bytes_read": int(metric("dram__bytes_read.sum")), "dram_bytes_write": int(metric("dram__bytes_write.sum")),
            "gpu_time_ms": metric("gpu__time_duration.sum") / (1e6 if units[names.index("gpu__time_duration.sum")] in ("nsecond", "ns") else 1.0),
            "source_stamp": kernel_source_stamp(), "git_sha": sha,
