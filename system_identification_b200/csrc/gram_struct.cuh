@@ -191,12 +191,14 @@ __device__ __forceinline__ void phase_legqr(const DevModel& M, long long base, l
 // The pivot loop is ROLLED: after pivot p every lane shifts its row one coordinate to the left, so the pivot coordinate is
 // always x[0] and the register array keeps static indices (unrolled over the pivots this phase was 30 KB of code that ran once
 // per super-batch, i.e. always from a cold instruction cache).
-template <int SB, int NRED>
+// LPS lanes per sample (lane b holds contact row b): 16 in general, 8 for a model with at most two contact frames (four samples
+// per warp: the phase is issue-bound, every lane of a warp pays for the rows of the others).
+template <int SB, int NRED, int LPS>
 __device__ __forceinline__ void phase_qbuild_red(const DevModel& M, long long base, long long N, double* __restrict__ ctx,
                                                  double* __restrict__ scr, int* s_bad, int t) {
-    constexpr int MR = 3 * MAXEE;
+    constexpr int MR = (3 * MAXEE < LPS) ? 3 * MAXEE : LPS;
     const unsigned full = 0xffffffffu;
-    const int s = t >> 4, b = t & 15, hbase = threadIdx.x & 16;
+    const int s = t / LPS, b = t % LPS, hbase = threadIdx.x & 31 & ~(LPS - 1);
     const bool live = (s < SB) && (base + s < N);
     double* sc = scr + (live ? s : 0) * SC_STRIDE;
     const int m3 = live ? (int)sc[SC_META] : 0;
@@ -219,10 +221,10 @@ __device__ __forceinline__ void phase_qbuild_red(const DevModel& M, long long ba
     }
     double mx = n2;
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(full, mx, o));
+    for (int o = LPS / 2; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(full, mx, o));
     const double tol = 1e-13 * mx;
     __syncwarp();                                            // every lane holds its row: the slots may now take reflectors
-    int cur = 0, rank = 0, dropped = 0;                      // uniform per half-warp
+    int cur = 0, rank = 0, dropped = 0;                      // uniform per sample (LPS lanes)
 #pragma unroll 1
     for (int p = 0; p < (MR < NRED ? MR : NRED); ++p) {
         if (!__any_sync(full, cur < m3)) break;
@@ -233,7 +235,7 @@ __device__ __forceinline__ void phase_qbuild_red(const DevModel& M, long long ba
         for (int r = 0; r < NRED; ++r) { if (r % 3 == 0) t0 = fma(x[r], x[r], t0); else if (r % 3 == 1) t1 = fma(x[r], x[r], t1); else t2 = fma(x[r], x[r], t2); }
         const double mytail2 = t0 + t1 + t2;
         while (__any_sync(full, !found && cur < m3)) {
-            const double tail2 = __shfl_sync(full, mytail2, hbase + min(cur, 15));
+            const double tail2 = __shfl_sync(full, mytail2, hbase + min(cur, LPS - 1));
             if (!found && cur < m3) {
                 if (tail2 > tol) found = true;
                 else { ++cur; dropped = 1; }                // dependent row: dropped (pinv semantics)
@@ -351,7 +353,7 @@ __device__ __forceinline__ void phase_rowdesc(const DevModel& M, long long base,
     int nd = 0, nsvtot = 0, stmask = 0;
     if (live) {
         nd = (int)c[CX_NQ]; nsvtot = (int)c[CX_NQ + 1];
-        for (int sl = 0; sl < MAXEE; ++sl) { const int kf = (int)sc[SC_META + 1 + sl]; if (kf >= 0) stmask |= 1 << kf; }
+        for (int sl = 0; sl < M.n_ee; ++sl) { const int kf = (int)sc[SC_META + 1 + sl]; if (kf >= 0) stmask |= 1 << kf; }
     }
     int nsv[ST_MAXLEG], nun[ST_MAXLEG], sb[ST_MAXLEG], us[ST_MAXLEG], nA = 0, nB = 0;      // static indices only: registers
 #pragma unroll
@@ -623,8 +625,9 @@ gram_struct_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         for (int it = t; it < ST_SB * ST_MAXLEG * MAXCH; it += GRAM_THREADS) phase_legqr<ST_SB>(M, base, Nlim, ctx, scr, inp, it);
         __syncthreads();
         F_TICK(4)
-        if (nred12) { for (int it = t; it < ((16 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, 12>(M, base, Nlim, ctx, scr, s_bad, it); }
-        else { for (int it = t; it < ((16 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, MAXV>(M, base, Nlim, ctx, scr, s_bad, it); }
+        if (nred12 && M.n_ee <= 2) { for (int it = t; it < ((8 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, 12, 8>(M, base, Nlim, ctx, scr, s_bad, it); }
+        else if (nred12) { for (int it = t; it < ((16 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, 12, 16>(M, base, Nlim, ctx, scr, s_bad, it); }
+        else { for (int it = t; it < ((16 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, MAXV, 16>(M, base, Nlim, ctx, scr, s_bad, it); }
         __syncthreads();
         F_TICK(3)
         if (warp == 0) phase_finish<ST_SB>(base, Nlim, inp, ctx, s_bad, t, s_stat);

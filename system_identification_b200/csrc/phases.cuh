@@ -298,8 +298,12 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
 template <int SB, int JLOFF = CX_P + 78>
 __device__ __forceinline__ void phase_feet(const DevModel& M, long long base, long long N, const double* __restrict__ inp,
                                            double* __restrict__ ctx, double* __restrict__ scr, int t) {
-    if (t >= SB * MAXEE * (MAXCH + 1)) return;
-    const int s = t % SB, u = t / SB, slot = u % MAXEE, e = u / MAXEE;
+    // stance slots beyond the model's contact frames do not exist: the items are dealt over n_ee slots, so that a biped's 350
+    // items fit one pass of 512 threads (nobody reads the slot table past n_ee)
+    const int nee = M.n_ee;
+    if (nee == 0) { if (t < SB) scr[t * SC_STRIDE + SC_META] = 0.0; return; }      // no contact frame: zero contact rows
+    if (t >= SB * nee * (MAXCH + 1)) return;
+    const int s = t % SB, u = t / SB, slot = u % nee, e = u / nee;
     if (base + s >= N) return;
     double* c = ctx + s * CX_STRIDE;
     double* sc = scr + s * SC_STRIDE;
