@@ -31,6 +31,13 @@ constexpr int SDP_MAXD = 12;
 constexpr int SDP_MAXC = 10 * SDP_MAXL + 2 * SDP_MAXD;     // 154
 constexpr int SDP_ROWS_PER_LINK = 22;                      // 10 (J) + 10 (C) + m>=0 + tr(JQ)>=0
 constexpr int SDP_MAXM = SDP_ROWS_PER_LINK * SDP_MAXL + 2 * SDP_MAXD;   // 310
+// Problems beyond that envelope (Unitree G1-29dof: L = 30, nd = 29, c = 358, m = 718) run the same kernel as the <BIG> instantiation:
+// the Newton matrix (c (c + 1) doubles, 1 MB) lives in the per-problem workspace (L2-resident) instead of shared memory, and the
+// factorisation / triangular solves are plain blocked loops of the whole thread block (chol_factor_big, chol_solve_big) instead of
+// the DMMA-fragment Cholesky tied to the 160-column tile tables.
+constexpr int SDP_BIG_MAXL = 32;
+constexpr int SDP_BIG_MAXD = 32;
+__host__ __device__ inline bool sdp_is_big(int L, int nd) { return L > SDP_MAXL || nd > SDP_MAXD; }
 constexpr int SDP_PLAN_LINK = 330;                         // doubles per link in the plan: M(100) Jmap(100) Cmap(100) q(10) Mphi0(10) phi0(10)
 constexpr int SDP_DEFAULT_MAX_ITERS = 1000;                 // Newton steps (the reference's default max_iters)
 constexpr int SDP_STATUS_INACCURATE = 1;                  // residuals within 1e3 x tolerance at the iteration cap (cvxpy's OPTIMAL_INACCURATE)
@@ -51,10 +58,14 @@ struct SdpParams {
 __host__ __device__ inline size_t sdp_warm_doubles(int L, int nd) {
     return (10 * (size_t)L + 2 * (size_t)nd) + ((size_t)L * SDP_ROWS_PER_LINK + 2 * (size_t)nd) + 4;   // + kernel start / end (globaltimer ns)
 }
-__host__ __device__ inline size_t sdp_ws_doubles(int L, int nd) {
+__host__ __device__ inline size_t sdp_ws_small_doubles(int L, int nd) {
     const size_t c = 10 * (size_t)L + 2 * (size_t)nd;
     return c * c + (size_t)L * SDP_ROWS_PER_LINK * 10 + (size_t)L * 100 + 2 * (size_t)nd + 16 +
            ((size_t)L * SDP_ROWS_PER_LINK + 2 * (size_t)nd);                               // + the row scales (warm start)
+}
+__host__ __device__ inline size_t sdp_ws_doubles(int L, int nd) {
+    const size_t c = 10 * (size_t)L + 2 * (size_t)nd;
+    return sdp_ws_small_doubles(L, nd) + (sdp_is_big(L, nd) ? c * (c + 1) : 0);             // large problems: + the Newton matrix
 }
 inline size_t sdp_plan_doubles(int L) { return (size_t)L * SDP_PLAN_LINK; }
 inline size_t sdp_workspace_bytes(int L, int nd) {
@@ -500,7 +511,120 @@ __device__ inline void chol_solve_warp(const double* A, int n, int ld, const dou
     for (int t = 0; t < SDP_SOLVE_T; ++t) { const int i = lane + 32 * t; if (i < n) x[i] = z[t]; }
 }
 
+// ---- large problems (BIG instantiation): A (n x n, lower triangle, leading dimension ld) in GLOBAL memory (L2-resident) -------------
+// Right-looking Cholesky blocked by 8 columns, the whole thread block: (1) the 8 x 8 diagonal block is factored by one thread in
+// shared memory; (2) one thread per row below forward-substitutes its eight panel entries (-> A and the shared panel buffer);
+// (3) warps take rows of the trailing matrix round-robin, lanes its columns: A[i][j] -= P[i] . P[j].  A keeps L (diagonal included),
+// invd[k] = 1 / L[k][k].  pbuf: 8 n + 80 doubles of shared memory.
+__device__ inline void chol_factor_big(double* A, int n, int ld, double* invd, double* pbuf, int tid) {
+    double* dblk = pbuf + 8 * (size_t)n;        // [8][8]
+    double* rinv = dblk + 64;                   // [8]
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int j0 = 0; j0 < n; j0 += 8) {
+        const int nb = (n - j0 < 8) ? n - j0 : 8;
+        if (tid < 64) {
+            const int r = tid >> 3, cc = tid & 7;
+            dblk[tid] = (r < nb && cc <= r) ? A[(size_t)(j0 + r) * ld + j0 + cc] : 0.0;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            for (int a = 0; a < nb; ++a) {
+                double d = dblk[8 * a + a];
+                for (int k = 0; k < a; ++k) d -= dblk[8 * a + k] * dblk[8 * a + k];
+                d = fmax(d, 1e-300);
+                const double ri = rsqrt(d);
+                dblk[8 * a + a] = d * ri; rinv[a] = ri;
+                for (int b = a + 1; b < nb; ++b) {
+                    double v = dblk[8 * b + a];
+                    for (int k = 0; k < a; ++k) v -= dblk[8 * b + k] * dblk[8 * a + k];
+                    dblk[8 * b + a] = v * ri;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid < 64) {
+            const int r = tid >> 3, cc = tid & 7;
+            if (r < nb && cc <= r) A[(size_t)(j0 + r) * ld + j0 + cc] = dblk[tid];
+        }
+        if (tid < nb) invd[j0 + tid] = rinv[tid];
+        for (int i = j0 + nb + tid; i < n; i += SDP_THREADS) {
+            double* Ai = A + (size_t)i * ld + j0;
+            double x[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) x[cc] = (cc < nb) ? Ai[cc] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) {
+                if (cc < nb) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) if (q < cc) x[cc] = fma(-x[q], dblk[8 * cc + q], x[cc]);
+                    x[cc] *= rinv[cc];
+                    Ai[cc] = x[cc];
+                }
+                pbuf[8 * (size_t)i + cc] = (cc < nb) ? x[cc] : 0.0;
+            }
+        }
+        __syncthreads();
+        for (int i = j0 + nb + warp; i < n; i += SDP_THREADS / 32) {
+            double pi[8];
+#pragma unroll
+            for (int cc = 0; cc < 8; ++cc) pi[cc] = pbuf[8 * (size_t)i + cc];
+            double* Ai = A + (size_t)i * ld;
+            for (int j = j0 + nb + lane; j <= i; j += 32) {
+                const double* pj = pbuf + 8 * (size_t)j;
+                double acc = Ai[j];
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) acc = fma(-pi[cc], pj[cc], acc);
+                Ai[j] = acc;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// x1 = (L L^T)^-1 b1, x2 = (L L^T)^-1 b2 in place (x1 / x2 hold b1 / b2 on entry), the whole thread block, blocked by 8: threads 0 / 1
+// solve the eight block unknowns of the two systems, then one thread per remaining row folds them in.
+__device__ inline void chol_solve_big(const double* A, int n, int ld, const double* invd, double* x1, double* x2, int tid) {
+    for (int j0 = 0; j0 < n; j0 += 8) {                          // forward: L z = b
+        const int nb = (n - j0 < 8) ? n - j0 : 8;
+        if (tid < 2) {
+            double* z = tid ? x2 : x1;
+            for (int a = 0; a < nb; ++a) {
+                double sacc = z[j0 + a];
+                for (int k = 0; k < a; ++k) sacc -= A[(size_t)(j0 + a) * ld + j0 + k] * z[j0 + k];
+                z[j0 + a] = sacc * invd[j0 + a];
+            }
+        }
+        __syncthreads();
+        for (int i = j0 + nb + tid; i < n; i += SDP_THREADS) {
+            const double* Ai = A + (size_t)i * ld + j0;
+            double s1 = x1[i], s2 = x2[i];
+            for (int cc = 0; cc < nb; ++cc) { const double l = Ai[cc]; s1 = fma(-l, x1[j0 + cc], s1); s2 = fma(-l, x2[j0 + cc], s2); }
+            x1[i] = s1; x2[i] = s2;
+        }
+        __syncthreads();
+    }
+    for (int j0 = ((n - 1) / 8) * 8; j0 >= 0; j0 -= 8) {          // backward: L^T x = z
+        const int nb = (n - j0 < 8) ? n - j0 : 8;
+        if (tid < 2) {
+            double* z = tid ? x2 : x1;
+            for (int a = nb - 1; a >= 0; --a) {
+                double sacc = z[j0 + a];
+                for (int k = a + 1; k < nb; ++k) sacc -= A[(size_t)(j0 + k) * ld + j0 + a] * z[j0 + k];
+                z[j0 + a] = sacc * invd[j0 + a];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < j0; i += SDP_THREADS) {
+            double s1 = x1[i], s2 = x2[i];
+            for (int cc = 0; cc < nb; ++cc) { const double l = A[(size_t)(j0 + cc) * ld + i]; s1 = fma(-l, x1[j0 + cc], s1); s2 = fma(-l, x2[j0 + cc], s2); }
+            x1[i] = s1; x2[i] = s2;
+        }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ the solver
+template <bool BIG>
 __global__ void __launch_bounds__(SDP_THREADS, 1)
 sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const double* __restrict__ stats_all,
                 double* __restrict__ ws_all, double* __restrict__ x_out_all, sysid_sdp_info* __restrict__ info_all,
@@ -518,8 +642,8 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* rsig = tf + 2 * (size_t)nd + 16;           // m  scale of every constraint row (one per LMI block): multipliers <-> unscaled units
     // shared memory carve-up
     const int ldw = c + 1;                             // odd: conflict-free column access
-    double* W = sm;                                    // c*(c+1)  Newton matrix (lower triangle), Cholesky-factored in place
-    double* gt = W + c * ldw;                          // c   scaled linear term
+    double* W = BIG ? ws + sdp_ws_small_doubles(L, nd) : sm;   // c*(c+1)  Newton matrix (lower triangle), Cholesky-factored in place; BIG: global memory
+    double* gt = BIG ? sm : W + c * ldw;               // c   scaled linear term
     double* at = gt + c;                               // c   scaled equality vector
     double* y = at + c;                                // c
     double* yt = y + c;                                // c   trial point / K^-1 grad
@@ -540,7 +664,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* red = invd + c;                            // 32
     // 8 x TILE_LD panel buffer of the factorisation: aliases gy|wv|pw|tv|evals (all dead between the Newton-matrix set-up
     // and the next evaluate()) when they are large enough, else its own buffer behind `red` (small problems)
-    double* pan = (4 * m + 8 * L >= SDP_PAN_DOUBLES) ? gy : red + 32;
+    double* pan = BIG ? red + 32 : ((4 * m + 8 * L >= SDP_PAN_DOUBLES) ? gy : red + 32);      // BIG: the 8 c + 80 doubles of chol_factor_big
     __shared__ double s_scalar[8];
 
     unsigned long long t_start_ = 0;
@@ -713,9 +837,9 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     auto evaluate = [&](const double* yy) -> double {
         for (int r = tid; r < m; r += SDP_THREADS) { const double gv = apply_A(yy, r); gy[r] = gv; wv[r] = lam[r] - sigma * gv; }
         __syncthreads();
-        {   // 2L eigen-problems: lanes 0 and 1 of each warp work in lockstep on blocks `warp` and `warp + 16`
+        {   // 2L eigen-problems: lanes 0 and 1 (BIG: 0 .. 3) of each warp work in lockstep on blocks `warp`, `warp + 16`, ...
             const int k = warp + (SDP_THREADS / 32) * lane;
-            if (lane < 2 && k < 2 * L) {
+            if (lane < (BIG ? 4 : 2) && k < 2 * L) {
                 const int off = (k >> 1) * SDP_ROWS_PER_LINK + 10 * (k & 1);
                 double ev[4], V[16];
                 eig_sym4(wv + off, ev, V, warm ? evecs + 16 * k : nullptr);
@@ -811,11 +935,14 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             if (wv[L * SDP_ROWS_PER_LINK + k] > 0.0) W[(np + k) * ldw + np + k] += sigma;
         __syncthreads();
         SDP_TICK(5)
+        if constexpr (BIG) chol_factor_big(W, c, ldw, invd, pan, tid);
+        else {
 #ifdef SYSID_PHASE_CLOCKS
-        chol_factor_smem(W, c, ldw, invd, pan, tid, chk);
+            chol_factor_smem(W, c, ldw, invd, pan, tid, chk);
 #else
-        chol_factor_smem(W, c, ldw, invd, pan, tid);
+            chol_factor_smem(W, c, ldw, invd, pan, tid);
 #endif
+        }
     };
 
     auto dot_c = [&](const double* u, const double* v) -> double {
@@ -905,8 +1032,14 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             SDP_TICK(0)
             newton_matrix_factor();
             SDP_TICK(1)
-            if (warp == 0) chol_solve_warp(W, c, ldw, grad, yt, lane);        // yt = K^-1 grad
-            else if (warp == 1) chol_solve_warp(W, c, ldw, at, Ka, lane);     // Ka = K^-1 at
+            if constexpr (BIG) {
+                for (int a = tid; a < c; a += SDP_THREADS) { yt[a] = grad[a]; Ka[a] = at[a]; }
+                __syncthreads();
+                chol_solve_big(W, c, ldw, invd, yt, Ka, tid);                     // yt = K^-1 grad, Ka = K^-1 at
+            } else {
+                if (warp == 0) chol_solve_warp(W, c, ldw, grad, yt, lane);        // yt = K^-1 grad
+                else if (warp == 1) chol_solve_warp(W, c, ldw, at, Ka, lane);     // Ka = K^-1 at
+            }
             __syncthreads();
             SDP_TICK(2)
             const double a_v1 = dot_c(at, yt), a_Ka = dot_c(at, Ka);
@@ -1044,8 +1177,8 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
 inline size_t sdp_plan_total_doubles(int L) { return sdp_plan_doubles(L) + 4; }
 
 inline int sdp_check_desc(const sysid_sdp_desc& d, bool need_arrays, char* msg, size_t msglen) {
-    if (d.num_links < 1 || d.num_links > SDP_MAXL || d.ndof < 0 || d.ndof > SDP_MAXD) {
-        snprintf(msg, msglen, "num_links %d / ndof %d outside this build's envelope (%d / %d)", d.num_links, d.ndof, SDP_MAXL, SDP_MAXD);
+    if (d.num_links < 1 || d.num_links > SDP_BIG_MAXL || d.ndof < 0 || d.ndof > SDP_BIG_MAXD) {
+        snprintf(msg, msglen, "num_links %d / ndof %d outside this build's envelope (%d / %d)", d.num_links, d.ndof, SDP_BIG_MAXL, SDP_BIG_MAXD);
         return SYSID_ERR_UNSUPPORTED;
     }
     if (need_arrays && (!d.phi_prior || !d.semi_axes || !d.centers)) { snprintf(msg, msglen, "bad sdp descriptor"); return SYSID_ERR_INVALID; }
@@ -1094,11 +1227,16 @@ inline int sdp_solve_planned(const sysid_sdp_desc& d, const double* dplan, const
     static const int dbg_start = [] { const char* e = std::getenv("SYSID_SDP_START"); return e ? std::atoi(e) : 0; }();       // diagnostic
     static const int dbg_stall = [] { const char* e = std::getenv("SYSID_SDP_STALL_BREAK"); return e ? std::atoi(e) : 1; }();
     prm.start_mode = dbg_start; prm.stall_break = dbg_stall;
-    const size_t smem = sizeof(double) * ((size_t)prm.c * (prm.c + 1) + 10 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + 32 +
-                                         ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES));
-    cudaError_t e = cudaFuncSetAttribute(sdp_alm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool big = sdp_is_big(L, nd);
+    const size_t vec = 10 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + (size_t)prm.c + 32;
+    const size_t smem = big ? sizeof(double) * (vec + 8 * (size_t)prm.c + 80)
+                            : sizeof(double) * ((size_t)prm.c * (prm.c + 1) + vec - (size_t)prm.c +
+                                                ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES));
+    cudaError_t e = big ? cudaFuncSetAttribute(sdp_alm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(sdp_alm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { snprintf(msg, msglen, "smem opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
-    sdp_alm_kernel<<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, (double*)workspace, x_out, info_out, warm_in, warm_out);
+    if (big) sdp_alm_kernel<true><<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, (double*)workspace, x_out, info_out, warm_in, warm_out);
+    else sdp_alm_kernel<false><<<batch, SDP_THREADS, smem, st>>>(prm, dplan, stats, (double*)workspace, x_out, info_out, warm_in, warm_out);
     e = cudaGetLastError();
     if (e != cudaSuccess) { snprintf(msg, msglen, "sdp launch failed: %s", cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
     return SYSID_OK;

@@ -58,3 +58,28 @@ def test_g1_29dof_gram_and_rmse_vs_oracle_twin():
     assert abs(out[0] - tot_o) <= 1e-9 * tot_o and np.abs(out[1:] - pj_o).max() <= 1e-9 * pj_o.max()
     with pytest.raises(Exception):
         dm.gram_accumulate(*dev, weights=torch.ones(N, dtype=torch.float64, device="cuda"))   # not on the large-model path
+
+
+def test_g1_29dof_identify_vs_oracle():
+    """Stage 3 at c = 358 (30 links, 29 joints: 60 LMIs, 718 constraint rows): the large-problem instantiation of the LMI solver
+    against the oracle's solve of the oracle's own statistics, through identify() from host arrays."""
+    import sys
+    sys.path.insert(0, H.ROOT)
+    from oracle import sdp as osdp
+    from oracle.cbuild import COracle
+    from src.sys_identification import SystemIdentification
+    N, c = 4000, 358
+    flat, data, dm, dev = _setup(N, seed=9)
+    si = SystemIdentification.from_flat_model(flat)
+    phi, bv, bc, info = si.identify(*data, return_info=True)
+    assert info["status"] in (0, 1) and phi.shape == (300,) and bv.shape == (29,) and bc.shape == (29,)
+    co = COracle(H.oracle_tree(flat), flat.ee_names)
+    so, _ = co.gram(*data)
+    G, r, s, n = H.split_stats(so, c)
+    prob = osdp.build_problem(G, r, float(s), n, 30, flat.phi_prior, flat.robot_mass, flat.ellipsoids, 29)
+    xo, _ = osdp.solve_alm(prob)
+    x = np.concatenate([phi, bv, bc])
+    assert H.rel(x, xo) <= 1e-4
+    for i in range(30):
+        assert H.rel(phi[10 * i:10 * i + 10], xo[10 * i:10 * i + 10]) <= 1e-4
+    assert abs(phi[0::10].sum() - flat.robot_mass) <= 1e-8 * flat.robot_mass and bv.min() >= -1e-9 and bc.min() >= -1e-9
