@@ -505,41 +505,62 @@ __device__ __forceinline__ void phase_fill_struct(const DevModel& M, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------- M phase
+// k-steps are software-pipelined by hand (the fragments of k-step ks + 1 are loaded before the DMMAs of k-step ks issue, then moved)
+// instead of unrolled: unrolling doubles the sixteen per-warp code variants, which are re-fetched every round.
 template <int W>
 __device__ __forceinline__ void st_mma_warp(const double* __restrict__ tileD, int ksD, const double* __restrict__ tileA, int ksA,
                                             const double* __restrict__ tileB, int ksB, int lane, double (&acc)[STILES_MAX_NT][2]) {
     using T = STiles<W>;
-    {
+    if (ksD > 0) {
         const double* base = tileD + (lane & 3) * TILE_LD + (lane >> 2);
-#pragma unroll ST_MMA_UNROLL
-        for (int ks = 0; ks < ksD; ++ks) {
-            double frag[T::NG];
+        double frag[T::NG], nxt[T::NG];
 #pragma unroll
-            for (int g = 0; g < T::NG; ++g) frag[g] = base[ks * 4 * TILE_LD + 8 * T::G(g)];
+        for (int g = 0; g < T::NG; ++g) frag[g] = base[8 * T::G(g)];
+#pragma unroll 1
+        for (int ks = 0; ks < ksD; ++ks) {
+            const double* nb = base + (ks + 1 < ksD ? ks + 1 : ks) * 4 * TILE_LD;
+#pragma unroll
+            for (int g = 0; g < T::NG; ++g) nxt[g] = nb[8 * T::G(g)];
 #pragma unroll
             for (int t = 0; t < T::NT; ++t) dmma884(acc[t][0], acc[t][1], frag[T::IA(t)], frag[T::IB(t)]);
+#pragma unroll
+            for (int g = 0; g < T::NG; ++g) frag[g] = nxt[g];
         }
     }
     if constexpr (T::NTA > 0) {
-        const double* base = tileA + (lane & 3) * ST_SLD + (lane >> 2);
-#pragma unroll ST_MMA_UNROLL
-        for (int ks = 0; ks < ksA; ++ks) {
-            double frag[T::NGA];
+        if (ksA > 0) {
+            const double* base = tileA + (lane & 3) * ST_SLD + (lane >> 2);
+            double frag[T::NGA], nxt[T::NGA];
 #pragma unroll
-            for (int g = 0; g < T::NGA; ++g) frag[g] = base[ks * 4 * ST_SLD + 8 * T::GA(g)];
+            for (int g = 0; g < T::NGA; ++g) frag[g] = base[8 * T::GA(g)];
+#pragma unroll 1
+            for (int ks = 0; ks < ksA; ++ks) {
+                const double* nb = base + (ks + 1 < ksA ? ks + 1 : ks) * 4 * ST_SLD;
 #pragma unroll
-            for (int t = 0; t < T::NTA; ++t) dmma884(acc[T::TA(t)][0], acc[T::TA(t)][1], frag[T::IAA(t)], frag[T::IBA(t)]);
+                for (int g = 0; g < T::NGA; ++g) nxt[g] = nb[8 * T::GA(g)];
+#pragma unroll
+                for (int t = 0; t < T::NTA; ++t) dmma884(acc[T::TA(t)][0], acc[T::TA(t)][1], frag[T::IAA(t)], frag[T::IBA(t)]);
+#pragma unroll
+                for (int g = 0; g < T::NGA; ++g) frag[g] = nxt[g];
+            }
         }
     }
     if constexpr (T::NTB > 0) {
-        const double* base = tileB + (lane & 3) * ST_SLD + (lane >> 2);
-#pragma unroll ST_MMA_UNROLL
-        for (int ks = 0; ks < ksB; ++ks) {
-            double frag[T::NGB];
+        if (ksB > 0) {
+            const double* base = tileB + (lane & 3) * ST_SLD + (lane >> 2);
+            double frag[T::NGB], nxt[T::NGB];
 #pragma unroll
-            for (int g = 0; g < T::NGB; ++g) frag[g] = base[ks * 4 * ST_SLD + 8 * T::GB(g)];
+            for (int g = 0; g < T::NGB; ++g) frag[g] = base[8 * T::GB(g)];
+#pragma unroll 1
+            for (int ks = 0; ks < ksB; ++ks) {
+                const double* nb = base + (ks + 1 < ksB ? ks + 1 : ks) * 4 * ST_SLD;
 #pragma unroll
-            for (int t = 0; t < T::NTB; ++t) dmma884(acc[T::TB(t)][0], acc[T::TB(t)][1], frag[T::IAB(t)], frag[T::IBB(t)]);
+                for (int g = 0; g < T::NGB; ++g) nxt[g] = nb[8 * T::GB(g)];
+#pragma unroll
+                for (int t = 0; t < T::NTB; ++t) dmma884(acc[T::TB(t)][0], acc[T::TB(t)][1], frag[T::IAB(t)], frag[T::IBB(t)]);
+#pragma unroll
+                for (int g = 0; g < T::NGB; ++g) frag[g] = nxt[g];
+            }
         }
     }
 }
