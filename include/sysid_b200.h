@@ -295,7 +295,7 @@ int sysid_sdp_solve_plan(const sysid_sdp_desc* desc, const void* plan, const dou
  * are additive, so the fit of the first `samples` samples of the log is a point and a set of multipliers within the statistical
  * noise of the final fit: it is solved as ONE thread block on an internal stream while the remaining chunks are uploaded and
  * contracted (they leave it one SM), and its record (warm_out) warm-starts the final sysid_sdp_solve_plan, which then needs a
- * handful of Newton steps instead of ~55.  On return, work submitted to `stream` is ordered after the pre-solve.  Skipped (record
+ * handful of Newton steps instead of ~55 (fewer still with the second stage, refine_at).  On return, work submitted to `stream` is ordered after the pre-solve.  Skipped (record
  * left invalid) when the log is shorter than 2 * samples.  All pointers in the struct are DEVICE pointers except desc. */
 typedef struct sysid_presolve {
     const sysid_sdp_desc* desc;       /* host; scalars only */
@@ -306,6 +306,10 @@ typedef struct sysid_presolve {
     sysid_sdp_info* info_scratch;     /* one record */
     double* warm_out;                 /* sysid_sdp_warm_len doubles */
     int64_t samples;                  /* length of the first chunk (0 = `chunk`) */
+    int64_t refine_at;                /* > 0: once that many samples are in, a SECOND pre-solve of the statistics so far is queued behind
+                                         the first one, warm-started from it; its record replaces the first one's in warm_out.  Pays on
+                                         logs long enough to hide both (~1 M samples); 0 = one stage */
+    double* stats_snapshot2;          /* stats_len doubles (needed when refine_at > 0) */
 } sysid_presolve;
 int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* const* arrays_host, const int32_t* dtypes,
                                         const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,

@@ -25,17 +25,17 @@ using namespace sysid;
 // handle falls back to per-call resources.
 struct HostStreamRes {
     cudaStream_t s_copy = nullptr, s_solve = nullptr;
-    cudaEvent_t ev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copied[2], consumed[2], start, snap, solved
+    cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // copied[2], consumed[2], start, snap, solved, snap2
     bool ok = false;
     bool create() {
         if (cudaStreamCreateWithFlags(&s_copy, cudaStreamNonBlocking) != cudaSuccess) return false;
         if (cudaStreamCreateWithFlags(&s_solve, cudaStreamNonBlocking) != cudaSuccess) return false;
-        for (int i = 0; i < 7; ++i) if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        for (int i = 0; i < 8; ++i) if (cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) return false;
         ok = true;
         return true;
     }
     void destroy() {
-        for (int i = 0; i < 7; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
+        for (int i = 0; i < 8; ++i) if (ev[i]) cudaEventDestroy(ev[i]);
         if (s_copy) cudaStreamDestroy(s_copy);       // pending work completes first; the runtime releases the stream afterwards
         if (s_solve) cudaStreamDestroy(s_solve);
         *this = HostStreamRes();
@@ -693,6 +693,7 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
     if (!model || !arrays_host || !dtypes || !lds_host || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
     if (pre && (!pre->desc || !pre->plan || !pre->sdp_workspace || !pre->stats_snapshot || !pre->x_scratch || !pre->info_scratch || !pre->warm_out))
         return fail(SYSID_ERR_INVALID, "null presolve argument");
+    if (pre && pre->refine_at > 0 && !pre->stats_snapshot2) return fail(SYSID_ERR_INVALID, "refine_at needs stats_snapshot2");
     const DevModel& M = model->dev;
     const int channels[5] = {M.nq, M.nv, M.nv, M.nd, M.n_ee};
     for (int a = 0; a < 5; ++a) {
@@ -721,7 +722,7 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
     }
     cudaStream_t cp = R->s_copy, sv = R->s_solve;
     cudaEvent_t* copied = &R->ev[0]; cudaEvent_t* consumed = &R->ev[2];
-    cudaEvent_t start = R->ev[4], snap = R->ev[5], solved = R->ev[6];
+    cudaEvent_t start = R->ev[4], snap = R->ev[5], solved = R->ev[6], snap2 = R->ev[7];
     int rc = SYSID_OK;
     auto cleanup = [&]() { if (R == &local) local.destroy(); };
     // LMI pre-solve (optional): the statistics are additive, so the fit of the first pre->samples samples is a point (and a set
@@ -734,7 +735,7 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
         first = (pre->samples > 0 && pre->samples < chunk) ? pre->samples : chunk;
         presolve = (N >= 2 * first);
     }
-    bool presolve_running = false;
+    bool presolve_running = false, refined = false;
 #define HOST_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(SYSID_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
     if (pre) HOST_TRY(cudaMemsetAsync(pre->warm_out, 0, sizeof(double) * warm_n, st));      // "no record" until the pre-solve has written one
     // the staging buffers may still be read by earlier work on `stream`
@@ -800,6 +801,20 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
             if (rc != SYSID_OK) { fail(rc, "pre-solve: %s", msg); cleanup(); return rc; }
             HOST_TRY(cudaEventRecord(solved, sv));
             presolve_running = true;
+        } else if (presolve_running && !refined && pre->refine_at > 0 && lo + n >= pre->refine_at && lo + n < N) {
+            // second stage: the statistics so far, solved behind the first pre-solve (same internal stream) from its record; the
+            // record it leaves is the start of the final solve.  Same scratch buffers: the stream orders the two solves.
+            const size_t slen = sysid_stats_len(model, friction);
+            copy_f64_kernel<<<(unsigned)((slen + 255) / 256), 256, 0, st>>>(stats, pre->stats_snapshot2, (int64_t)slen);
+            HOST_TRY(cudaGetLastError());
+            HOST_TRY(cudaEventRecord(snap2, st));
+            HOST_TRY(cudaStreamWaitEvent(sv, snap2, 0));
+            char msg[256] = "";
+            rc = sdp_solve_planned(*pre->desc, (const double*)pre->plan, pre->stats_snapshot2, (int64_t)slen, 1, pre->x_scratch,
+                                   pre->info_scratch, pre->sdp_workspace, pre->sdp_workspace_bytes, pre->warm_out, pre->warm_out, sv, msg, sizeof(msg));
+            if (rc != SYSID_OK) { fail(rc, "pre-solve (second stage): %s", msg); cleanup(); return rc; }
+            HOST_TRY(cudaEventRecord(solved, sv));
+            refined = true;
         }
         lo += n;
     }

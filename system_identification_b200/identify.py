@@ -41,6 +41,16 @@ PRESOLVE_MIN_LOG = 600_000        # the pre-solve (a cold solve, ~9 ms) only pay
                                   # the first chunk of one shard is 6 % of the log and its fit a poorer start: 37 final Newton steps, not 23)
 
 
+# A SECOND pre-solve stage: the statistics of the first PRESOLVE_REFINE_FRACTION of the shard, solved behind the first stage and
+# warm-started from it; its record starts the final solve (13 Newton steps instead of 23 on the 1 M-sample G1 log: 18.6 instead of
+# 20.1 ms).  Only where the stream hides both stages -- ~1 + 9 + 4 ms of solves against 14 ms of statistics per 1 M samples; at a
+# fraction of 0.5 and more the chain overruns the stream and the final solve waits for it (tools/presolve_refine_study.py).
+PRESOLVE_REFINE_MIN_LOG = 900_000
+PRESOLVE_REFINE_FRACTION = 0.45
+PRESOLVE_TOL = None                # tolerance of the pre-solves (None: the final solve's; looser ones were measured: 1e-6 costs the final
+                                   # solve 7 more Newton steps, 1e-5 twenty)
+
+
 def _plan_for(sysid, L, nd, lambda_reg, tol, max_iters, reg_type):
     """Device plan of the LMI problem, built once per (prior, ellipsoids, mass, lambda, ...) and cached on the sysid object."""
     from .ops import SdpPlan
@@ -111,8 +121,9 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         # host float64 / float32 arrays: chunked upload overlapped with the kernel inside the library
         n0 = min(int(chunk), max(PRESOLVE_MIN_SAMPLES, n_loc // 8))
         use_pre = (presolve is True and n_loc >= PRESOLVE_MIN_LOG or presolve == "force") and plan is not None and n_loc >= 2 * n0
+        refine = int(PRESOLVE_REFINE_FRACTION * n_loc) if (use_pre and n_loc >= PRESOLVE_REFINE_MIN_LOG) else 0
         dm.gram_accumulate_host(*arrays, friction=friction, weights=weights, stats=stats, info=counts, chunk=chunk,
-                                presolve=plan if use_pre else None, presolve_samples=n0)
+                                presolve=plan if use_pre else None, presolve_samples=n0, presolve_refine_at=refine, presolve_tol=PRESOLVE_TOL)
         warm = plan.warm if use_pre else None
     else:
         dev = [a if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64) else to_device(a) for a in arrays]

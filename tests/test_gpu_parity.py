@@ -531,6 +531,15 @@ def test_presolve_warm_start_same_optimum_fewer_steps():
     for i in range(13):
         assert H.rel(phi_w[10 * i:10 * i + 10], phi_c[10 * i:10 * i + 10]) <= 1e-5
     assert info_w["iterations"] < info_c["iterations"]
+    # second pre-solve stage (statistics of the first 45 % of the log, warm-started from the first stage): same optimum again
+    import system_identification_b200.identify as idm
+    keep = idm.PRESOLVE_REFINE_MIN_LOG
+    try:
+        idm.PRESOLVE_REFINE_MIN_LOG = 0
+        phi_r, bv_r, bc_r, info_r = identify(si, *host, return_info=True, presolve="force", chunk=16384)
+    finally:
+        idm.PRESOLVE_REFINE_MIN_LOG = keep
+    assert info_r["status"] == 0 and H.rel(np.concatenate([phi_r, bv_r, bc_r]), xc) <= 1e-6 and info_r["iterations"] < info_c["iterations"]
     # plan-based solve == one-shot entry; garbage warm records are ignored
     st = dm.gram_accumulate(*_up((q, dq, ddq, tau, cnt)))
     plan = SdpPlan(13, 12, flat.phi_prior, flat.ellipsoids, flat.robot_mass)
