@@ -50,12 +50,10 @@ constexpr int ST_TILE_S = ST_SROWS * ST_SLD;
 constexpr int ST_FSCR = ST_SB * (SC_STRIDE + IN_CHANNELS);
 constexpr int ST_FRONT = (ST_TILE_D + 2 * ST_TILE_S > ST_FSCR) ? ST_TILE_D + 2 * ST_TILE_S : ST_FSCR;
 constexpr size_t ST_SMEM_BYTES = sizeof(double) * (ST_FRONT + ST_SB * CX_STRIDE);
-constexpr int ST_JL = CX_Q + 11 * QLD;            // leg columns of J_c (feet -> legqr): tail of the Q slot, clear of the stored vectors
 constexpr int ST_TAUCOL = 144, ST_ROOTCOL = 146;
 static_assert((GRAM_WARPS - 2) * 32 >= ST_SB * NQMAX, "qcols runs on warps 1 .. 14");
 static_assert(ST_SROWS <= 32 && ST_DROWS <= 32, "one lane per tile row in the fill");
 static_assert(ST_SB % ST_TS == 0 && ST_SB <= 32 && ST_SLD % 16 == 4 && ST_SMEM_BYTES + 6144 <= 232448, "layout");
-static_assert(ST_JL + 3 * MAXEE * MAXCH <= CX_W && 6 * QLD <= ST_JL, "leg columns fit behind the six stored sparse vectors");
 static_assert(IN_DDQ - IN_DQ + MAXV >= 3 * MAXD, "the dead dq / ddq channels hold the range coefficients of the legs");
 
 __device__ __forceinline__ int st_rec_leg(uint32_t r) { return r & 3; }
@@ -73,40 +71,66 @@ __device__ __forceinline__ const double* st_vector(uint32_t desc, const double* 
     return (qsel & 16) ? unit + (qsel & 15) * QLD : c + CX_Q + qsel * QLD;
 }
 
-// ---------------------------------------------------------------------------------------------- leg QR
-// Thread per (sample, leg, column i of Q_leg).  Stance leg: Householder QR of J_leg^T (len x 3, len = joints between the foot and
-// the root, 3..6), recomputed by each of the leg's column threads (150 flops; the alternative is one thread per leg running all
-// six columns one after the other while fifteen warps wait).  Column thread i < 3 writes the range coefficients [joint][i] into
-// dead input channels, i >= 3 the null vector i - 3 straight into the basis (rows sbase ..); thread 0 also writes T = J_leg Q_range
-// into the leg part of the slot's three rows of the reduced Jacobian (scratch rows, where qbuild_red expects them) and the joints'
-// reduced offset (-1: swing leg / joint beyond the foot).
+// ---------------------------------------------------------------------------------------------- feet + leg QR (one phase)
+// Items [0, SB n_ee): (sample, stance slot) -- the slot's contact frame, its world-aligned lever arm and the stance bookkeeping
+// (what phase_feet's e == MAXCH items do).  Items after that: (sample, leg, column i of Q_leg).  A column thread reads the
+// contact flags itself, forms the leg columns of its foot's contact-Jacobian rows (phase_feet's other items: here every column
+// thread forms all of them, 45 flops each, instead of waiting one barrier interval for them), then: stance leg: Householder QR of
+// J_leg^T (len x 3, len = joints between the foot and the root, 3..6), recomputed by each of the leg's column threads (150
+// flops; the alternative is one thread per leg running all six columns one after the other while fifteen warps wait).  Column
+// thread i < 3 writes the range coefficients [joint][i] into dead input channels, i >= 3 the null vector i - 3 straight into the
+// basis (rows sbase ..); thread 0 also writes T = J_leg Q_range into the leg part of the slot's three rows of the reduced
+// Jacobian (scratch rows, where qbuild_red expects them) and the joints' reduced offset (-1: swing leg / joint beyond the foot).
 template <int SB>
-__device__ __forceinline__ void phase_legqr(const DevModel& M, long long base, long long N, double* __restrict__ ctx,
-                                            double* __restrict__ scr, double* __restrict__ inp, int t) {
-    if (t >= SB * ST_MAXLEG * MAXCH) return;
-    const int s = t % SB, u = t / SB, leg = u % ST_MAXLEG, i = u / ST_MAXLEG;
-    if (base + s >= N || leg >= M.nfch) return;
+__device__ __forceinline__ void phase_feet_legqr(const DevModel& M, long long base, long long N, double* __restrict__ ctx,
+                                                 double* __restrict__ scr, double* __restrict__ inp, int t) {
+    const int nee = M.n_ee, nslot_items = SB * nee;
+    if (nee == 0 && t < SB) scr[t * SC_STRIDE + SC_META] = 0.0;      // no contact frame: zero contact rows
+    if (t < nslot_items) {
+        const int s = t % SB, slot = t / SB;
+        if (base + s >= N) return;
+        double* sc = scr + s * SC_STRIDE;
+        int m = 0, kf = -1;
+#pragma unroll
+        for (int k = 0; k < MAXEE; ++k)
+            if (k < nee && inp[(IN_CNT + k) * SB + s] != 0.0) { if (m == slot) kf = k; ++m; }    // truthiness rule of the reference (state 2, NaN: stance)
+        if (slot == 0) sc[SC_META] = (double)(3 * m);
+        sc[SC_META + 1 + slot] = (double)kf;
+        if (kf < 0) return;
+        const int jf = M.ee_joint[kf];
+        double rf[3];
+        if (jf == 1) { rf[0] = M.ee_off[kf][0]; rf[1] = M.ee_off[kf][1]; rf[2] = M.ee_off[kf][2]; }
+        else {
+            const double* X = ctx + s * CX_STRIDE + CX_X + 12 * (jf - 2);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) rf[k] = X[9 + k] + X[3 * k] * M.ee_off[kf][0] + X[3 * k + 1] * M.ee_off[kf][1] + X[3 * k + 2] * M.ee_off[kf][2];
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) sc[SC_RF + 3 * slot + k] = sc[SC_RB + 3 * k] * rf[0] + sc[SC_RB + 3 * k + 1] * rf[1] + sc[SC_RB + 3 * k + 2] * rf[2];
+        return;
+    }
+    const int tt = t - nslot_items, nleg = M.nfch;
+    if (tt >= SB * nleg * MAXCH) return;
+    const int s = tt % SB, u = tt / SB, leg = u % nleg, i = u / nleg;
+    if (base + s >= N) return;
     double* c = ctx + s * CX_STRIDE;
     double* sc = scr + s * SC_STRIDE;
-    const int m = (int)sc[SC_META] / 3;
     const int kfoot = M.st_cfoot[leg];
-    int slot = -1, off = 0, sbase = 0;
-    for (int sl = 0; sl < MAXEE; ++sl) {
-        if (sl >= m) break;
-        const int kf = (int)sc[SC_META + 1 + sl];
-        const int ln = M.chain_len[kf];
-        if (kf == kfoot) { slot = sl; break; }
-        if (ln > 0) { off += 3; sbase += ln - 3; }
-    }
-    if (leg == 0 && i == 0) {
-        // contact frames on the root body (fixed-base emulation): their rows have no leg part
-        for (int sl = 0; sl < m; ++sl) {
-            const int kf = (int)sc[SC_META + 1 + sl];
-            if (M.chain_len[kf] == 0) {
+    // stance slots in contact-frame order: this leg's slot, the reduced-coordinate offset and the stored-vector base before it
+    int m = 0, slot = -1, off = 0, sbase = 0;
+#pragma unroll
+    for (int k = 0; k < MAXEE; ++k) {
+        if (k < nee && inp[(IN_CNT + k) * SB + s] != 0.0) {
+            const int ln = M.chain_len[k];
+            if (k == kfoot) slot = m;
+            else if (kfoot >= 0 && k < kfoot && ln > 0) { off += 3; sbase += ln - 3; }
+            if (leg == 0 && i == 0 && ln == 0) {
+                // a contact frame on the root body (fixed-base emulation): its rows have no leg part
 #pragma unroll
                 for (int x = 0; x < 3; ++x)
-                    for (int cc = 6; cc < MAXV; ++cc) sc[SC_WM + (3 * sl + x) * MAXV + cc] = 0.0;
+                    for (int cc = 6; cc < MAXV; ++cc) sc[SC_WM + (3 * m + x) * MAXV + cc] = 0.0;
             }
+            ++m;
         }
     }
     const int flen = M.fch_len[leg], j0 = M.fch[leg][0];           // the leg's joints are j0 .. j0 + flen - 1 (root -> leaf)
@@ -120,11 +144,30 @@ __device__ __forceinline__ void phase_legqr(const DevModel& M, long long base, l
         for (int e = len; e < flen; ++e) inp[(IN_TAU + (j0 + e - 2)) * SB + s] = -1.0;
         for (int e = 0; e < len; ++e) inp[(IN_TAU + (j0 + e - 2)) * SB + s] = (double)off;
     }
+    // leg columns of the foot's three contact-Jacobian rows: (R_b z_c) x (R_b (r_f - p_c)), c = joint e of the foot chain
     double a[MAXCH][3], v[3][MAXCH];
+    {
+        double Rb[9];
 #pragma unroll
-    for (int e = 0; e < MAXCH; ++e) {
+        for (int k = 0; k < 9; ++k) Rb[k] = sc[SC_RB + k];
+        const int jf = M.ee_joint[kfoot];
+        const double* Xf = c + CX_X + 12 * (jf - 2);
+        double rf[3];
 #pragma unroll
-        for (int x = 0; x < 3; ++x) a[e][x] = (e < len) ? c[ST_JL + 3 * (slot * MAXCH + e) + x] : 0.0;
+        for (int k = 0; k < 3; ++k) rf[k] = Xf[9 + k] + Xf[3 * k] * M.ee_off[kfoot][0] + Xf[3 * k + 1] * M.ee_off[kfoot][1] + Xf[3 * k + 2] * M.ee_off[kfoot][2];
+#pragma unroll
+        for (int e = 0; e < MAXCH; ++e) {
+            if (e < len) {
+                const int cj = j0 + len - 1 - e;
+                const double* A = c + CX_A + 6 * (cj - 2);
+                const double* X = c + CX_X + 12 * (cj - 2);
+                const double ax0 = A[3], ax1 = A[4], ax2 = A[5];
+                const double bx = rf[0] - X[9], by = rf[1] - X[10], bz = rf[2] - X[11];
+                const double a0 = Rb[0] * ax0 + Rb[1] * ax1 + Rb[2] * ax2, a1 = Rb[3] * ax0 + Rb[4] * ax1 + Rb[5] * ax2, a2 = Rb[6] * ax0 + Rb[7] * ax1 + Rb[8] * ax2;
+                const double dx = Rb[0] * bx + Rb[1] * by + Rb[2] * bz, dy = Rb[3] * bx + Rb[4] * by + Rb[5] * bz, dz = Rb[6] * bx + Rb[7] * by + Rb[8] * bz;
+                a[e][0] = a1 * dz - a2 * dy; a[e][1] = a2 * dx - a0 * dz; a[e][2] = a0 * dy - a1 * dx;
+            } else { a[e][0] = 0.0; a[e][1] = 0.0; a[e][2] = 0.0; }
+        }
     }
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
@@ -186,7 +229,7 @@ __device__ __forceinline__ void phase_legqr(const DevModel& M, long long base, l
 // ---------------------------------------------------------------------------------------------- reduced QR
 // phase_qbuild on the reduced Jacobian [J_base | T_f ...] (same sixteen-lanes-per-sample Householder QR, same rank rule: the row
 // norms and elimination remainders are those of J_c, the leg parts having only been rotated).  Lane b assembles the base part of
-// its row; the leg part was written by phase_legqr.  Leaves rank in SC_META, the number of dense vectors in CX_NQ and the number
+// its row; the leg part was written by phase_feet_legqr.  Leaves rank in SC_META, the number of dense vectors in CX_NQ and the number
 // of stored sparse vectors in CX_NQ + 1.
 // The pivot loop is ROLLED: after pivot p every lane shifts its row one coordinate to the left, so the pivot coordinate is
 // always x[0] and the register array keeps static indices (unrolled over the pivots this phase was 30 KB of code that ran once
@@ -640,12 +683,9 @@ gram_struct_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         for (int it = t; it < 2 * ((ST_SB * M.nfch + 31) & ~31); it += GRAM_THREADS) phase_chains<ST_SB>(M, base, Nlim, inp, ctx, scr, it);
         __syncthreads();
         F_TICK(1)
-        for (int it = t; it < ST_SB * MAXEE * (MAXCH + 1); it += GRAM_THREADS) phase_feet<ST_SB, ST_JL>(M, base, Nlim, inp, ctx, scr, it);
+        for (int it = t; it < ST_SB * (M.n_ee + M.nfch * MAXCH); it += GRAM_THREADS) phase_feet_legqr<ST_SB>(M, base, Nlim, ctx, scr, inp, it);
         __syncthreads();
         F_TICK(2)
-        for (int it = t; it < ST_SB * ST_MAXLEG * MAXCH; it += GRAM_THREADS) phase_legqr<ST_SB>(M, base, Nlim, ctx, scr, inp, it);
-        __syncthreads();
-        F_TICK(4)
         if (nred12 && M.n_ee <= 2) { for (int it = t; it < ((8 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, 12, 8>(M, base, Nlim, ctx, scr, s_bad, it); }
         else if (nred12) { for (int it = t; it < ((16 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, 12, 16>(M, base, Nlim, ctx, scr, s_bad, it); }
         else { for (int it = t; it < ((16 * ST_SB + 31) & ~31); it += GRAM_THREADS) phase_qbuild_red<ST_SB, MAXV, 16>(M, base, Nlim, ctx, scr, s_bad, it); }
