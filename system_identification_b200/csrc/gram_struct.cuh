@@ -455,13 +455,14 @@ __device__ __forceinline__ void st_emit(const double* __restrict__ c, int j, con
 }
 
 // One pass of the round's tile fill: dense rows [d0, d0 + Dn) of the round and, when SA / SBn are given, the class rows.
-// A WARP takes one task = one body for all rows of a tile (lane = row): the pose, body motion and Pluecker axes of a sample are
-// then read by all of its rows at once (shared-memory broadcast) and the walk down the leg is warp-uniform.  Every row -- dense,
-// stored sparse or unit vector (a row of the identity table `unit`) -- is a coefficient vector of 18 numbers, so ONE straight-line
-// code path serves them all: the walk is unrolled to MAXLEN joints behind warp-uniform guards, a unit vector simply multiplies zeros.  Tasks (M.st_task, sorted by cost on the
-// host): kind 0 dense rows x joint body; 1 dense rows x (root body, torque column, padding); 2 / 3 class rows x class slot (slot 0
-// also writes the row's torque block).  Warp w takes tasks w and 2 NW - 1 - w of the sorted list (heavy with light).
-template <int NT, int MAXLEN>
+// A WARP takes one task = a run of (at most ST_GROUP) consecutive bodies of one leg for all rows of a tile (lane = row): the pose,
+// body motion and Pluecker axes of a sample are then read by all of its rows at once (shared-memory broadcast), the walk down the
+// leg is warp-uniform, and the bodies of a run share it (a walk per body made 21 joint steps per six-joint leg, runs of two make
+// 12).  Every row -- dense, stored sparse or unit vector (a row of the identity table `unit`) -- is a coefficient vector of 18
+// numbers, so ONE code path serves them all; a unit vector simply multiplies zeros.  Tasks (M.st_task, sorted by cost on the host):
+// kind 0 dense rows x run; 1 dense rows x (root body, torque column, padding); 2 / 3 class rows x run (the run that holds class slot
+// 0 also writes the row's torque block).  Warp w takes tasks w and 2 NW - 1 - w of the sorted list (heavy with light).
+template <int NT>
 __device__ __forceinline__ void phase_fill_struct(const DevModel& M, const double* __restrict__ ctx, const double* __restrict__ unit,
                                                   double* __restrict__ tileD, double* __restrict__ tileA, double* __restrict__ tileB,
                                                   const uint32_t* __restrict__ descD, const uint32_t* __restrict__ descA,
@@ -477,7 +478,8 @@ __device__ __forceinline__ void phase_fill_struct(const DevModel& M, const doubl
     for (int pass = 0; pass < 2; ++pass) {
         const int ti = pass ? 2 * NW - 1 - warp : warp;
         if (ti >= ntask) continue;
-        const int code = M.st_task[ti], kind = code >> 4, arg = code & 15;
+        const uint32_t code = M.st_task[ti];
+        const int kind = code & 15;
         if (kind == 1) {
             // ---- dense rows: root body, torque column, padding
             if (lane >= Dn) continue;
@@ -502,36 +504,43 @@ __device__ __forceinline__ void phase_fill_struct(const DevModel& M, const doubl
                 }
             continue;
         }
-        // ---- rows of one tile x one joint body (warp-uniform: tile, pitch, columns, joint)
+        // ---- rows of one tile x a run of bodies (warp-uniform: tile, pitch, columns, joints)
         const int X = kind - 2;                                     // -2: dense tile
-        const int j = (kind == 0) ? arg : M.st_slotjoint[X][arg];
-        const uint32_t rec = M.st_jrec[j];
+        const int j0 = (code >> 4) & 15, cnt = (code >> 8) & 15, slot0 = (code >> 12) & 15;
         const int nrows = (kind == 0) ? Dn : (X ? SBn : SA);
         if (lane >= nrows) continue;
         const uint32_t desc = ((kind == 0) ? descD : (X ? descB : descA))[lane];
         double* row = (kind == 0) ? tileD + lane * TILE_LD : (X ? tileB : tileA) + lane * ST_SLD;
-        const int bcol = (kind == 0) ? st_rec_bcol(rec) : 10 * arg, fvcol = (kind == 0) ? st_rec_fvcol(rec) : 60 + arg;
         const double* c = ctx + (desc & 31) * CX_STRIDE;
         const double* Qk = st_vector(desc, c, unit);
         const double wsq = c[CX_W];
-        const int pos = st_rec_pos(rec), jf = j - pos;
-        double d[6], pj = 0.0;
+        const int pos0 = st_rec_pos(M.st_jrec[j0]), jf = j0 - pos0;
+        double d[6];
 #pragma unroll
         for (int cc = 0; cc < 6; ++cc) d[cc] = Qk[cc] * wsq;
 #pragma unroll
-        for (int e2 = 0; e2 < MAXLEN; ++e2) {
-            if (e2 <= pos) {                                        // warp-uniform: joints beyond the body's depth are skipped
-                pj = Qk[4 + jf + e2] * wsq;
+        for (int e2 = 0; e2 < MAXCH - 1; ++e2) {                     // joints above the run: walked, not emitted (warp-uniform guards)
+            if (e2 < pos0) {
+                const double pj = Qk[4 + jf + e2] * wsq;
                 const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (jf + e2 - 2));
 #pragma unroll
                 for (int cc = 0; cc < 3; ++cc) { const double2 ak = A2[cc]; d[2 * cc] = fma(pj, ak.x, d[2 * cc]); d[2 * cc + 1] = fma(pj, ak.y, d[2 * cc + 1]); }
             }
         }
-        st_emit(c, j, d, row + bcol);
-        const double dv = c[CX_DQ + j - 2];
-        row[fvcol] = friction ? pj * dv : 0.0;
-        row[fvcol + 6] = friction ? pj * st_sign(dv) : 0.0;
-        if (kind != 0 && arg == 0) {
+        for (int b = 0; b < cnt; ++b) {
+            const int j = j0 + b;
+            const double pj = Qk[4 + j] * wsq;
+            const double2* A2 = reinterpret_cast<const double2*>(c + CX_A + 6 * (j - 2));
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) { const double2 ak = A2[cc]; d[2 * cc] = fma(pj, ak.x, d[2 * cc]); d[2 * cc + 1] = fma(pj, ak.y, d[2 * cc + 1]); }
+            const uint32_t rec = M.st_jrec[j];
+            const int bcol = (kind == 0) ? st_rec_bcol(rec) : 10 * (slot0 + b), fvcol = (kind == 0) ? st_rec_fvcol(rec) : 60 + slot0 + b;
+            st_emit(c, j, d, row + bcol);
+            const double dv = c[CX_DQ + j - 2];
+            row[fvcol] = friction ? pj * dv : 0.0;
+            row[fvcol + 6] = friction ? pj * st_sign(dv) : 0.0;
+        }
+        if ((code >> 16) & 1) {
             // torque entry of the class row (coefficients outside its leg are zero), the rest of the torque block, unused slots
             const int ns = M.st_nslot[X];
             double tau = 0.0;
@@ -654,7 +663,6 @@ gram_struct_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     if (warp == 0) tmem_alloc(&s_tmem, TMEM_PARK_COLS);
     tmem_fence_before_sync();
     double acc[STILES_MAX_NT][2];
-    const bool maxlen3 = M.st_maxlen <= 3;     // longest leg: the walk of the tile fill is unrolled to 3 or MAXCH joints
     const bool nred12 = M.st_nred <= 12;       // reduced Jacobian has 6 + 3 (legs with a contact frame) columns: 12 for a biped, 18 for a quadruped
     const long long nseg = SEG ? (args.N + args.seg_len - 1) / args.seg_len : 1;
 #ifdef SYSID_PHASE_CLOCKS
@@ -711,10 +719,8 @@ gram_struct_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
             for (int d0 = 0; d0 == 0 || d0 < Dtot; d0 += ST_DROWS) {
                 const int Dn = min(ST_DROWS, Dtot - d0);
                 const bool firstpass = d0 == 0;
-                if (maxlen3) phase_fill_struct<GRAM_THREADS, 3>(M, ctx, s_unit, tileD, tileA, tileB, &s_descD[rd][d0], s_descS[0][rd], s_descS[1][rd], Dn,
-                                                                firstpass ? SA : 0, firstpass ? SBn : 0, args.friction, t);
-                else phase_fill_struct<GRAM_THREADS, MAXCH>(M, ctx, s_unit, tileD, tileA, tileB, &s_descD[rd][d0], s_descS[0][rd], s_descS[1][rd], Dn,
-                                                            firstpass ? SA : 0, firstpass ? SBn : 0, args.friction, t);
+                phase_fill_struct<GRAM_THREADS>(M, ctx, s_unit, tileD, tileA, tileB, &s_descD[rd][d0], s_descS[0][rd], s_descS[1][rd], Dn,
+                                                firstpass ? SA : 0, firstpass ? SBn : 0, args.friction, t);
                 __syncthreads();
                 PHASE_TICK(clkC)
                 tmem_unpark<STILES_MAX_NT>(tpark, acc);

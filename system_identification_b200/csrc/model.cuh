@@ -11,6 +11,10 @@ constexpr int MAXD = 12;     // actuated joints
 constexpr int MAXEE = 4;     // contact frames
 constexpr int MAXCH = 6;     // longest foot chain (joints between the foot and the root, root excluded)
 constexpr int CW = 160;      // padded width of one stacked row: 10*nb + 2*d + 1 (tau column) <= 155 -> 160
+#ifndef SYSID_ST_GROUP
+#define SYSID_ST_GROUP 2
+#endif
+constexpr int ST_GROUP = SYSID_ST_GROUP;   // bodies of a leg one tile-fill task emits (the walk down the leg is shared between them)
 constexpr int ST_MAXLEG = 4;  // legs (simple chains below the root) the structured-basis Gram kernel handles
 constexpr int PROJ_PARTS = 4;      // the projection phase of the fused kernel deals every sample's bodies to this many warps
 constexpr int PROJ_MAXITEMS = 12;  // chain-walk steps of one part (prefix joints it only accumulates + joints whose body it emits)
@@ -60,12 +64,13 @@ struct DevModel {
     int8_t st_cfoot[ST_MAXLEG];      // contact frame on leg c (index into ee_*), -1: none
     int8_t st_ccls[ST_MAXLEG];       // column class of leg c
     uint32_t st_jrec[MAXJ];          // per joint >= 2: leg | position in the leg << 2 | class << 5 | class slot << 6 | body column << 9 | viscous column << 17
-    // tile fill: one warp task = one body for all rows of a tile; kind << 4 | argument, kind 0: dense rows x joint (argument),
-    // 1: dense rows x root body + torque column, 2 / 3: class A / B rows x class slot (argument); sorted by cost, heaviest first
+    // tile fill: one warp task = a run of consecutive bodies of one leg (ST_GROUP at most) for all rows of a tile:
+    // kind | first joint << 4 | bodies << 8 | class slot of the first body << 12 | (class task that also writes the torque block) << 16;
+    // kind 0: dense rows, 1: dense rows x root body + torque column, 2 / 3: class A / B rows; sorted by cost, heaviest first
     int8_t st_ntask;
     int8_t st_maxlen;                // joints of the longest leg
     int8_t st_nred;                  // columns of the reduced contact Jacobian: 6 + 3 (legs with a contact frame)
-    uint8_t st_task[32];
+    uint32_t st_task[32];
 };
 
 }  // namespace sysid
