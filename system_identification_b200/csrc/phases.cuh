@@ -66,6 +66,9 @@ constexpr int SC_META = SC_RF + 3 * MAXEE;          // 3m, then the foot index o
 constexpr int SC_WM = SC_META + 1 + MAXEE;          // [3*MAXEE][MAXV] W = L^-1 J_c (16-byte aligned rows)
 constexpr int SC_SC = SC_WM + 3 * MAXEE * MAXV;     // [MAXD][2] sin, cos of the revolute joints
 constexpr int SC_STRIDE = SC_SC + 2 * MAXD + 8;     // 274 == 2 (mod 16): lanes of consecutive samples hit distinct banks
+constexpr int SC_RL = SC_WM;                        // [MAXD][10] joint rotations pR_j Rot(axis_j, q_j) (9, row-major; + 1 pad): formed by `sincos`
+                                                    // (thread per joint) for the serial walks of `chains`; the W slot is not in use before `feet`
+static_assert(10 * MAXD <= 3 * MAXEE * MAXV, "the joint rotations fit the W slot");
 static_assert(SC_WM % 2 == 0 && SC_STRIDE % 16 == 2 && MAXV % 2 == 0, "W rows are read as double2, conflict-free across samples");
 
 // ---- staged inputs of a super-batch (doubles): channel-major, element (channel, sample) at inp[channel * SB + sample]
@@ -157,12 +160,25 @@ __device__ __forceinline__ void phase_sincos(const DevModel& M, long long base, 
     sincos(inp[(IN_Q + 4 + k) * SB + s], &sn, &cs);
     scr[s * SC_STRIDE + SC_SC + 2 * k] = sn;
     scr[s * SC_STRIDE + SC_SC + 2 * k + 1] = cs;
+    {
+        double Rl[9];
+        joint_rotation_compose(M, k + 2, sn, cs, Rl);
+        double2* dst = reinterpret_cast<double2*>(scr + s * SC_STRIDE + SC_RL + 10 * k);
+        dst[0] = make_double2(Rl[0], Rl[1]); dst[1] = make_double2(Rl[2], Rl[3]); dst[2] = make_double2(Rl[4], Rl[5]);
+        dst[3] = make_double2(Rl[6], Rl[7]); dst[4] = make_double2(Rl[8], 0.0);
+    }
     if (k == 0) {
         double probe = 0.0;
 #pragma unroll 4
         for (int ch = 0; ch < IN_CNT; ++ch) probe += inp[ch * SB + s];     // contacts and weights are not probed
         if (!(fabs(probe) < 1e300)) atomicOr(&s_bad[s], 2);
     }
+}
+
+__device__ __forceinline__ void load_joint_rotation(const double* __restrict__ src, double (&Rl)[9]) {
+    const double2* s2 = reinterpret_cast<const double2*>(src);
+    const double2 a = s2[0], b = s2[1], c = s2[2], d = s2[3];
+    Rl[0] = a.x; Rl[1] = a.y; Rl[2] = b.x; Rl[3] = b.y; Rl[4] = c.x; Rl[5] = c.y; Rl[6] = d.x; Rl[7] = d.y; Rl[8] = src[8];
 }
 
 // ---------------------------------------------------------------------------------------------- chains
@@ -186,7 +202,7 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
         for (int e = 0; e < len; ++e) {
             const int j = M.fch[ch][e];
             double Rl[9];
-            joint_rotation_compose(M, j, scs[2 * (j - 2)], scs[2 * (j - 2) + 1], Rl);
+            load_joint_rotation(scr + s * SC_STRIDE + SC_RL + 10 * (j - 2), Rl);
             const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
             if (e == 0) {
 #pragma unroll
@@ -257,7 +273,7 @@ __device__ __forceinline__ void phase_chains(const DevModel& M, long long base, 
         const int j = M.fch[ch][e];
         const double qd = in[(IN_DQ + 4 + j) * SB], qdd = in[(IN_DDQ + 4 + j) * SB];
         double Rl[9];
-        joint_rotation_compose(M, j, scs[2 * (j - 2)], scs[2 * (j - 2) + 1], Rl);
+        load_joint_rotation(scr + s * SC_STRIDE + SC_RL + 10 * (j - 2), Rl);
         const double px = M.pp[j][0], py = M.pp[j][1], pz = M.pp[j][2];
         // actInv of the parent's (v, a), then the joint's own contribution
         const double tvx = v[0] - (py * v[5] - pz * v[4]), tvy = v[1] - (pz * v[3] - px * v[5]), tvz = v[2] - (px * v[4] - py * v[3]);
