@@ -310,6 +310,8 @@ typedef struct sysid_presolve {
                                          the first one, warm-started from it; its record replaces the first one's in warm_out.  Pays on
                                          logs long enough to hide both (~1 M samples); 0 = one stage */
     double* stats_snapshot2;          /* stats_len doubles (needed when refine_at > 0) */
+    double first_tol;                 /* > 0: tolerance of the FIRST pre-solve (the second stage and the final solve keep desc->tol): with a
+                                         second stage behind it, the first only has to get the multipliers roughly right */
 } sysid_presolve;
 int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* const* arrays_host, const int32_t* dtypes,
                                         const int64_t* lds_host, int64_t N, const double* weights_host, int32_t friction,

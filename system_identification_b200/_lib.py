@@ -51,7 +51,7 @@ class SdpInfo(C.Structure):
 class Presolve(C.Structure):
     _fields_ = [("desc", C.POINTER(SdpDesc)), ("plan", C.c_void_p), ("sdp_workspace", C.c_void_p), ("sdp_workspace_bytes", C.c_size_t),
                 ("stats_snapshot", C.c_void_p), ("x_scratch", C.c_void_p), ("info_scratch", C.c_void_p), ("warm_out", C.c_void_p),
-                ("samples", C.c_int64), ("refine_at", C.c_int64), ("stats_snapshot2", C.c_void_p)]
+                ("samples", C.c_int64), ("refine_at", C.c_int64), ("stats_snapshot2", C.c_void_p), ("first_tol", C.c_double)]
 
 
 SDP_INFO_DTYPE = np.dtype([("status", "<i4"), ("iterations", "<i4"), ("refactorizations", "<i4"), ("reserved", "<i4"),

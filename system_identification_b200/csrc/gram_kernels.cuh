@@ -175,6 +175,8 @@ struct GramArgs {
     double* partial;      // [gridDim][PARTIAL_DOUBLES]; segmented mode: [segments][PARTIAL_DOUBLES]
     long long seg_len;    // 0: one Gram of the whole launch (super-batches dealt round-robin to the CTAs).  > 0: one Gram per SEGMENT of
                           // seg_len consecutive samples (block bootstrap): segments dealt round-robin, each worked through by one CTA
+    int accumulate;       // gram_struct_kernel, whole-launch mode: start from the CTA's partial Gram in `partial` instead of zero (host
+                          // streaming: the chunks of a log add up in the partials and are reduced once, not once per chunk)
 };
 
 #ifdef SYSID_PHASE_CLOCKS

@@ -636,6 +636,20 @@ __device__ __forceinline__ void st_store_dispatch(int w, double* __restrict__ pa
     }
 }
 
+template <int W = 0>
+__device__ __forceinline__ void st_load_dispatch(int w, const double* __restrict__ partial, int lane, double (&acc)[STILES_MAX_NT][2]) {
+    if constexpr (W < GRAM_WARPS) {
+        if (w == W) {
+            using T = STiles<W>;
+#pragma unroll
+            for (int t = 0; t < T::NT; ++t) {
+                const double2 v = *reinterpret_cast<const double2*>(partial + T::ID(t) * 64 + (lane >> 2) * 8 + 2 * (lane & 3));
+                acc[t][0] = v.x; acc[t][1] = v.y;
+            }
+        } else st_load_dispatch<W + 1>(w, partial, lane, acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- the kernel
 // Same launch shape, arguments, partial-Gram layout (tile coordinates) and segmented mode as gram_fused_kernel; the columns of
 // the partial Grams are in TILE order, which gram_reduce_kernel undoes (ColMap).
@@ -657,7 +671,8 @@ gram_struct_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
     __shared__ uint32_t s_tmem;
     __shared__ double s_unit[MAXD * QLD];      // identity table: row u = the unit vector of joint u + 2 (coefficient 6 + u)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, t = tid;
-    if (tid < 3) s_stat[tid] = 0.0;
+    const bool resume = !SEG && args.accumulate;       // continue from this CTA's partial Gram (host streaming)
+    if (tid < 3) s_stat[tid] = resume ? args.partial[(size_t)blockIdx.x * PARTIAL_DOUBLES + GRAM_NTILES * 64 + tid] : 0.0;
     if (tid < ST_SB) s_bad[tid] = 0;
     if (tid < MAXD * QLD) s_unit[tid] = (tid % QLD == 6 + tid / QLD) ? 1.0 : 0.0;
     if (warp == 0) tmem_alloc(&s_tmem, TMEM_PARK_COLS);
@@ -707,6 +722,7 @@ gram_struct_kernel(const __grid_constant__ DevModel M, const GramArgs args) {
         if (first_sb) {
 #pragma unroll
             for (int k = 0; k < STILES_MAX_NT; ++k) { acc[k][0] = 0.0; acc[k][1] = 0.0; }
+            if (resume) st_load_dispatch(warp, partial, lane, acc);
             tmem_park<STILES_MAX_NT>(tpark, acc);
         }
         if (t < ST_SB) s_bad[t] = 0;

@@ -547,7 +547,7 @@ size_t sysid_gram_from_stack_workspace_bytes(int32_t c) {
 static int gram_accumulate_impl(const sysid_model* model, const double* q, const double* dq, const double* ddq,
                                 const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
                                 int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
-                                int reserve_sms, void* stream);
+                                int reserve_sms, void* stream, bool keep_partials = false);
 
 int sysid_gram_accumulate(const sysid_model* model, const double* q, const double* dq, const double* ddq,
                           const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
@@ -561,7 +561,9 @@ int sysid_gram_accumulate(const sysid_model* model, const double* q, const doubl
 static int gram_accumulate_impl(const sysid_model* model, const double* q, const double* dq, const double* ddq,
                                 const double* tau, const double* contact, int64_t N, int64_t ld, const double* weights,
                                 int32_t friction, double* stats, int64_t* info, void* workspace, size_t workspace_bytes,
-                                int reserve_sms, void* stream) {
+                                int reserve_sms, void* stream, bool keep_partials) {
+    // keep_partials (structured kernel only; the caller zeroed the partial Grams first): this launch ADDS to the partial Grams in
+    // the workspace and nothing is reduced -- gram_reduce_partials does that once for all chunks of a streamed log
     if (!model || !q || !dq || !ddq || !tau || !stats || !workspace) return fail(SYSID_ERR_INVALID, "null argument");
     if (model->dev.n_ee > 0 && !contact) return fail(SYSID_ERR_INVALID, "null contact array");
     if (N < 0 || ld < N) return fail(SYSID_ERR_INVALID, "bad N/ld");
@@ -581,11 +583,14 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     if (debug_kernel) fprintf(stderr, "[sysid] gram kernel: %s (st_ok %d)\n", structured ? "structured" : "unstructured", (int)model->dev.st_ok);
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, weights, ld);
-    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = 0;
+    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = 0; a.accumulate = 0;
+    if (keep_partials && !structured) return fail(SYSID_ERR_INVALID, "keep_partials needs the structured kernel");
     if (structured) {
         int rc = opt_in_smem(gram_struct_kernel<false>, ST_SMEM_BYTES);
         if (rc) return rc;
+        a.accumulate = keep_partials ? 1 : 0;
         gram_struct_kernel<false><<<grid, GRAM_THREADS, ST_SMEM_BYTES, st>>>(M, a);
+        if (keep_partials) { CUDA_TRY(cudaGetLastError()); return SYSID_OK; }
     } else {
         int rc = opt_in_smem(gram_fused_kernel<false>, GRAM_SMEM_BYTES);
         if (rc) return rc;
@@ -596,6 +601,17 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     const int total = (c + 1) * (c + 2) / 2;
     gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, (double)M.nv, 0.0, stats,
                                                              (long long*)info, make_colmap(M, friction ? 1 : 0, structured));
+    CUDA_TRY(cudaGetLastError());
+    return SYSID_OK;
+}
+
+// Reduction of the partial Grams a streamed log accumulated with keep_partials (ADDS into stats, like every reduction here).
+static int gram_reduce_partials(const sysid_model* model, int32_t friction, double* stats, int64_t* info, void* workspace, cudaStream_t st) {
+    const DevModel& M = model->dev;
+    const int c = M.nparams + (friction ? 2 * M.nd : 0);
+    const int total = (c + 1) * (c + 2) / 2;
+    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, model->sm_count, c, (double)M.nv, 0.0, stats,
+                                                             (long long*)info, make_colmap(M, friction ? 1 : 0, true));
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
 }
@@ -627,7 +643,7 @@ int sysid_gram_blocks(const sysid_model* model, const double* q, const double* d
     const bool structured = use_struct(model);
     GramArgs a{};
     a.io = make_io(q, dq, ddq, tau, contact, nullptr, ld);
-    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = block;
+    a.N = N; a.friction = friction ? 1 : 0; a.partial = (double*)workspace; a.seg_len = block; a.accumulate = 0;
     const int grid = (int)(nseg < model->sm_count ? nseg : model->sm_count);
     if (structured) {
         int rc = opt_in_smem(gram_struct_kernel<true>, ST_SMEM_BYTES);
@@ -749,6 +765,10 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
     bool presolve_running = false, refined = false;
 #define HOST_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { rc = fail(SYSID_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); cleanup(); return rc; } } while (0)
     if (pre) HOST_TRY(cudaMemsetAsync(pre->warm_out, 0, sizeof(double) * warm_n, st));      // "no record" until the pre-solve has written one
+    // structured kernel: the chunks add up in the per-CTA partial Grams and are reduced ONCE (a reduction per chunk reads 16 MB of
+    // partials: 70 us x ~14 chunks of a 1 M-sample log); the pre-solve snapshots are reductions of the partials so far
+    const bool keep = use_struct(model) && !model->big;
+    if (keep) HOST_TRY(cudaMemsetAsync(workspace, 0, sizeof(double) * (size_t)model->sm_count * PARTIAL_DOUBLES, st));
     // the staging buffers may still be read by earlier work on `stream`
     HOST_TRY(cudaEventRecord(start, st));
     HOST_TRY(cudaStreamWaitEvent(cp, start, 0));
@@ -795,19 +815,27 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
                 HOST_TRY(cudaGetLastError());
             }
         rc = gram_accumulate_impl(model, dst[0], dst[1], dst[2], dst[3], M.n_ee > 0 ? dst[4] : nullptr, n, chunk,
-                                  weights_host ? dst[5] : nullptr, friction, stats, info, workspace, gram_ws, presolve_running ? 1 : 0, st);
+                                  weights_host ? dst[5] : nullptr, friction, stats, info, workspace, gram_ws, presolve_running ? 1 : 0, st, keep);
         if (rc != SYSID_OK) { cleanup(); return rc; }
         HOST_TRY(cudaEventRecord(consumed[b], st));
         if (presolve && !presolve_running && lo + n >= first) {
             const size_t slen = sysid_stats_len(model, friction);
             // snapshot by a kernel, not cudaMemcpyAsync: a device-to-device copy would queue on a copy engine behind the 72 MB
             // host-to-device transfer of the next chunk and stall `stream` for more than a millisecond
-            copy_f64_kernel<<<(unsigned)((slen + 255) / 256), 256, 0, st>>>(stats, pre->stats_snapshot, (int64_t)slen);
-            HOST_TRY(cudaGetLastError());
+            if (keep) {
+                HOST_TRY(cudaMemsetAsync(pre->stats_snapshot, 0, sizeof(double) * slen, st));
+                rc = gram_reduce_partials(model, friction, pre->stats_snapshot, nullptr, workspace, st);
+                if (rc != SYSID_OK) { cleanup(); return rc; }
+            } else {
+                copy_f64_kernel<<<(unsigned)((slen + 255) / 256), 256, 0, st>>>(stats, pre->stats_snapshot, (int64_t)slen);
+                HOST_TRY(cudaGetLastError());
+            }
             HOST_TRY(cudaEventRecord(snap, st));
             HOST_TRY(cudaStreamWaitEvent(sv, snap, 0));
             char msg[256] = "";
-            rc = sdp_solve_planned(*pre->desc, (const double*)pre->plan, pre->stats_snapshot, (int64_t)slen, 1, pre->x_scratch,
+            sysid_sdp_desc d1 = *pre->desc;
+            if (pre->first_tol > 0.0) d1.tol = pre->first_tol;
+            rc = sdp_solve_planned(d1, (const double*)pre->plan, pre->stats_snapshot, (int64_t)slen, 1, pre->x_scratch,
                                    pre->info_scratch, pre->sdp_workspace, pre->sdp_workspace_bytes, nullptr, pre->warm_out, sv, msg, sizeof(msg));
             if (rc != SYSID_OK) { fail(rc, "pre-solve: %s", msg); cleanup(); return rc; }
             HOST_TRY(cudaEventRecord(solved, sv));
@@ -816,8 +844,14 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
             // second stage: the statistics so far, solved behind the first pre-solve (same internal stream) from its record; the
             // record it leaves is the start of the final solve.  Same scratch buffers: the stream orders the two solves.
             const size_t slen = sysid_stats_len(model, friction);
-            copy_f64_kernel<<<(unsigned)((slen + 255) / 256), 256, 0, st>>>(stats, pre->stats_snapshot2, (int64_t)slen);
-            HOST_TRY(cudaGetLastError());
+            if (keep) {
+                HOST_TRY(cudaMemsetAsync(pre->stats_snapshot2, 0, sizeof(double) * slen, st));
+                rc = gram_reduce_partials(model, friction, pre->stats_snapshot2, nullptr, workspace, st);
+                if (rc != SYSID_OK) { cleanup(); return rc; }
+            } else {
+                copy_f64_kernel<<<(unsigned)((slen + 255) / 256), 256, 0, st>>>(stats, pre->stats_snapshot2, (int64_t)slen);
+                HOST_TRY(cudaGetLastError());
+            }
             HOST_TRY(cudaEventRecord(snap2, st));
             HOST_TRY(cudaStreamWaitEvent(sv, snap2, 0));
             char msg[256] = "";
@@ -829,6 +863,7 @@ int sysid_gram_accumulate_host_presolve(const sysid_model* model, const void* co
         }
         lo += n;
     }
+    if (keep) { rc = gram_reduce_partials(model, friction, stats, info, workspace, st); if (rc != SYSID_OK) { cleanup(); return rc; } }
     if (presolve_running) HOST_TRY(cudaStreamWaitEvent(st, solved, 0));      // later work on `stream` sees the warm-start record
 #undef HOST_TRY
     cleanup();

@@ -47,6 +47,9 @@ PRESOLVE_MIN_LOG = 600_000        # the pre-solve (a cold solve, ~9 ms) only pay
 # fraction of 0.5 and more the chain overruns the stream and the final solve waits for it (tools/presolve_refine_study.py).
 PRESOLVE_REFINE_MIN_LOG = 900_000
 PRESOLVE_REFINE_FRACTION = 0.45
+PRESOLVE_FIRST_TOL = 1e-7          # tolerance of the first pre-solve when a second stage follows (the second stage and the final solve keep
+                                   # the caller's): the chain of pre-solves, not the stream, bounds identify() on the 1 M-sample log, and the
+                                   # last decades of the first stage buy nothing -- 17.6 instead of 18.7 ms; 1e-6: the same; 1e-4: 22-26 ms
 PRESOLVE_TOL = None                # tolerance of the pre-solves (None: the final solve's; looser ones were measured: 1e-6 costs the final
                                    # solve 7 more Newton steps, 1e-5 twenty)
 
@@ -123,7 +126,8 @@ def identify(sysid, q, dq, ddq, tau, cnt, lambda_reg=1e-1, tol=1e-10, max_iters=
         use_pre = (presolve is True and n_loc >= PRESOLVE_MIN_LOG or presolve == "force") and plan is not None and n_loc >= 2 * n0
         refine = int(PRESOLVE_REFINE_FRACTION * n_loc) if (use_pre and n_loc >= PRESOLVE_REFINE_MIN_LOG) else 0
         dm.gram_accumulate_host(*arrays, friction=friction, weights=weights, stats=stats, info=counts, chunk=chunk,
-                                presolve=plan if use_pre else None, presolve_samples=n0, presolve_refine_at=refine, presolve_tol=PRESOLVE_TOL)
+                                presolve=plan if use_pre else None, presolve_samples=n0, presolve_refine_at=refine, presolve_tol=PRESOLVE_TOL,
+                                presolve_first_tol=PRESOLVE_FIRST_TOL if refine else None)
         warm = plan.warm if use_pre else None
     else:
         dev = [a if (isinstance(a, torch.Tensor) and a.is_cuda and a.dtype == torch.float64) else to_device(a) for a in arrays]

@@ -140,7 +140,7 @@ class DeviceModel:
         return out
 
     def gram_accumulate_host(self, q, dq, ddq, tau, cnt, friction=True, weights=None, stats=None, info=None, chunk=131072,
-                             device=None, presolve=None, presolve_samples=0, presolve_refine_at=0, presolve_tol=None):
+                             device=None, presolve=None, presolve_samples=0, presolve_refine_at=0, presolve_tol=None, presolve_first_tol=None):
         """gram_accumulate for arrays still in HOST memory: float64 OR float32 torch CPU tensors / numpy arrays, channel-major
         with unit inner stride (pinned memory for full PCIe speed) -- exactly what the reference's read_data returns
         (float32 q / contact, float64 dq / ddq / tau; demo/solo_identification.py:10-33).  The upload is chunked and
@@ -174,7 +174,7 @@ class DeviceModel:
         pre = None
         if presolve is not None:
             # presolve: an SdpPlan -- the LMI fit of the first chunk is solved behind the stream and left in presolve.warm
-            pre = presolve.presolve_struct(presolve_samples, presolve_refine_at, presolve_tol)
+            pre = presolve.presolve_struct(presolve_samples, presolve_refine_at, presolve_tol, presolve_first_tol)
         _lib.check(self.lib.sysid_gram_accumulate_host_presolve(self.handle, ptrs, dts, lds, N,
                                                                 C.c_void_p(wh.data_ptr()) if wh is not None else None,
                                                                 1 if friction else 0, _ptr(stats), _ptr(info), _ptr(ws), ws.numel(), chunk,
@@ -374,7 +374,7 @@ class SdpPlan:
             self._ws[k] = torch.empty(self.lib.sysid_sdp_solve_workspace_bytes(self.L, self.nd, batch), dtype=torch.uint8, device=self.device)
         return self._ws[k]
 
-    def presolve_struct(self, samples=0, refine_at=0, tol=None):
+    def presolve_struct(self, samples=0, refine_at=0, tol=None, first_tol=None):
         """tol: tolerance of the pre-solves (default: the plan's own).  They only produce a starting point, so a looser one shortens the
         chain hidden behind the stream without changing where the final solve converges."""
         if self._pre is None:
@@ -393,6 +393,7 @@ class SdpPlan:
         self._pre.samples = int(samples)
         self._pre.refine_at = int(refine_at)
         self._pre_desc.tol = float(tol) if tol else self.desc.tol
+        self._pre.first_tol = float(first_tol) if first_tol else 0.0
         return self._pre
 
     def presolve_info(self):

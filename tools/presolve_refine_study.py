@@ -19,8 +19,8 @@ dev[3] = bench.identifiable_tau(flat, dm, dev, seed=17)
 pinned = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (q, dq, ddq, tau, cnt)]
 pinned[3] = dev[3].cpu().pin_memory()
 res = {}
-for tol, frac in ((None, 0.0), (None, 0.45), (1e-6, 0.0), (1e-6, 0.45), (1e-6, 0.55), (1e-6, 0.65), (1e-7, 0.55), (1e-5, 0.55), (1e-5, 0.65)):
-    idm.PRESOLVE_TOL = tol
+for tol, frac in ((None, 0.0), (None, 0.45), (None, 0.6), (1e-7, 0.45), (1e-6, 0.45), (1e-6, 0.55), (1e-6, 0.65), (1e-5, 0.45), (1e-5, 0.6), (1e-4, 0.5), (1e-4, 0.65)):
+    idm.PRESOLVE_FIRST_TOL = tol
     idm.PRESOLVE_REFINE_FRACTION = frac
     idm.PRESOLVE_REFINE_MIN_LOG = 900_000 if frac > 0 else 10**12
     best, it = None, None
@@ -29,5 +29,5 @@ for tol, frac in ((None, 0.0), (None, 0.45), (1e-6, 0.0), (1e-6, 0.45), (1e-6, 0
         out = idm.identify(si, *pinned, sharded=True, return_info=True)
         torch.cuda.synchronize(); dt = (time.perf_counter() - t0) * 1e3
         if best is None or dt < best: best, it = dt, int(out[3]["iterations"])
-    res["tol_%s_refine_%.2f" % (tol, frac)] = {"identify_ms": round(best, 3), "final_newton_steps": it}
+    res["first_tol_%s_refine_%.2f" % (tol, frac)] = {"identify_ms": round(best, 3), "final_newton_steps": it}
 print(json.dumps(res))
