@@ -599,7 +599,7 @@ static int gram_accumulate_impl(const sysid_model* model, const double* q, const
     CUDA_TRY(cudaGetLastError());
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
     const int total = (c + 1) * (c + 2) / 2;
-    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, (double)M.nv, 0.0, stats,
+    gram_reduce_kernel<<<(total * REDUCE_LANES + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, (double)M.nv, 0.0, stats,
                                                              (long long*)info, make_colmap(M, friction ? 1 : 0, structured));
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
@@ -610,7 +610,7 @@ static int gram_reduce_partials(const sysid_model* model, int32_t friction, doub
     const DevModel& M = model->dev;
     const int c = M.nparams + (friction ? 2 * M.nd : 0);
     const int total = (c + 1) * (c + 2) / 2;
-    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, model->sm_count, c, (double)M.nv, 0.0, stats,
+    gram_reduce_kernel<<<(total * REDUCE_LANES + 255) / 256, 256, 0, st>>>((const double*)workspace, model->sm_count, c, (double)M.nv, 0.0, stats,
                                                              (long long*)info, make_colmap(M, friction ? 1 : 0, true));
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
@@ -660,7 +660,7 @@ int sysid_gram_blocks(const sysid_model* model, const double* q, const double* d
     CUDA_TRY(cudaMemsetAsync(stats_blocks, 0, sizeof(double) * (size_t)stats_stride * (size_t)nseg, st));
     for (long long y0 = 0; y0 < nseg; y0 += 65535) {
         const unsigned ny = (unsigned)((nseg - y0 < 65535) ? (nseg - y0) : 65535);
-        gram_reduce_kernel<<<dim3((total + 255) / 256, ny), 256, 0, st>>>((const double*)workspace + (size_t)y0 * PARTIAL_DOUBLES, 1, c, (double)M.nv, 0.0,
+        gram_reduce_kernel<<<dim3((total * REDUCE_LANES + 255) / 256, ny), 256, 0, st>>>((const double*)workspace + (size_t)y0 * PARTIAL_DOUBLES, 1, c, (double)M.nv, 0.0,
                                                                         stats_blocks + (size_t)y0 * stats_stride, (long long*)info,
                                                                         make_colmap(M, friction ? 1 : 0, structured), (long long)stats_stride);
         CUDA_TRY(cudaGetLastError());
@@ -902,7 +902,7 @@ int sysid_gram_from_stack(const double* A, const double* b, int64_t rows, int32_
     gram_stack_kernel<<<grid, GRAM_THREADS, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     const int total = (c + 1) * (c + 2) / 2;
-    gram_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, 0.0, (double)rows, stats, nullptr, make_colmap(DevModel{}, 0, false));
+    gram_reduce_kernel<<<(total * REDUCE_LANES + 255) / 256, 256, 0, st>>>((const double*)workspace, grid, c, 0.0, (double)rows, stats, nullptr, make_colmap(DevModel{}, 0, false));
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
 }
