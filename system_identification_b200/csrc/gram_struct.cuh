@@ -16,8 +16,9 @@
 // of the whole tree for the sparse rows.
 //
 // Layout of a round (ST_TS samples): dense rows in a 160-column tile, the sparse rows of each class in an 80-column tile (72 class
-// columns + the block of the torque column); row descriptors are built once per super-batch by warp 0 (prefix sums by shuffles).
-// The fill is task-parallel: (dense row, joint body), (dense row, root body + torque), (sparse row, class slot).
+// columns + the block of the torque column); row descriptors are built once per super-batch by one warp (prefix sums by shuffles).
+// The fill is task-parallel, one warp per task, lane = tile row: (dense rows, run of two bodies of a leg), (dense rows, root body +
+// torque column), (class rows, run of two bodies).  DESIGN.md section 4.1 has the measurements behind each of these choices.
 #pragma once
 #include "gram_kernels.cuh"
 
