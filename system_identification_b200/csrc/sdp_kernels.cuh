@@ -336,7 +336,7 @@ __device__ __forceinline__ void chol_update_tiles(const double* pan, int tp, int
         default: FN<15>(__VA_ARGS__); break;                                                               \
     }
 
-__device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, double* pan, int tid, long long* dbg = nullptr) {
+__device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, double* pan0, double* pan1, int tid, long long* dbg = nullptr) {
     static_assert(SDP_THREADS == 512, "tile ownership tables are for 16 warps");
     const int warp = tid >> 5, lane = tid & 31;
     const unsigned full = 0xffffffffu;
@@ -349,11 +349,12 @@ __device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, 
 #endif
     SDP_WARP_CALL(chol_load_tiles, A, n, ld, lane, acc)
     CH_TICK(0)
+    SDP_WARP_CALL(chol_publish_panel, pan0, 0, lane, acc)
+    __syncthreads();
+    CH_TICK(1)
     for (int tp = 0; tp < 20; ++tp) {
         if (8 * tp >= n) break;
-        SDP_WARP_CALL(chol_publish_panel, pan, tp, lane, acc)
-        __syncthreads();
-        CH_TICK(1)
+        double* pan = (tp & 1) ? pan1 : pan0;             // this panel; the other buffer receives the next one during the update
         const int row = 8 * tp + tid;                     // one thread per row at or below the panel's diagonal block
         if (8 * tp + 32 * warp < 160) {                   // warp-uniform: this warp has rows to solve
             // 8 x 8 diagonal block, lane b (< 8) owns row b
@@ -428,6 +429,10 @@ __device__ inline void chol_factor_smem(double* A, int n, int ld, double* invd, 
         __syncthreads();
         CH_TICK(2)
         SDP_WARP_CALL(chol_update_tiles, pan, tp, lane, acc)
+        if (tp + 1 < 20 && 8 * (tp + 1) < n) {            // the next panel's tiles are final: publish them into the other buffer
+            double* nxt = (tp & 1) ? pan0 : pan1;
+            SDP_WARP_CALL(chol_publish_panel, nxt, tp + 1, lane, acc)
+        }
         __syncthreads();
         CH_TICK(3)
     }
@@ -646,13 +651,9 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* gt = BIG ? sm : W + c * ldw;               // c   scaled linear term
     double* at = gt + c;                               // c   scaled equality vector
     double* y = at + c;                                // c
-    double* yt = y + c;                                // c   trial point / K^-1 grad
-    double* hy = yt + c;                               // c   Hs y
+    double* hy = y + c;                                // c   Hs y
     double* grad = hy + c;                             // c
-    double* dy = grad + c;                             // c   Newton direction
-    double* Ka = dy + c;                               // c   K^-1 at, then Hs dy
-    double* rhs = Ka + c;                              // c   x = T y at the end
-    double* lam = rhs + c;                             // m   multiplier
+    double* lam = grad + c;                            // m   multiplier
     double* c0 = lam + m;                              // m
     double* gy = c0 + m;                               // m   g(y) = A y + c0 at the last evaluated point
     double* wv = gy + m;                               // m   lam - sigma g(y)
@@ -664,7 +665,15 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
     double* red = invd + c;                            // 32
     // 8 x TILE_LD panel buffer of the factorisation: aliases gy|wv|pw|tv|evals (all dead between the Newton-matrix set-up
     // and the next evaluate()) when they are large enough, else its own buffer behind `red` (small problems)
-    double* pan = BIG ? red + 32 : ((4 * m + 8 * L >= SDP_PAN_DOUBLES) ? gy : red + 32);      // BIG: the 8 c + 80 doubles of chol_factor_big
+    const bool pan_alias = 4 * m + 8 * L >= SDP_PAN_DOUBLES;
+    double* pan = BIG ? red + 32 : (pan_alias ? gy : red + 32);      // BIG: the 8 c + 80 doubles of chol_factor_big
+    double* yt = red + 32 + (BIG ? 8 * c + 80 : (pan_alias ? 0 : SDP_PAN_DOUBLES));   // c   trial point / K^-1 grad
+    double* dy = yt + c;                               // c   Newton direction
+    double* Ka = dy + c;                               // c   K^-1 at, then Hs dy
+    double* rhs = Ka + c;                              // c   x = T y at the end
+    // second panel buffer (the panels of the factorisation alternate between the two: the next panel is published while the
+    // current one is still being read): yt|dy|Ka|rhs, dead during the factorisation, plus the padding behind them
+    double* pan2 = yt;
     __shared__ double s_scalar[8];
 
     unsigned long long t_start_ = 0;
@@ -870,8 +879,28 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
 
     // W <- Cholesky factor of Hs + sigma A^T D A at the current evaluation point (uses wv / evals / evecs)
     auto newton_matrix_factor = [&]() {
-        for (int a = warp; a < c; a += SDP_THREADS / 32)
-            for (int b = lane; b <= a; b += 32) W[a * ldw + b] = Hs[(size_t)a * c + b];
+        if constexpr (BIG) {
+            for (int a = warp; a < c; a += SDP_THREADS / 32)
+                for (int b = lane; b <= a; b += 32) W[a * ldw + b] = Hs[(size_t)a * c + b];
+        } else {
+            // lower triangle of Hs (L2) -> W (shared): four rows x five column steps = up to 20 independent loads in flight per thread
+            // (a plain row loop is one L2 latency per 32 columns)
+            for (int a0 = warp; a0 < c; a0 += 4 * (SDP_THREADS / 32)) {
+                double v[4][SDP_SOLVE_T];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int a = a0 + r * (SDP_THREADS / 32);
+#pragma unroll
+                    for (int k = 0; k < SDP_SOLVE_T; ++k) { const int b = lane + 32 * k; v[r][k] = (a < c && b <= a) ? Hs[(size_t)a * c + b] : 0.0; }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int a = a0 + r * (SDP_THREADS / 32);
+#pragma unroll
+                    for (int k = 0; k < SDP_SOLVE_T; ++k) { const int b = lane + 32 * k; if (a < c && b <= a) W[a * ldw + b] = v[r][k]; }
+                }
+            }
+        }
         __syncthreads();
         // one warp per link: lane a (< 10) owns column a of the link's 10 x 10 diagonal block
         for (int i = warp; i < L; i += SDP_THREADS / 32) {
@@ -938,9 +967,9 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         if constexpr (BIG) chol_factor_big(W, c, ldw, invd, pan, tid);
         else {
 #ifdef SYSID_PHASE_CLOCKS
-            chol_factor_smem(W, c, ldw, invd, pan, tid, chk);
+            chol_factor_smem(W, c, ldw, invd, pan, pan2, tid, chk);
 #else
-            chol_factor_smem(W, c, ldw, invd, pan, tid);
+            chol_factor_smem(W, c, ldw, invd, pan, pan2, tid);
 #endif
         }
     };
@@ -1003,13 +1032,43 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
         }
         __syncthreads();
     }
-    for (int a = warp; a < c; a += SDP_THREADS / 32) {       // hy = Hs y  (Hs in global memory / L2)
-        double s = 0.0;
-        for (int b = lane; b < c; b += 32) s += Hs[(size_t)a * c + b] * y[b];
+    // out = Hs v  (Hs in global memory / L2; warp per row).  Small problems: four rows at a time, their <= 20 loads issued before
+    // the first use (one L2 latency per four rows instead of per 32 columns); same summation order per row as the plain loop.
+    auto hs_matvec = [&](const double* v, double* out) {
+        if constexpr (BIG) {
+            for (int a = warp; a < c; a += SDP_THREADS / 32) {
+                double s = 0.0;
+                for (int b = lane; b < c; b += 32) s += Hs[(size_t)a * c + b] * v[b];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) hy[a] = s;
-    }
+                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                if (lane == 0) out[a] = s;
+            }
+        } else {
+            double vv[SDP_SOLVE_T];
+#pragma unroll
+            for (int k = 0; k < SDP_SOLVE_T; ++k) { const int b = lane + 32 * k; vv[k] = (b < c) ? v[b] : 0.0; }
+            for (int a0 = warp; a0 < c; a0 += 4 * (SDP_THREADS / 32)) {
+                double h[4][SDP_SOLVE_T];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int a = a0 + r * (SDP_THREADS / 32);
+#pragma unroll
+                    for (int k = 0; k < SDP_SOLVE_T; ++k) { const int b = lane + 32 * k; h[r][k] = (a < c && b < c) ? Hs[(size_t)a * c + b] : 0.0; }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int a = a0 + r * (SDP_THREADS / 32);
+                    double s = 0.0;
+#pragma unroll
+                    for (int k = 0; k < SDP_SOLVE_T; ++k) { const int b = lane + 32 * k; if (b < c) s += h[r][k] * vv[k]; }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0 && a < c) out[a] = s;
+                }
+            }
+        }
+    };
+    hs_matvec(y, hy);                                         // hy = Hs y
     __syncthreads();
     const double gnorm = sqrt(dot_c(gt, gt));
 
@@ -1045,13 +1104,7 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
             const double a_v1 = dot_c(at, yt), a_Ka = dot_c(at, Ka);
             for (int a = tid; a < c; a += SDP_THREADS) dy[a] = -(yt[a] - Ka[a] * (a_v1 / a_Ka));
             __syncthreads();
-            for (int a = warp; a < c; a += SDP_THREADS / 32) {    // Ka <- Hs dy (reuse buffer)
-                double s = 0.0;
-                for (int b = lane; b < c; b += 32) s += Hs[(size_t)a * c + b] * dy[b];
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                if (lane == 0) Ka[a] = s;
-            }
+            hs_matvec(dy, Ka);                                    // Ka <- Hs dy (reuse buffer)
             __syncthreads();
             const double gd = dot_c(grad, dy), q2 = dot_c(dy, Ka);
             double lin = 0.0;
@@ -1231,7 +1284,8 @@ inline int sdp_solve_planned(const sysid_sdp_desc& d, const double* dplan, const
     const size_t vec = 10 * (size_t)prm.c + 6 * (size_t)prm.m + 40 * (size_t)prm.L + (size_t)prm.c + 32;
     const size_t smem = big ? sizeof(double) * (vec + 8 * (size_t)prm.c + 80)
                             : sizeof(double) * ((size_t)prm.c * (prm.c + 1) + vec - (size_t)prm.c +
-                                                ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES));
+                                                ((4 * (size_t)prm.m + 8 * (size_t)prm.L >= (size_t)SDP_PAN_DOUBLES) ? 0 : (size_t)SDP_PAN_DOUBLES) +
+                                                ((size_t)SDP_PAN_DOUBLES > 4 * (size_t)prm.c ? (size_t)SDP_PAN_DOUBLES - 4 * (size_t)prm.c : 0));   // second panel buffer
     cudaError_t e = big ? cudaFuncSetAttribute(sdp_alm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                         : cudaFuncSetAttribute(sdp_alm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { snprintf(msg, msglen, "smem opt-in (%zu B) failed: %s", smem, cudaGetErrorString(e)); return SYSID_ERR_CUDA; }
