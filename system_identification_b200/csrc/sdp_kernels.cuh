@@ -840,23 +840,23 @@ sdp_alm_kernel(const SdpParams prm, const double* __restrict__ plan, const doubl
 #else
 #define SDP_TICK(k)
 #endif
-    // penalty schedule: sigma x4 after EVERY outer iteration up to 1e7.  The textbook rule (x10 when the KKT residual fell by less than
-    // 4x, cap 1e6 -- round 1) leaves the tail of the solve at sigma = 1e6, where the multiplier iteration contracts by 0.22 per outer
-    // iteration, just under its own threshold: 59 / 62 / 56 / 29 Newton steps on the G1 (250 k samples, two torque seeds; 20 k) and
-    // Spot problems against 46 / 46 / 46 / 26 with this one (tools/sdp_sigma_sweep.py; x10 or a cap of 3e6 are erratic, 45-88 steps;
-    // at 1e8 the inner iteration stalls on the rounding noise of sigma A y).  Same optima (1e-7 relative).
+    // penalty schedule: sigma x10 when the KKT residual fell by less than 4x, cap 1e6 (the textbook rule).  Measured alternatives
+    // (tools/sdp_sigma_sweep.py, profiles/sdp_sigma_sweep_r02g.json; overrides SYSID_SDP_SIGMA_GROWTH / _CAP / _THRESH / SIGMA0): x4 after
+    // EVERY outer iteration up to 1e7 needs 49 / 48 / 49 / 26 Newton steps instead of 59 / 62 / 56 / 29 on the sweep's G1 and Spot problems
+    // but 57 / 65 / 64 instead of 56 / 58 / 56 on the 1 M-sample logs of bench.py at 2 / 4 / 8 ranks -- no robust gain, not adopted; x10 every
+    // iteration or caps of 3e6 / 3e7 are erratic (37-88 steps); at 1e8 the inner iteration stalls on the rounding noise of sigma A y.
 #ifndef SYSID_SDP_SIGMA_GROWTH
-#define SYSID_SDP_SIGMA_GROWTH 4.0
-#define SYSID_SDP_SIGMA_CAP 1e7
-#define SYSID_SDP_SIGMA_THRESH 0.0
+#define SYSID_SDP_SIGMA_GROWTH 10.0
+#define SYSID_SDP_SIGMA_CAP 1e6
+#define SYSID_SDP_SIGMA_THRESH 0.25
 #endif
 #ifndef SYSID_SDP_SIGMA0
 #define SYSID_SDP_SIGMA0 1e4        // initial penalty: 1e4 needs ~20 % fewer Newton steps than 1 on the Solo / Spot / G1 problems (same optima)
 #endif
     double sigma = prm.sigma0;
     // solves of a warm-start chain (the pre-solves behind the host stream, which leave a record, and the solve a VALID record starts)
-    // keep the round-1 schedule: a record left at sigma = 1e7 costs the next solve of the chain more Newton steps than the cold
-    // solve saves (measured on the 1 M-sample G1 log: 24 final steps instead of 13)
+    // always run the default schedule, whatever the overrides say: a record left at sigma = 1e7 costs the next solve of the chain
+    // more Newton steps than a faster cold solve saves (measured on the 1 M-sample G1 log: 24 final steps instead of 13)
     double sg_growth = prm.sigma_growth, sg_cap = prm.sigma_cap, sg_thresh = prm.sigma_thresh;
     if (warm_out_all != nullptr) { sg_growth = 10.0; sg_cap = 1e6; sg_thresh = 0.25; }
     const double eps = fmax(10.0 * prm.tol, 1e-11);
