@@ -333,6 +333,134 @@ big_syrk_kernel(const double* __restrict__ R, long long rows, double sign, doubl
     }
 }
 
+// Row-class version of the SYRK (round 2, end): the rows of a chunk are taken CLASS BY CLASS -- class v = row v of every sample (R is
+// [ns][rps][BCW]) -- because the support of a row of Ytilde is structural: joint row v holds the ten columns of every body below its
+// joint, its own two friction columns and the torque column, nothing else.  masks.m[v] has one bit per 8-column tile that row v can
+// touch: a CTA skips the classes that miss one of its two 64-column blocks (G1-29dof: 322 of 735 class x block pairs remain), a warp
+// skips the 8 x 8 tiles whose A- or B-side tile is structurally zero (16 % of the DMMAs remain).  Panels (32 samples of one class)
+// arrive through a three-stage cp.async ring in shared memory: two are in flight while one is contracted, one barrier per panel.
+// Fixed order: bit-reproducible.
+struct RowMasks { unsigned long long m[BV]; };
+constexpr int SY_PF = SY_ROWS * SY_BLK / 2 / SY_THREADS;        // 16-byte copies per thread and side of a panel (4)
+constexpr int SY_STAGES = 3;                                    // panels in flight per CTA (cp.async ring in shared memory)
+constexpr int SY_STAGE_DOUBLES = 2 * SY_ROWS * SY_LD;
+constexpr size_t SY_ROWS_SMEM = sizeof(double) * SY_STAGES * SY_STAGE_DOUBLES;      // 104 448 B: two CTAs per SM
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(SY_THREADS, 2)
+big_syrk_rows_kernel(const double* __restrict__ R, int ns, int rps, const __grid_constant__ RowMasks masks, double sign,
+                     double* __restrict__ partial) {
+    extern __shared__ __align__(16) double sy_sm[];
+    __shared__ int vlist[BV];
+    __shared__ int s_nact;
+    const int blk = blockIdx.x, nz = gridDim.y, z = blockIdx.y;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
+    const int bj = blk - bi * (bi + 1) / 2;
+    const bool diag = (bi == bj);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
+    int per = (ns + nz - 1) / nz;
+    per = (per + SY_ROWS - 1) / SY_ROWS * SY_ROWS;
+    const int s0 = z * per, s1 = min(ns, s0 + per);
+    if (threadIdx.x == 0) {
+        int n = 0;
+        for (int v = 0; v < rps; ++v) {
+            const unsigned long long m = masks.m[v];
+            if (((m >> (8 * bi)) & 0xffull) && ((m >> (8 * bj)) & 0xffull)) vlist[n++] = v;
+        }
+        s_nact = n;
+    }
+    __syncthreads();
+    const int npan = (s1 > s0) ? (s1 - s0 + SY_ROWS - 1) / SY_ROWS : 0;
+    const int total = s_nact * npan;
+    double acc[8][2];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    // panel p = 32 samples of class vlist[p / npan] -> ring stage p % SY_STAGES; always commits a group (possibly empty) so that
+    // the wait below counts the same for every thread and every p
+    auto issue = [&](int p) {
+        if (p < total) {
+            const int v = vlist[p / npan], sb = s0 + SY_ROWS * (p % npan);
+            double* PA = sy_sm + (p % SY_STAGES) * SY_STAGE_DOUBLES;
+            double* PB = PA + SY_ROWS * SY_LD;
+#pragma unroll
+            for (int i = 0; i < SY_PF; ++i) {
+                const int idx = threadIdx.x + SY_THREADS * i, rr = idx >> 5, c2 = idx & 31;
+                const int smp = sb + rr;
+                if (smp < s1) {
+                    const double* src = R + ((size_t)smp * rps + v) * BCW;
+                    cp_async16(PA + rr * SY_LD + 2 * c2, src + bi * SY_BLK + 2 * c2);
+                    if (!diag) cp_async16(PB + rr * SY_LD + 2 * c2, src + bj * SY_BLK + 2 * c2);
+                } else {
+                    *reinterpret_cast<double2*>(PA + rr * SY_LD + 2 * c2) = make_double2(0.0, 0.0);
+                    if (!diag) *reinterpret_cast<double2*>(PB + rr * SY_LD + 2 * c2) = make_double2(0.0, 0.0);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int p = 0; p < SY_STAGES - 1; ++p) issue(p);
+    for (int p = 0; p < total; ++p) {
+        cp_async_wait<SY_STAGES - 2>();                    // this thread's copies of panel p have landed ...
+        __syncthreads();                                   // ... and everybody's; stage (p - 1) % SY_STAGES is free again
+        issue(p + SY_STAGES - 1);
+        const double* PA = sy_sm + (p % SY_STAGES) * SY_STAGE_DOUBLES;
+        const double* Bs = diag ? PA : PA + SY_ROWS * SY_LD;
+        const unsigned long long m = masks.m[vlist[p / npan]];
+        const unsigned ma = (unsigned)((m >> (8 * bi)) & 0xffull), mb = (unsigned)((m >> (8 * bj)) & 0xffull);
+        if ((ma >> warp) & 1u) {                           // warp-uniform: this warp's eight output rows see the class at all
+#pragma unroll
+            for (int ks = 0; ks < SY_ROWS / 4; ++ks) {
+                const double a = PA[(4 * ks + kk) * SY_LD + 8 * warp + r];
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if ((mb >> t) & 1u) dmma884(acc[t][0], acc[t][1], a, Bs[(4 * ks + kk) * SY_LD + 8 * t + r]);
+            }
+        }
+    }
+    cp_async_wait<0>();
+    double* out = partial + ((size_t)z * SY_NBLK + blk) * SY_BLK * SY_BLK;
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+        double2* q = reinterpret_cast<double2*>(out + (8 * warp + r) * SY_BLK + 8 * t + 2 * kk);
+        double2 v2 = *q;
+        v2.x += sign * acc[t][0]; v2.y += sign * acc[t][1];      // sign = +-1: exact
+        *q = v2;
+    }
+}
+
+// host: structural tile masks of the rows of Ytilde (see big_rows_kernel / big_tail_kernel for who writes what)
+inline RowMasks big_row_masks(const BigModel& M, int friction) {
+    RowMasks k;
+    for (int v = 0; v < BV; ++v) k.m[v] = 0ull;
+    auto set = [&](int v, int col) { k.m[v] |= 1ull << (col / 8); };
+    for (int i = 1; i < M.njoints; ++i)                        // body i: its ten columns in the rows of every joint above it
+        for (int j = i; j > 0; j = M.parent[j]) {
+            const int iv = M.idx_v[j], nr = (M.jtype[j] == JT_FF) ? 6 : 1;
+            for (int rr = 0; rr < nr; ++rr)
+                for (int c = 0; c < 10; ++c) set(iv + rr, 10 * (i - 1) + c);
+        }
+    const int np = M.nparams, ctau = np + (friction ? 2 * M.nd : 0);
+    for (int kq = 0; kq < M.nd; ++kq) {
+        if (friction) { set(6 + kq, np + kq); set(6 + kq, np + M.nd + kq); }
+        set(6 + kq, ctau);
+    }
+    return k;
+}
+// Z = W Ytilde: dense rows, but only 3 n_ee of the BMR row slots of a sample are ever used (the rest stay zero)
+inline RowMasks big_z_masks(const BigModel& M) {
+    RowMasks k;
+    for (int v = 0; v < BV; ++v) k.m[v] = (v < 3 * M.n_ee) ? (1ull << (BCW / 8)) - 1ull : 0ull;
+    return k;
+}
+
 // stats = [G (c x c) | r (c) | s | n] += sum_z partial (fixed order); element (i, j), i >= j, of the augmented (c+1) x (c+1) Gram
 __global__ void big_reduce_kernel(const double* __restrict__ partial, int nz, int c, double n_add, double* __restrict__ stats) {
     const int ca = c + 1, total = ca * (ca + 1) / 2;
