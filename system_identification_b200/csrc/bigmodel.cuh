@@ -273,19 +273,28 @@ __global__ void big_contact_kernel(const __grid_constant__ BigModel M, const Sam
     if (lost && rankloss) atomicAdd(rankloss, 1);
 }
 
-// Z[s][k][col] = sum_r W[s][k][r] Ytilde[s][r][col]
+// Z[s][k][col] = sum_r W[s][k][r] Ytilde[s][r][col]: thread per (sample, column), all contact rows of the sample at once -- the column
+// of Ytilde is read once instead of once per contact row (the W rows are warp-wide broadcasts); same summation order per element
 __global__ void big_zrows_kernel(const __grid_constant__ BigModel M, int ns, const double* __restrict__ Yt, const double* __restrict__ W,
                                  const int* __restrict__ m3, double* __restrict__ Z) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)ns * BMR * BCW) return;
-    const int col = (int)(e % BCW), k = (int)((e / BCW) % BMR), s = (int)(e / ((long long)BCW * BMR));
-    double t = 0.0;
-    if (k < m3[s]) {
-        const double* w = W + ((size_t)s * BMR + k) * BV;
+    if (e >= (long long)ns * BCW) return;
+    const int col = (int)(e % BCW), s = (int)(e / BCW);
+    const int m = m3[s];
+    double acc[BMR];
+#pragma unroll
+    for (int k = 0; k < BMR; ++k) acc[k] = 0.0;
+    if (m > 0) {
+        const double* w = W + (size_t)s * BMR * BV;
         const double* y = Yt + (size_t)s * M.nv * BCW + col;
-        for (int r = 0; r < M.nv; ++r) t = fma(w[r], y[(size_t)r * BCW], t);
+        for (int r = 0; r < M.nv; ++r) {
+            const double yv = y[(size_t)r * BCW];
+#pragma unroll
+            for (int k = 0; k < BMR; ++k) if (k < m) acc[k] = fma(w[k * BV + r], yv, acc[k]);
+        }
     }
-    Z[e] = t;
+#pragma unroll
+    for (int k = 0; k < BMR; ++k) Z[((size_t)s * BMR + k) * BCW + col] = acc[k];
 }
 
 // ---------------------------------------------------------------------------------------------- syrk
@@ -547,7 +556,7 @@ __global__ void big_err_final_kernel(int nd, long long N, const double* __restri
 }
 
 // chunk workspace layout (doubles): kin | Ytilde | Z | W | partial | e2 / sums; ints: m3 | rankloss
-constexpr int BIG_CHUNK = 2048;
+constexpr int BIG_CHUNK = 8192;        // samples per pass: the thread-per-sample kernels (kin, contact) are latency-bound, a chunk must fill the SMs
 constexpr int BIG_NZ = 16;
 struct BigWs {
     double* kin; double* Yt; double* Z; double* W; double* partial; double* e2; int* m3; int* rankloss;

@@ -422,8 +422,8 @@ static int big_chunk_rows(const sysid_model* model, const SampleIO& io, long lon
     big::big_tail_kernel<<<(ns * B.nd + 127) / 128, 128, 0, st>>>(B, io, base, ns, friction, w.Yt);
     if (contacts) {
         big::big_contact_kernel<<<(ns + 63) / 64, 64, 0, st>>>(B, io, base, ns, w.kin, w.W, w.m3, w.rankloss);
-        const long long tot = (long long)ns * big::BMR * big::BCW;
-        big::big_zrows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, ns, w.Yt, w.W, w.m3, w.Z);
+        const long long tot = (long long)ns * big::BCW;
+        big::big_zrows_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(B, ns, w.Yt, w.W, w.m3, w.Z);
     }
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;

@@ -37,7 +37,7 @@ def test_g1_29dof_regressor_projector_blocks_vs_oracle():
 
 def test_g1_29dof_gram_and_rmse_vs_oracle_twin():
     from oracle.cbuild import COracle
-    N, c = 5000, 358                                                          # three chunks of the large-model path, ragged tail
+    N, c = 20000, 358                                                         # three chunks (8 192 samples) of the large-model path, ragged tail
     flat, data, dm, dev = _setup(N, seed=8)
     co = COracle(H.oracle_tree(flat), flat.ee_names)
     so, _ = co.gram(*data)
