@@ -294,55 +294,12 @@ __global__ void big_zrows_kernel(const __grid_constant__ BigModel M, int ns, con
         }
     }
 #pragma unroll
-    for (int k = 0; k < BMR; ++k) Z[((size_t)s * BMR + k) * BCW + col] = acc[k];
+    for (int k = 0; k < BMR; ++k) if (k < 3 * M.n_ee) Z[((size_t)s * BMR + k) * BCW + col] = acc[k];      // the other slots are never read
 }
 
 // ---------------------------------------------------------------------------------------------- syrk
-// partial[z][blk][64][64] += sign * R^T R over this CTA's slice of the rows of R (rows x BCW), blk = lower-triangular 64 x 64
-// output block (bi >= bj).  Warp w owns tile row w of the block (8 tiles); operands staged through shared memory 32 rows at a
-// time with pitch 68 (== 4 mod 16: conflict-free DMMA fragment loads).
-__global__ void __launch_bounds__(SY_THREADS)
-big_syrk_kernel(const double* __restrict__ R, long long rows, double sign, double* __restrict__ partial) {
-    __shared__ __align__(16) double PA[SY_ROWS * SY_LD], PB[SY_ROWS * SY_LD];
-    const int blk = blockIdx.x, nz = gridDim.y, z = blockIdx.y;
-    int bi = 0;
-    while ((bi + 1) * (bi + 2) / 2 <= blk) ++bi;
-    const int bj = blk - bi * (bi + 1) / 2;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, kk = lane & 3;
-    long long per = (rows + nz - 1) / nz;
-    per = (per + SY_ROWS - 1) / SY_ROWS * SY_ROWS;
-    const long long r0 = (long long)z * per, r1 = min(rows, r0 + per);
-    double acc[8][2];
-#pragma unroll
-    for (int t = 0; t < 8; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
-    for (long long rb = r0; rb < r1; rb += SY_ROWS) {
-        for (int e = threadIdx.x; e < SY_ROWS * SY_BLK; e += SY_THREADS) {
-            const int rr = e / SY_BLK, cc = e % SY_BLK;
-            const long long gr = rb + rr;
-            const double* src = R + (size_t)gr * BCW;
-            PA[rr * SY_LD + cc] = (gr < r1) ? sign * src[bi * SY_BLK + cc] : 0.0;
-            PB[rr * SY_LD + cc] = (gr < r1) ? src[bj * SY_BLK + cc] : 0.0;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int ks = 0; ks < SY_ROWS / 4; ++ks) {
-            const double a = PA[(4 * ks + kk) * SY_LD + 8 * warp + r];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) dmma884(acc[t][0], acc[t][1], a, PB[(4 * ks + kk) * SY_LD + 8 * t + r]);
-        }
-        __syncthreads();
-    }
-    double* out = partial + ((size_t)z * SY_NBLK + blk) * SY_BLK * SY_BLK;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        double2* p = reinterpret_cast<double2*>(out + (8 * warp + r) * SY_BLK + 8 * t + 2 * kk);
-        double2 v = *p;
-        v.x += acc[t][0]; v.y += acc[t][1];
-        *p = v;
-    }
-}
-
-// Row-class version of the SYRK (round 2, end): the rows of a chunk are taken CLASS BY CLASS -- class v = row v of every sample (R is
+// partial[z][blk][64][64] += sign * R^T R, blk = lower-triangular 64 x 64 output block, z = slice of the chunk's samples.
+// The rows of a chunk are taken CLASS BY CLASS -- class v = row v of every sample (R is
 // [ns][rps][BCW]) -- because the support of a row of Ytilde is structural: joint row v holds the ten columns of every body below its
 // joint, its own two friction columns and the torque column, nothing else.  masks.m[v] has one bit per 8-column tile that row v can
 // touch: a CTA skips the classes that miss one of its two 64-column blocks (G1-29dof: 322 of 735 class x block pairs remain), a warp
@@ -398,17 +355,21 @@ big_syrk_rows_kernel(const double* __restrict__ R, int ns, int rps, const __grid
             const int v = vlist[p / npan], sb = s0 + SY_ROWS * (p % npan);
             double* PA = sy_sm + (p % SY_STAGES) * SY_STAGE_DOUBLES;
             double* PB = PA + SY_ROWS * SY_LD;
+            const unsigned long long m = masks.m[v];
+            const unsigned ma = (unsigned)((m >> (8 * bi)) & 0xffull), mb = (unsigned)((m >> (8 * bj)) & 0xffull);
 #pragma unroll
             for (int i = 0; i < SY_PF; ++i) {
                 const int idx = threadIdx.x + SY_THREADS * i, rr = idx >> 5, c2 = idx & 31;
                 const int smp = sb + rr;
+                // only the 8-column tiles the class can touch are moved (the contraction below never reads the others)
+                const bool wa = (ma >> (c2 >> 2)) & 1u, wb = !diag && ((mb >> (c2 >> 2)) & 1u);
                 if (smp < s1) {
                     const double* src = R + ((size_t)smp * rps + v) * BCW;
-                    cp_async16(PA + rr * SY_LD + 2 * c2, src + bi * SY_BLK + 2 * c2);
-                    if (!diag) cp_async16(PB + rr * SY_LD + 2 * c2, src + bj * SY_BLK + 2 * c2);
+                    if (wa) cp_async16(PA + rr * SY_LD + 2 * c2, src + bi * SY_BLK + 2 * c2);
+                    if (wb) cp_async16(PB + rr * SY_LD + 2 * c2, src + bj * SY_BLK + 2 * c2);
                 } else {
-                    *reinterpret_cast<double2*>(PA + rr * SY_LD + 2 * c2) = make_double2(0.0, 0.0);
-                    if (!diag) *reinterpret_cast<double2*>(PB + rr * SY_LD + 2 * c2) = make_double2(0.0, 0.0);
+                    if (wa) *reinterpret_cast<double2*>(PA + rr * SY_LD + 2 * c2) = make_double2(0.0, 0.0);
+                    if (wb) *reinterpret_cast<double2*>(PB + rr * SY_LD + 2 * c2) = make_double2(0.0, 0.0);
                 }
             }
         }
@@ -557,7 +518,7 @@ __global__ void big_err_final_kernel(int nd, long long N, const double* __restri
 
 // chunk workspace layout (doubles): kin | Ytilde | Z | W | partial | e2 / sums; ints: m3 | rankloss
 constexpr int BIG_CHUNK = 8192;        // samples per pass: the thread-per-sample kernels (kin, contact) are latency-bound, a chunk must fill the SMs
-constexpr int BIG_NZ = 16;
+constexpr int BIG_NZ = 64;            // sample slices per output block: 1 344 CTAs of uneven weight (6 .. 33 row classes) balance over 296 slots
 struct BigWs {
     double* kin; double* Yt; double* Z; double* W; double* partial; double* e2; int* m3; int* rankloss;
     size_t bytes;

@@ -521,19 +521,13 @@ static int big_gram(const sysid_model* model, const SampleIO& io, int64_t N, int
     CUDA_TRY(cudaMemsetAsync(w.rankloss, 0, sizeof(int) * 4, st));
     const big::RowMasks ymasks = big::big_row_masks(B, friction), zmasks = big::big_z_masks(B);
     CUDA_TRY(cudaFuncSetAttribute(big::big_syrk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big::SY_ROWS_SMEM));
-    static const bool legacy_syrk = [] { const char* e = std::getenv("SYSID_BIG_SYRK_LEGACY"); return e && std::atoi(e) != 0; }();
     for (int64_t lo = 0; lo < N; lo += big::BIG_CHUNK) {
         const int ns = (int)((N - lo < big::BIG_CHUNK) ? (N - lo) : big::BIG_CHUNK);
         int rc = big_chunk_rows(model, io, lo, ns, friction, true, w, st);
         if (rc != SYSID_OK) return rc;
-        if (legacy_syrk) {                             // diagnostic (SYSID_BIG_SYRK_LEGACY=1): the dense row-major SYRK of the first version
-            big::big_syrk_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, 0, st>>>(w.Yt, (long long)ns * B.nv, 1.0, w.partial);
-            big::big_syrk_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, 0, st>>>(w.Z, (long long)ns * big::BMR, -1.0, w.partial);
-        } else {
-            // Ytilde^T Ytilde class by class on the structural masks of its rows, then - Z^T Z (dense rows)
-            big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, st>>>(w.Yt, ns, B.nv, ymasks, 1.0, w.partial);
-            big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, st>>>(w.Z, ns, big::BMR, zmasks, -1.0, w.partial);
-        }
+        // Ytilde^T Ytilde class by class on the structural masks of its rows, then - Z^T Z (dense rows, 3 n_ee slots per sample)
+        big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, st>>>(w.Yt, ns, B.nv, ymasks, 1.0, w.partial);
+        big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, st>>>(w.Z, ns, big::BMR, zmasks, -1.0, w.partial);
         CUDA_TRY(cudaGetLastError());
     }
     const int total = (c + 1) * (c + 2) / 2;
