@@ -26,6 +26,7 @@ jobs = [
     ("spot", "spot_description/spot.urdf", os.path.join(FILES, "spot_description/spot_config.yaml"), SPOT_FALLBACK, False),
     ("g1_12dof", "g1_description/g1_12dof.urdf", os.path.join(OUT, "g1_12dof_config.yaml"), G1_FALLBACK, True),
     ("g1_29dof", "g1_description/g1_29dof.urdf", os.path.join(OUT, "g1_29dof_config.yaml"), G1_FALLBACK, True),
+    ("g1_29dof_lock_waist", "g1_description/g1_29dof_lock_waist.urdf", os.path.join(OUT, "g1_29dof_config.yaml"), G1_FALLBACK, True),
 ]
 for name, urdf, cfg, fb, merged in jobs:
     with open(cfg) as f:
