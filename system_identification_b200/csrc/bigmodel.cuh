@@ -41,6 +41,9 @@ struct BigModel {
     double ee_off[BEE][3];
 };
 
+// one bit per 8-column tile of a row of Ytilde that the row can touch at all (big_row_masks, below)
+struct RowMasks { unsigned long long m[BV]; };
+
 __device__ __forceinline__ void mat3mul(const double* A, const double* B, double* C) {
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -275,8 +278,8 @@ __global__ void big_contact_kernel(const __grid_constant__ BigModel M, const Sam
 
 // Z[s][k][col] = sum_r W[s][k][r] Ytilde[s][r][col]: thread per (sample, column), all contact rows of the sample at once -- the column
 // of Ytilde is read once instead of once per contact row (the W rows are warp-wide broadcasts); same summation order per element
-__global__ void big_zrows_kernel(const __grid_constant__ BigModel M, int ns, const double* __restrict__ Yt, const double* __restrict__ W,
-                                 const int* __restrict__ m3, double* __restrict__ Z) {
+__global__ void big_zrows_kernel(const __grid_constant__ BigModel M, const __grid_constant__ RowMasks masks, int ns,
+                                 const double* __restrict__ Yt, const double* __restrict__ W, const int* __restrict__ m3, double* __restrict__ Z) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)ns * BCW) return;
     const int col = (int)(e % BCW), s = (int)(e / BCW);
@@ -288,6 +291,7 @@ __global__ void big_zrows_kernel(const __grid_constant__ BigModel M, int ns, con
         const double* w = W + (size_t)s * BMR * BV;
         const double* y = Yt + (size_t)s * M.nv * BCW + col;
         for (int r = 0; r < M.nv; ++r) {
+            if (!((masks.m[r] >> (col >> 3)) & 1ull)) continue;        // structurally zero in this column's tile: an exact no-op skipped
             const double yv = y[(size_t)r * BCW];
 #pragma unroll
             for (int k = 0; k < BMR; ++k) if (k < m) acc[k] = fma(w[k * BV + r], yv, acc[k]);
@@ -306,7 +310,6 @@ __global__ void big_zrows_kernel(const __grid_constant__ BigModel M, int ns, con
 // skips the 8 x 8 tiles whose A- or B-side tile is structurally zero (16 % of the DMMAs remain).  Panels (32 samples of one class)
 // arrive through a three-stage cp.async ring in shared memory: two are in flight while one is contracted, one barrier per panel.
 // Fixed order: bit-reproducible.
-struct RowMasks { unsigned long long m[BV]; };
 constexpr int SY_PF = SY_ROWS * SY_BLK / 2 / SY_THREADS;        // 16-byte copies per thread and side of a panel (4)
 constexpr int SY_STAGES = 3;                                    // panels in flight per CTA (cp.async ring in shared memory)
 constexpr int SY_STAGE_DOUBLES = 2 * SY_ROWS * SY_LD;

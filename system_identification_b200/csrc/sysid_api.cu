@@ -423,7 +423,7 @@ static int big_chunk_rows(const sysid_model* model, const SampleIO& io, long lon
     if (contacts) {
         big::big_contact_kernel<<<(ns + 63) / 64, 64, 0, st>>>(B, io, base, ns, w.kin, w.W, w.m3, w.rankloss);
         const long long tot = (long long)ns * big::BCW;
-        big::big_zrows_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(B, ns, w.Yt, w.W, w.m3, w.Z);
+        big::big_zrows_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(B, big::big_row_masks(B, friction), ns, w.Yt, w.W, w.m3, w.Z);
     }
     CUDA_TRY(cudaGetLastError());
     return SYSID_OK;
