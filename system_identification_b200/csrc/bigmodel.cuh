@@ -524,9 +524,12 @@ constexpr int BIG_CHUNK = 8192;        // samples per pass: the thread-per-sampl
 constexpr int BIG_NZ = 64;            // sample slices per output block: 1 344 CTAs of uneven weight (6 .. 33 row classes) balance over 296 slots
 struct BigWs {
     double* kin; double* Yt; double* Z; double* W; double* partial; double* e2; int* m3; int* rankloss;
+    double* kin2; double* Yt2; double* Z2; double* W2; int* m32;       // second set of the per-chunk buffers (== the first when absent)
     size_t bytes;
 };
-inline BigWs big_workspace(const BigModel& M, void* base) {
+// two = true: a second set of the per-chunk buffers (kin, Ytilde, Z, W, m3) behind the first, for the statistics pass that builds the
+// rows of chunk i + 1 while the SYRK of chunk i runs on another stream; big_workspace_alt() returns the view on that set
+inline BigWs big_workspace(const BigModel& M, void* base, bool two = false) {
     BigWs w;
     char* p = (char*)base;
     auto take = [&](size_t n) { char* q = p; p += (n + 255) & ~(size_t)255; return q; };
@@ -538,8 +541,21 @@ inline BigWs big_workspace(const BigModel& M, void* base) {
     w.e2 = (double*)take(sizeof(double) * ((size_t)BIG_CHUNK * BV + BV));
     w.m3 = (int*)take(sizeof(int) * BIG_CHUNK);
     w.rankloss = (int*)take(sizeof(int) * 4);
+    w.kin2 = w.kin; w.Yt2 = w.Yt; w.Z2 = w.Z; w.W2 = w.W; w.m32 = w.m3;
+    if (two) {
+        w.kin2 = (double*)take(sizeof(double) * BIG_CHUNK * (size_t)M.njoints * KIN);
+        w.Yt2 = (double*)take(sizeof(double) * BIG_CHUNK * (size_t)M.nv * BCW);
+        w.Z2 = (double*)take(sizeof(double) * BIG_CHUNK * (size_t)BMR * BCW);
+        w.W2 = (double*)take(sizeof(double) * BIG_CHUNK * (size_t)BMR * BV);
+        w.m32 = (int*)take(sizeof(int) * BIG_CHUNK);
+    }
     w.bytes = (size_t)(p - (char*)base);
     return w;
+}
+inline BigWs big_workspace_alt(const BigWs& w) {
+    BigWs a = w;
+    a.kin = w.kin2; a.Yt = w.Yt2; a.Z = w.Z2; a.W = w.W2; a.m3 = w.m32;
+    return a;
 }
 
 }  // namespace big

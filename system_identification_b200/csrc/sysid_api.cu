@@ -429,12 +429,12 @@ static int big_chunk_rows(const sysid_model* model, const SampleIO& io, long lon
     return SYSID_OK;
 }
 
-static size_t big_workspace_bytes(const sysid_model* model) { return big::big_workspace(model->bm, nullptr).bytes + 256; }
+static size_t big_workspace_bytes(const sysid_model* model) { return big::big_workspace(model->bm, nullptr, true).bytes + 256; }
 
 // per-sample outputs of the large-model path need scratch the small-model ABI has no argument for: stream-ordered allocation
 static int big_batch(const sysid_model* model, const SampleIO& io, int64_t N, int friction, double* Y, double* A, double* b, double* P, cudaStream_t st) {
     void* buf = nullptr;
-    CUDA_TRY(cudaMallocAsync(&buf, big_workspace_bytes(model), st));
+    CUDA_TRY(cudaMallocAsync(&buf, big::big_workspace(model->bm, nullptr).bytes + 256, st));
     const big::BigWs w = big::big_workspace(model->bm, buf);
     const big::BigModel& B = model->bm;
     const int ncols = B.nparams + (friction ? 2 * B.nd : 0);
@@ -515,21 +515,47 @@ static int big_gram(const sysid_model* model, const SampleIO& io, int64_t N, int
     if (io.weights) return fail(SYSID_ERR_UNSUPPORTED, "per-sample weights are not available on the large-model path");
     if (workspace_bytes < big_workspace_bytes(model)) return fail(SYSID_ERR_WORKSPACE, "workspace %zu B < %zu B", workspace_bytes, big_workspace_bytes(model));
     const big::BigModel& B = model->bm;
-    const big::BigWs w = big::big_workspace(B, (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255));
+    const big::BigWs w = big::big_workspace(B, (void*)(((uintptr_t)workspace + 255) & ~(uintptr_t)255), true);
+    const big::BigWs walt = big::big_workspace_alt(w);
     const int c = B.nparams + (friction ? 2 * B.nd : 0);
     CUDA_TRY(cudaMemsetAsync(w.partial, 0, sizeof(double) * (size_t)big::BIG_NZ * big::SY_NBLK * big::SY_BLK * big::SY_BLK, st));
     CUDA_TRY(cudaMemsetAsync(w.rankloss, 0, sizeof(int) * 4, st));
     const big::RowMasks ymasks = big::big_row_masks(B, friction), zmasks = big::big_z_masks(B);
     CUDA_TRY(cudaFuncSetAttribute(big::big_syrk_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big::SY_ROWS_SMEM));
-    for (int64_t lo = 0; lo < N; lo += big::BIG_CHUNK) {
+    // Two streams, two sets of chunk buffers: the rows of chunk i + 1 (thread-per-sample kernels bound by their own latency, which leave
+    // most of every SM idle) are built on `stream` while the two SYRK passes of chunk i run on an internal one; the SYRK launches stay
+    // in order on that stream (one partial buffer), the reduction waits for the last of them.
+    struct Side {
+        cudaStream_t s = nullptr; cudaEvent_t rows[2] = {nullptr, nullptr}, syrk[2] = {nullptr, nullptr};
+        bool create() {
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return false;
+            for (int k = 0; k < 2; ++k)
+                if (cudaEventCreateWithFlags(&rows[k], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&syrk[k], cudaEventDisableTiming) != cudaSuccess) return false;
+            return true;
+        }
+        ~Side() {           // destroying a stream / an event with work pending is deferred by the runtime until that work is done
+            for (int k = 0; k < 2; ++k) { if (rows[k]) cudaEventDestroy(rows[k]); if (syrk[k]) cudaEventDestroy(syrk[k]); }
+            if (s) cudaStreamDestroy(s);
+        }
+    } side;
+    if (!side.create()) return fail(SYSID_ERR_CUDA, "creating the internal stream of the large-model statistics failed");
+    int64_t i = 0;
+    for (int64_t lo = 0; lo < N; lo += big::BIG_CHUNK, ++i) {
         const int ns = (int)((N - lo < big::BIG_CHUNK) ? (N - lo) : big::BIG_CHUNK);
-        int rc = big_chunk_rows(model, io, lo, ns, friction, true, w, st);
+        const int k = (int)(i & 1);
+        const big::BigWs& wk = k ? walt : w;
+        if (i >= 2) CUDA_TRY(cudaStreamWaitEvent(st, side.syrk[k], 0));          // the SYRK of chunk i - 2 has consumed this set
+        int rc = big_chunk_rows(model, io, lo, ns, friction, true, wk, st);
         if (rc != SYSID_OK) return rc;
+        CUDA_TRY(cudaEventRecord(side.rows[k], st));
+        CUDA_TRY(cudaStreamWaitEvent(side.s, side.rows[k], 0));
         // Ytilde^T Ytilde class by class on the structural masks of its rows, then - Z^T Z (dense rows, 3 n_ee slots per sample)
-        big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, st>>>(w.Yt, ns, B.nv, ymasks, 1.0, w.partial);
-        big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, st>>>(w.Z, ns, big::BMR, zmasks, -1.0, w.partial);
+        big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, side.s>>>(wk.Yt, ns, B.nv, ymasks, 1.0, w.partial);
+        big::big_syrk_rows_kernel<<<dim3(big::SY_NBLK, big::BIG_NZ), big::SY_THREADS, big::SY_ROWS_SMEM, side.s>>>(wk.Z, ns, big::BMR, zmasks, -1.0, w.partial);
         CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(side.syrk[k], side.s));
     }
+    if (i > 0) CUDA_TRY(cudaStreamWaitEvent(st, side.syrk[(i - 1) & 1], 0));
     const int total = (c + 1) * (c + 2) / 2;
     big::big_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(w.partial, big::BIG_NZ, c, (double)B.nv * (double)N, stats);
     CUDA_TRY(cudaGetLastError());
