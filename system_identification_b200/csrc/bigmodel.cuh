@@ -3,7 +3,7 @@
 //
 // At c = 358 the Gram is 1 035 8x8 tiles -- 530 KB of accumulators, more than one SM's registers and tensor memory together --
 // so the single-CTA-per-SM fusion of gram_kernels.cuh does not carry over.  This path is the same mathematics in the plain
-// two-step form, chunk by chunk through HBM, every kernel generic in the tree size:
+// two-step form, chunk by chunk (8 192 samples) through HBM -- rows of chunk i + 1 beside the SYRK of chunk i -- generic in the tree size:
 //
 //   kin        thread per sample            forward kinematics: local / world placements, spatial velocity and gravity-biased
 //                                           acceleration of every joint (pinocchio's first loop)
@@ -11,8 +11,8 @@
 //   tail       thread per (sample, joint)   friction and torque columns of Ytilde
 //   contact    thread per sample            J_c (LOCAL_WORLD_ALIGNED, raw-quaternion R_b), S = J J^T, Cholesky with the pinv rank
 //                                           rule, W = L^-1 J_c  (P = I - W^T W)
-//   zrows      thread per (sample, k, col)  Z = W Ytilde  (<= 12 rows per sample)
-//   syrk       DMMA, 64 x 64 output blocks  partial Grams of  Ytilde^T Ytilde - Z^T Z  =  Ytilde^T P Ytilde  (P is a projector)
+//   zrows      thread per (sample, column)  Z = W Ytilde  (3 n_ee rows per sample at once; structurally zero rows of the column skipped)
+//   syrk_rows  DMMA, 64 x 64 output blocks  partial Grams of  Ytilde^T Ytilde - Z^T Z  =  Ytilde^T P Ytilde, rows class by class on tile masks
 //   reduce     thread per element           partials -> stats = [G | r | s | n], fixed summation order (bit-reproducible)
 //
 // The torque column rides along as column c, like in the fused kernel.  Not here (refused with SYSID_ERR_UNSUPPORTED for these
